@@ -1,0 +1,7 @@
+"""B200-native OpenPose keypoint extraction (body + hand) behind the reference's call API.
+
+    from isl_b200 import Body, Hand, util
+    candidate, subset = Body(model_path, 'body25')(frame)        # src/body.py:16,39
+    for x, y, w, is_left in util.handDetect(candidate, subset, frame):   # src/util.py:242
+        peaks = Hand(model_path)(frame[y:y+w, x:x+w, :])         # src/hand.py:16,24
+"""

@@ -1,0 +1,346 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution (see conv_umma.cuh for the data layout).
+//
+// Warp roles inside one 192-thread CTA (one output tile of <=128 pixels x n_tile channels):
+//   warp 0      : TMA producer  (one lane) - walks (tap, 64-channel block) and fills the smem ring
+//   warp 1      : TMEM owner + MMA issuer (one lane) - tcgen05.mma per K=16 slice, tcgen05.commit
+//                 releases ring slots and finally signals the epilogue
+//   warps 2..5  : epilogue - tcgen05.ld the accumulator (warp w may only touch TMEM lanes
+//                 32*(w%4)..+31), bias + ReLU/PReLU, bf16 pack, 16-byte stores into the NHWC slice;
+//                 network heads additionally (or only) store fp32.
+#include "conv_umma.cuh"
+
+#include <stdio.h>
+#include <string.h>
+
+#include "ptx.cuh"
+
+namespace islpose {
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr uint32_t kASlotBytes = 128 * 128;  // 128 pixel rows x 64 bf16
+constexpr int kMaxStages = 8;
+constexpr uint32_t kCtrlBytes = 256 + 2 * 256 * 4;  // barriers + bias + slope
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const ConvArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
+  uint8_t* const gbase = smem_raw + (base - raw);
+
+  const uint32_t sA0 = base;
+  const uint32_t sB0 = base + a.stages * kASlotBytes;
+  const uint32_t ctrl = sB0 + a.stages * a.b_stage_bytes;
+  uint8_t* const gctrl = gbase + (ctrl - base);
+  const uint32_t bar_full = ctrl;         // kMaxStages x 8 B
+  const uint32_t bar_empty = ctrl + 64;   // kMaxStages x 8 B
+  const uint32_t bar_accum = ctrl + 128;  // accumulator ready
+  const uint32_t tmem_slot = ctrl + 136;  // TMEM base address written by tcgen05.alloc
+  volatile uint32_t* const tmem_slot_g = reinterpret_cast<volatile uint32_t*>(gctrl + 136);
+  float* const s_bias = reinterpret_cast<float*>(gctrl + 256);
+  float* const s_slope = s_bias + 256;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // tile coordinates
+  const int t = blockIdx.x;
+  const int tx = t % a.tiles_x;
+  const int ty = (t / a.tiles_x) % a.tiles_y;
+  const int img = t / (a.tiles_x * a.tiles_y);
+  const int x0 = tx * a.bw;
+  const int y0 = ty * a.bh;
+  const int n0 = blockIdx.y * a.n_tile;
+
+  const int cblocks = (a.cin_k16 + 3) >> 2;
+  const int taps = a.ksize * a.ksize;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < a.stages; ++s) {
+      ptx::mbar_init(bar_full + 8 * s, 1);
+      ptx::mbar_init(bar_empty + 8 * s, 1);
+    }
+    ptx::mbar_init(bar_accum, 1);
+    ptx::mbar_fence_init();
+    ptx::prefetch_tensormap(&tmA);
+    ptx::prefetch_tensormap(&tmB);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, a.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  if (warp >= 2) {
+    for (int i = threadIdx.x - 64; i < a.n_tile; i += kThreads - 64) {
+      s_bias[i] = a.bias[n0 + i];
+      s_slope[i] = a.slope[n0 + i];
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_g;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const uint32_t tx_bytes = 128u * a.bw * a.bh + 128u * a.n_tile;
+      int it = 0;
+      for (int tap = 0; tap < taps; ++tap) {
+        const int ky = tap / a.ksize;
+        const int kx = tap - ky * a.ksize;
+        for (int cb = 0; cb < cblocks; ++cb, ++it) {
+          const int s = it % a.stages;
+          const uint32_t ph = (it / a.stages) & 1;
+          ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          ptx::mbar_arrive_expect_tx(bar_full + 8 * s, tx_bytes);
+          ptx::tma_load_4d(sA0 + s * kASlotBytes, &tmA, bar_full + 8 * s, cb * 64, x0 + kx - a.pad,
+                           y0 + ky - a.pad, img);
+          ptx::tma_load_3d(sB0 + s * a.b_stage_bytes, &tmB, bar_full + 8 * s, cb * 64, n0, tap);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = ptx::umma_idesc_bf16(128, a.n_tile);
+      int it = 0;
+      for (int tap = 0; tap < taps; ++tap) {
+        for (int cb = 0; cb < cblocks; ++cb, ++it) {
+          const int s = it % a.stages;
+          const uint32_t ph = (it / a.stages) & 1;
+          ptx::mbar_wait(bar_full + 8 * s, ph);
+          ptx::tc_fence_after();
+          const uint64_t da = ptx::umma_desc_sw128(sA0 + s * kASlotBytes);
+          const uint64_t db = ptx::umma_desc_sw128(sB0 + s * a.b_stage_bytes);
+          const int ksteps = min(4, a.cin_k16 - cb * 4);
+          for (int k = 0; k < ksteps; ++k) {
+            // +32 bytes (16 bf16) along K inside the 128-byte swizzle row = +2 in the >>4 address field
+            ptx::umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(bar_empty + 8 * s);  // slot reusable once these MMAs have read it
+        }
+      }
+      ptx::umma_commit(bar_accum);
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue
+    const int q = warp & 3;          // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;   // accumulator row = pixel index inside the tile box
+    const int py = row / a.bw;
+    const int px = row - py * a.bw;
+    const int x = x0 + px;
+    const int y = y0 + py;
+    const bool valid = (row < a.bw * a.bh) && (x < a.W) && (y < a.H);
+    const long long pix = (static_cast<long long>(img) * a.H + y) * a.W + x;
+
+    ptx::mbar_wait(bar_accum, 0);
+    ptx::tc_fence_after();
+
+    for (int c = 0; c < a.n_tile; c += 32) {
+      uint32_t r[32];
+      ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, r);
+      ptx::tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float acc = __uint_as_float(r[i]) + s_bias[c + i];
+        v[i] = acc > 0.f ? acc : acc * s_slope[c + i];
+      }
+      if (valid) {
+        if (a.out_bf16 != nullptr) {
+          __nv_bfloat16* dst = a.out_bf16 + pix * a.out_pix_stride + n0 + c;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (n0 + c + 8 * j < a.cout_store) {
+              uint4 pk;
+              __nv_bfloat162 h;
+              h = __floats2bfloat162_rn(v[8 * j + 0], v[8 * j + 1]);
+              pk.x = *reinterpret_cast<uint32_t*>(&h);
+              h = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+              pk.y = *reinterpret_cast<uint32_t*>(&h);
+              h = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
+              pk.z = *reinterpret_cast<uint32_t*>(&h);
+              h = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+              pk.w = *reinterpret_cast<uint32_t*>(&h);
+              *reinterpret_cast<uint4*>(dst + 8 * j) = pk;
+            }
+          }
+        }
+        if (a.out_f32 != nullptr) {
+          float* dst = a.out_f32 + pix * a.out_f32_pix_stride + n0 + c;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (n0 + c + i < a.cout) dst[i] = v[i];
+          }
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tmem_dealloc(tmem_base, a.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+  }
+  return fn;
+}
+
+int fail(char* err, int errlen, const char* fmt, long long a = 0, long long b = 0, long long c = 0) {
+  if (err != nullptr && errlen > 0) snprintf(err, errlen, fmt, a, b, c);
+  return 1;
+}
+
+}  // namespace
+
+int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
+  if (d.ksize != 1 && d.ksize != 3 && d.ksize != 7)
+    return fail(err, errlen, "conv: unsupported kernel size %lld", d.ksize);
+  if (d.in_c % 8 != 0 || d.in_cstride % 8 != 0 || d.in_c <= 0)
+    return fail(err, errlen, "conv: input slice channels (%lld) and stride (%lld) must be multiples of 8",
+                d.in_c, d.in_cstride);
+  if ((reinterpret_cast<uintptr_t>(d.in) & 15) != 0 || (reinterpret_cast<uintptr_t>(d.w) & 15) != 0)
+    return fail(err, errlen, "conv: input / weight pointers must be 16-byte aligned");
+  if (d.out_bf16 != nullptr &&
+      ((reinterpret_cast<uintptr_t>(d.out_bf16) & 15) != 0 || d.out_cstride % 8 != 0))
+    return fail(err, errlen, "conv: bf16 output slice must be 16-byte aligned (stride %lld)", d.out_cstride);
+  if (d.out_bf16 == nullptr && d.out_f32 == nullptr) return fail(err, errlen, "conv: no output given");
+  if (d.N <= 0 || d.H <= 0 || d.W <= 0 || d.cout <= 0) return fail(err, errlen, "conv: empty problem");
+  EncodeTiledFn encode = get_encode_tiled();
+  if (encode == nullptr) return fail(err, errlen, "conv: cuTensorMapEncodeTiled entry point not found");
+
+  ConvArgs& a = out->args;
+  memset(out, 0, sizeof(*out));
+  a.ksize = d.ksize;
+  a.pad = (d.ksize - 1) / 2;
+  a.cin_k16 = (d.in_c + 15) / 16;
+  a.H = d.H;
+  a.W = d.W;
+
+  // Pixel tile: the box (bw x bh) with bw*bh <= 128 that covers the image with the fewest tiles.
+  int bw = d.force_bw, bh = d.force_bh;
+  if (bw <= 0 || bh <= 0) {
+    long long best = -1;
+    for (int w = 1; w <= 128 && w <= d.W; ++w) {
+      int h = 128 / w;
+      if (h > d.H) h = d.H;
+      const long long tiles = static_cast<long long>((d.W + w - 1) / w) * ((d.H + h - 1) / h);
+      if (best < 0 || tiles < best || (tiles == best && w * h < bw * bh)) {
+        best = tiles;
+        bw = w;
+        bh = h;
+      }
+    }
+  }
+  if (bw * bh > 128 || bw > 256 || bh > 256) return fail(err, errlen, "conv: bad pixel tile %lldx%lld", bw, bh);
+  a.bw = bw;
+  a.bh = bh;
+  a.tiles_x = (d.W + bw - 1) / bw;
+  a.tiles_y = (d.H + bh - 1) / bh;
+  const long long m_tiles = static_cast<long long>(a.tiles_x) * a.tiles_y * d.N;
+
+  // Channel tile (UMMA N): multiple of 16, at most 256.
+  const int cout16 = (d.cout + 15) / 16 * 16;
+  int n_tile = d.force_n_tile;
+  if (n_tile <= 0) {
+    if (cout16 <= 256) {
+      n_tile = cout16;
+    } else {
+      n_tile = (m_tiles >= 148) ? 256 : 128;
+    }
+  }
+  if (n_tile % 16 != 0 || n_tile > 256 || n_tile < 16) return fail(err, errlen, "conv: bad channel tile %lld", n_tile);
+  const int n_tiles = (cout16 + n_tile - 1) / n_tile;
+  a.n_tile = n_tile;
+  a.cout = d.cout;
+  a.cout_store = (d.cout + 7) / 8 * 8;
+  a.b_stage_bytes = (static_cast<uint32_t>(n_tile) * 128u + 1023u) & ~1023u;
+  int cols = 32;
+  while (cols < (n_tile + 31) / 32 * 32) cols <<= 1;
+  a.tmem_cols = cols;
+
+  const uint32_t per_stage = kASlotBytes + a.b_stage_bytes;
+  int stages = d.force_stages;
+  if (stages <= 0) {
+    stages = static_cast<int>((200u * 1024u) / per_stage);
+    const int iters = d.ksize * d.ksize * ((a.cin_k16 + 3) / 4);
+    if (stages > iters) stages = iters;
+  }
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 1) stages = 1;
+  a.stages = stages;
+  out->smem_bytes = stages * per_stage + kCtrlBytes + 1024;
+  if (out->smem_bytes > 227u * 1024u) return fail(err, errlen, "conv: shared memory budget exceeded (%lld B)", out->smem_bytes);
+
+  a.out_bf16 = d.out_bf16;
+  a.out_pix_stride = d.out_cstride;
+  a.out_f32 = d.out_f32;
+  a.out_f32_pix_stride = d.out_f32_cstride;
+  a.bias = d.bias;
+  a.slope = d.slope;
+
+  // Tensor maps. A: (C, W, H, N) over the NHWC slice; B: (Cin, Cout, taps) over the packed weights.
+  {
+    cuuint64_t gdim[4] = {static_cast<cuuint64_t>(d.in_c), static_cast<cuuint64_t>(d.W),
+                          static_cast<cuuint64_t>(d.H), static_cast<cuuint64_t>(d.N)};
+    cuuint64_t gstr[3] = {static_cast<cuuint64_t>(d.in_cstride) * 2,
+                          static_cast<cuuint64_t>(d.in_cstride) * 2 * d.W,
+                          static_cast<cuuint64_t>(d.in_cstride) * 2 * d.W * d.H};
+    cuuint32_t box[4] = {64, static_cast<cuuint32_t>(bw), static_cast<cuuint32_t>(bh), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&out->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(d.in), gdim,
+                        gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(err, errlen, "conv: activation tensor map rejected (CUresult %lld)", r);
+  }
+  {
+    cuuint64_t gdim[3] = {static_cast<cuuint64_t>(d.in_c), static_cast<cuuint64_t>(d.cout),
+                          static_cast<cuuint64_t>(d.ksize * d.ksize)};
+    cuuint64_t gstr[2] = {static_cast<cuuint64_t>(d.in_c) * 2, static_cast<cuuint64_t>(d.in_c) * 2 * d.cout};
+    cuuint32_t box[3] = {64, static_cast<cuuint32_t>(n_tile), 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(&out->tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(d.w), gdim, gstr,
+                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(err, errlen, "conv: weight tensor map rejected (CUresult %lld)", r);
+  }
+
+  out->grid = dim3(static_cast<unsigned>(m_tiles), static_cast<unsigned>(n_tiles), 1);
+  out->flops = 2.0 * d.in_c * d.cout * d.ksize * d.ksize * static_cast<double>(d.H) * d.W * d.N;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return fail(err, errlen, "conv: cannot raise dynamic shared memory limit (%lld)", e);
+    attr_set = true;
+  }
+  return 0;
+}
+
+int conv_run(const ConvLaunch& l, cudaStream_t stream) {
+  conv_umma_kernel<<<l.grid, kThreads, l.smem_bytes, stream>>>(l.tmA, l.tmB, l.args);
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+}  // namespace islpose

@@ -1,0 +1,83 @@
+// Implicit-GEMM convolution for the OpenPose CPM stacks (reference: src/model.py:25-64 builds every
+// layer as nn.Conv2d(k in {1,3,7}, stride 1, pad (k-1)/2) + ReLU | PReLU | nothing).
+//
+// Data layout in HBM
+//   activations : NHWC bf16, one buffer may hold several concatenated tensors; a layer reads a channel
+//                 *slice* [c0, c0+Cin) of a buffer with `cstride` channels per pixel (this is how
+//                 torch.cat in model.py:177,190,199,308-324,397-405 disappears: producers write slices).
+//   weights     : bf16 [tap = ky*k+kx][Cout][Cin8]   (Cin8 = Cin rounded up to 8, zero padded)
+//   outputs     : bf16 slice of an NHWC buffer and/or fp32 NHWC [N,H,W,cout] (network heads)
+//
+// GEMM view: D[128 pixels, Cout-tile] = sum over (tap, 64-channel block) A[128 pixels, 64] * B[Cout-tile, 64]^T
+//   A tile = one TMA box (64 ch, bw, bh, 1 image) fetched at pixel offset (kx-pad, ky-pad): TMA zero-fills
+//            out-of-image pixels, which *is* the convolution's zero padding, and out-of-slice channels.
+//   B tile = one TMA box (64 ch, Cout-tile, 1 tap) of the packed weights.
+//   Both land in 128B-swizzled K-major shared memory and feed tcgen05.mma (M=128, N=Cout-tile, K=16)
+//   with the fp32 accumulator in TMEM. bw*bh may be < 128: the unused accumulator lanes are never read.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace islpose {
+
+// One convolution layer as the host describes it.
+struct ConvDesc {
+  // input slice
+  const __nv_bfloat16* in;  // points at channel c0 of pixel (0,0,0)
+  int in_c;                 // channels in the slice (multiple of 8)
+  int in_cstride;           // channels per pixel of the underlying buffer (multiple of 8)
+  int N, H, W;
+  // weights
+  const __nv_bfloat16* w;  // [k*k][cout][in_c]
+  int cout;
+  int ksize;  // 1, 3 or 7
+  const float* bias;   // [>= n_tiles*n_tile], zero padded
+  const float* slope;  // negative-side slope per channel: 0 = ReLU, 1 = identity, else PReLU weight
+  // outputs (either may be null)
+  __nv_bfloat16* out_bf16;  // points at channel offset of pixel 0
+  int out_cstride;          // channels per pixel of the destination buffer (multiple of 8)
+  float* out_f32;           // [N,H,W,out_f32_cstride]
+  int out_f32_cstride;
+  // tuning overrides (0 = auto)
+  int force_n_tile;
+  int force_stages;
+  int force_bw, force_bh;
+};
+
+// A fully resolved launch (tensor maps built once, reusable for every replay).
+struct ConvArgs {
+  int ksize, pad;
+  int cin_k16;  // number of K=16 steps that cover the input slice
+  int bw, bh;
+  int tiles_x, tiles_y;
+  int H, W;
+  int n_tile;
+  int cout;        // fp32 channels stored
+  int cout_store;  // bf16 channels stored (cout rounded up to 8)
+  int stages;
+  int tmem_cols;
+  uint32_t b_stage_bytes;
+  __nv_bfloat16* out_bf16;
+  long long out_pix_stride;
+  float* out_f32;
+  long long out_f32_pix_stride;
+  const float* bias;
+  const float* slope;
+};
+
+struct ConvLaunch {
+  alignas(64) CUtensorMap tmA;
+  alignas(64) CUtensorMap tmB;
+  ConvArgs args;
+  dim3 grid;
+  uint32_t smem_bytes;
+  double flops;  // algorithmic: 2*Cin*Cout*k*k*H*W*N on the unpadded slice width the caller states
+};
+
+// Returns 0 on success; on failure writes a message into err (if non-null).
+int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen);
+int conv_run(const ConvLaunch& l, cudaStream_t stream);
+
+}  // namespace islpose
