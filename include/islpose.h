@@ -1,0 +1,128 @@
+/* islpose - C ABI of the B200 (sm_100a) OpenPose keypoint-extraction kernels.
+ *
+ * The reference (sunilsarolkarcds/ISL-SignLanguage-Translation) is pure Python and has no FFI of its own; its
+ * boundary for this path is Body.__call__ (src/body.py:39), Hand.__call__ (src/hand.py:24) and util.handDetect
+ * (src/util.py:242). This library is what a Python shim behind those three signatures binds with ctypes
+ * (INTEGRATION.md shows the stub). Each entry point below names the reference lines it replaces.
+ *
+ * Conventions: every function returns 0 on success and non-zero on failure, in which case
+ * islpose_last_error() returns a thread-local message. All data pointers are DEVICE pointers unless the
+ * name starts with h_. Every launch is asynchronous on the given stream (a cudaStream_t passed as void*).
+ * No torch types, no C++ types.
+ */
+#ifndef ISLPOSE_H_
+#define ISLPOSE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ISLPOSE_ABI_VERSION 1
+#define ISLPOSE_MAX_SCALES 8
+
+int islpose_abi_version(void);
+const char* islpose_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Network plans: a recorded list of kernel launches (one per layer) over caller-owned device buffers,
+ * replayed per forward. Replaces nn.Module.forward of bodypose_model / bodypose_25_model / handpose_model
+ * (src/model.py:179-207, 302-329, 394-407). Activations are NHWC bf16; torch.cat disappears because
+ * producers write channel slices of shared buffers. */
+typedef struct islpose_plan islpose_plan;
+
+typedef struct islpose_conv_desc {
+  const void* in;       /* bf16 NHWC, points at the first channel of the input slice at pixel 0 */
+  int32_t in_c;         /* channels of the slice (multiple of 8) */
+  int32_t in_cstride;   /* channels per pixel of the buffer holding the slice (multiple of 8) */
+  int32_t n, h, w;      /* batch and spatial size (stride 1, "same" padding: output has the same size) */
+  const void* weights;  /* bf16 [k*k][cout][in_c]: nn.Conv2d weight [cout][cin][ky][kx] re-packed tap-major */
+  int32_t cout;
+  int32_t ksize;        /* 1, 3 or 7 (src/model.py:35-37) */
+  const float* bias;    /* fp32, at least 512 entries, zero padded */
+  const float* slope;   /* fp32, at least 512 entries: 0 = ReLU, 1 = no activation, else per-channel PReLU */
+  void* out_bf16;       /* bf16 NHWC slice (may be NULL): receives cout rounded up to 8 channels, pad = 0 */
+  int32_t out_cstride;  /* channels per pixel of that buffer */
+  float* out_f32;       /* fp32 planar NCHW (may be NULL): channel 0 of this layer inside [n][out_f32_channels][h][w] */
+  int32_t out_f32_channels;
+  int32_t n_tile, stages, tile_w, tile_h; /* tuning overrides, 0 = automatic */
+} islpose_conv_desc;
+
+int islpose_plan_create(islpose_plan** out);
+int islpose_plan_destroy(islpose_plan* plan);
+int islpose_plan_add_conv(islpose_plan* plan, const islpose_conv_desc* desc);
+/* nn.MaxPool2d(2, 2, 0) (src/model.py:30-32) on a full NHWC bf16 buffer */
+int islpose_plan_add_maxpool2x2(islpose_plan* plan, const void* in, void* out, int32_t n, int32_t h, int32_t w, int32_t c);
+/* fp32 NCHW [n,3,h,w] network input -> bf16 [n,h,w,32] rows of the first layer's 3x3x3 patches (27 + 5 zeros) */
+int islpose_plan_add_im2col3x3(islpose_plan* plan, const float* in_nchw, void* out_nhwc32, int32_t n, int32_t h, int32_t w);
+int islpose_plan_run(const islpose_plan* plan, void* stream);
+int32_t islpose_plan_num_launches(const islpose_plan* plan);
+double islpose_plan_conv_flops(const islpose_plan* plan); /* sum of 2*Cin*Cout*k*k*H*W*N over the slices as given */
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Pre-processing: cv2.resize(INTER_CUBIC, fx=fy=scale) + util.padRightDownCorner(8, 128) + x/256-0.5 + HWC->CHW
+ * (src/body.py:53-56, src/hand.py:37-40, src/util.py:12-32). frames: uint8 [n,H,W,3] contiguous.
+ * rh,rw = round-half-even(H*scale, W*scale); hp,wp = rh,rw rounded up to multiples of 8.
+ * out_nchw: fp32 [n,3,hp,wp]; out_u8 (optional, may be NULL): the padded uint8 image [n,hp,wp,3]. */
+int islpose_resize_pad_normalize(const uint8_t* frames, int32_t n, int32_t H, int32_t W, double scale, int32_t rh,
+                                 int32_t rw, int32_t hp, int32_t wp, float* out_nchw, uint8_t* out_u8, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * One scale of a call: the network output and the geometry of the two cubic resizes that bring it to frame size. */
+typedef struct islpose_scale {
+  const float* lowres; /* fp32 planar NCHW [n][channels][gh][gw] */
+  int32_t gh, gw;      /* stride-8 grid = hp/8, wp/8 */
+  int32_t hc, wc;      /* x8 up-sampled map cropped to the un-padded resized image: rh, rw */
+} islpose_scale;
+
+/* Map post-processing (src/body.py:69-81, src/hand.py:51-56): x8 cubic, crop, cubic to (W,H), /S, accumulate in
+ * float64. Writes channels [0, parts) of the result as planes: out float64 [n][parts][H][W].
+ * double_running_sum != 0 reproduces `heatmap_avg += heatmap_avg + heatmap / S` (body.py:80). */
+int islpose_maps_accumulate(const islpose_scale* scales, int32_t n_scales, int32_t channels, int32_t n, int32_t H,
+                            int32_t W, int32_t parts, int32_t double_running_sum, double* out, void* stream);
+
+/* Peak detection (src/body.py:86-107): scipy gaussian_filter(sigma=3) in float64 with reflect borders, 4-neighbour
+ * NMS against zero-filled shifts, threshold; peaks of every (frame, part) plane sorted in row-major order.
+ * h_gauss: the 25 float64 filter weights, a HOST pointer. cap <= 1024 peaks per plane.
+ * counts int32 [planes]; keys uint32 [planes][cap] = y*W+x; scores float64 [planes][cap] = unsmoothed value. */
+int islpose_body_peaks(const double* heat, int32_t planes, int32_t H, int32_t W, const double* h_gauss, double thre1,
+                       int32_t cap, int32_t* counts, uint32_t* keys, double* scores, int32_t* overflow, void* stream);
+
+/* Connection scoring, greedy matching, person assembly and pruning (src/body.py:109-235). PAF values are sampled
+ * from the stride-8 PAF maps on demand (both cubic stages and the mean over scales). model_kind: 0 coco, 1 body25.
+ * Scratch and outputs are caller-allocated; see islpose_group_buffers. */
+typedef struct islpose_group_buffers {
+  int32_t cap;             /* peak capacity per part used in islpose_body_peaks */
+  const int32_t* counts;
+  const uint32_t* keys;
+  const double* scores;
+  int32_t cand_cap;        /* <= 2048 connection candidates per limb */
+  int32_t* cand_count;     /* [n*nlimbs] */
+  uint32_t* cand_pair;     /* [n*nlimbs*cand_cap] */
+  double* cand_score;      /* [n*nlimbs*cand_cap] */
+  int32_t* conn_count;     /* [n*nlimbs] */
+  int32_t* conn_ij;        /* [n*nlimbs*cap*2] */
+  double* conn_score;      /* [n*nlimbs*cap] */
+  int32_t max_cand;
+  double* candidate;       /* out [n][max_cand][4]: x, y, score, id */
+  int32_t* n_cand;         /* out [n] */
+  int32_t max_person;
+  double* subset;          /* out [n][max_person][njoint+1] */
+  int32_t* n_person;       /* out [n] */
+  int32_t* overflow;       /* out [1]: non-zero if a capacity was exceeded */
+} islpose_group_buffers;
+
+int islpose_body_group(const islpose_scale* paf_scales, int32_t n_scales, int32_t model_kind, int32_t n, int32_t H,
+                       int32_t W, double thre2, int32_t mid_num, const islpose_group_buffers* buffers, void* stream);
+
+/* Hand key points (src/hand.py:58-74): gaussian sigma=3, threshold, 8-connected labelling, heaviest component,
+ * first arg-max. heat float64 [planes][H][W] (from islpose_maps_accumulate, planes = hands*21);
+ * smoothed/labels/mass: scratch of planes*H*W elements each; out_xy int32 [planes][2] (x, y; 0,0 = not found). */
+int islpose_hand_peaks(const double* heat, int32_t planes, int32_t H, int32_t W, const double* h_gauss, double thre,
+                       double* smoothed, int32_t* labels, double* mass, int32_t* out_xy, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISLPOSE_H_ */

@@ -1,0 +1,95 @@
+"""ctypes binding of libislpose.so (C ABI declared in include/islpose.h).
+
+There is no CPU fallback: if the library is missing or a call fails, an exception is raised.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libislpose.so")
+
+MAX_SCALES = 8
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [("in_", C.c_void_p), ("in_c", C.c_int32), ("in_cstride", C.c_int32), ("n", C.c_int32), ("h", C.c_int32),
+                ("w", C.c_int32), ("weights", C.c_void_p), ("cout", C.c_int32), ("ksize", C.c_int32),
+                ("bias", C.c_void_p), ("slope", C.c_void_p), ("out_bf16", C.c_void_p), ("out_cstride", C.c_int32),
+                ("out_f32", C.c_void_p), ("out_f32_channels", C.c_int32), ("n_tile", C.c_int32), ("stages", C.c_int32),
+                ("tile_w", C.c_int32), ("tile_h", C.c_int32)]
+
+
+class Scale(C.Structure):
+    _fields_ = [("lowres", C.c_void_p), ("gh", C.c_int32), ("gw", C.c_int32), ("hc", C.c_int32), ("wc", C.c_int32)]
+
+
+class GroupBuffers(C.Structure):
+    _fields_ = [("cap", C.c_int32), ("counts", C.c_void_p), ("keys", C.c_void_p), ("scores", C.c_void_p),
+                ("cand_cap", C.c_int32), ("cand_count", C.c_void_p), ("cand_pair", C.c_void_p),
+                ("cand_score", C.c_void_p), ("conn_count", C.c_void_p), ("conn_ij", C.c_void_p),
+                ("conn_score", C.c_void_p), ("max_cand", C.c_int32), ("candidate", C.c_void_p), ("n_cand", C.c_void_p),
+                ("max_person", C.c_int32), ("subset", C.c_void_p), ("n_person", C.c_void_p), ("overflow", C.c_void_p)]
+
+
+# every symbol include/islpose.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "islpose_abi_version": (C.c_int, []),
+    "islpose_last_error": (C.c_char_p, []),
+    "islpose_plan_create": (C.c_int, [C.POINTER(C.c_void_p)]),
+    "islpose_plan_destroy": (C.c_int, [C.c_void_p]),
+    "islpose_plan_add_conv": (C.c_int, [C.c_void_p, C.POINTER(ConvDesc)]),
+    "islpose_plan_add_maxpool2x2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "islpose_plan_add_im2col3x3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
+    "islpose_plan_run": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "islpose_plan_num_launches": (C.c_int32, [C.c_void_p]),
+    "islpose_plan_conv_flops": (C.c_double, [C.c_void_p]),
+    "islpose_resize_pad_normalize": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_int32,
+                                               C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "islpose_maps_accumulate": (C.c_int, [C.POINTER(Scale), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                          C.c_int32, C.c_void_p, C.c_void_p]),
+    "islpose_body_peaks": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.c_double, C.c_int32,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "islpose_body_group": (C.c_int, [C.POINTER(Scale), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double,
+                                     C.c_int32, C.POINTER(GroupBuffers), C.c_void_p]),
+    "islpose_hand_peaks": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.c_double,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+}
+
+_lib = None
+
+
+class IslposeError(RuntimeError):
+    pass
+
+
+def lib():
+    """The loaded library. Raises IslposeError when libislpose.so has not been built (no fallback exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise IslposeError("libislpose.so is missing at %s - build it with `python -c 'import __graft_entry__ as g; "
+                               "g.build()'` (nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        if handle.islpose_abi_version() != 1:
+            raise IslposeError("libislpose.so has ABI version %d, expected 1" % handle.islpose_abi_version())
+        _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise IslposeError("%s failed: %s" % (what, lib().islpose_last_error().decode("utf-8", "replace")))
+
+
+def stream_ptr():
+    import torch
+
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)

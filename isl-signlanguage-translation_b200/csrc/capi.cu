@@ -1,0 +1,287 @@
+// extern "C" surface declared in include/islpose.h. Plain pointers and sizes only.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/islpose.h"
+#include "conv_umma.cuh"
+#include "prepost.cuh"
+
+using namespace islpose;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int set_err(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+
+int check_cuda(const char* what) {
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_err("%s: %s", what, cudaGetErrorString(e));
+  return 0;
+}
+
+enum OpKind { kConv = 0, kPool = 1, kIm2col = 2 };
+
+struct Op {
+  OpKind kind;
+  ConvLaunch conv;  // kConv
+  const void* in;   // kPool / kIm2col
+  void* out;
+  int n, h, w, c;
+};
+
+const int kCocoA[19] = {1, 1, 2, 3, 5, 6, 1, 8, 9, 1, 11, 12, 1, 0, 14, 0, 15, 2, 5};
+const int kCocoB[19] = {2, 5, 3, 4, 6, 7, 8, 9, 10, 11, 12, 13, 0, 14, 16, 15, 17, 16, 17};
+const int kCocoX[19] = {12, 20, 14, 16, 22, 24, 0, 2, 4, 6, 8, 10, 28, 30, 34, 32, 36, 18, 26};
+const int kB25A[24] = {1, 1, 2, 3, 1, 5, 6, 1, 8, 9, 10, 8, 12, 13, 0, 0, 15, 16, 11, 11, 14, 14, 22, 19};
+const int kB25B[24] = {0, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 24, 22, 21, 19, 23, 20};
+const int kB25X[24] = {30, 14, 16, 18, 22, 24, 26, 0, 6, 2, 4, 8, 10, 12, 32, 34, 36, 38, 50, 46, 44, 40, 48, 42};
+
+LimbTable limb_table(int model_kind) {
+  LimbTable lt;
+  memset(&lt, 0, sizeof(lt));
+  if (model_kind == 1) {
+    lt.nlimbs = 24;
+    lt.njoint = 26;
+    for (int k = 0; k < 24; ++k) {
+      lt.a[k] = kB25A[k];
+      lt.b[k] = kB25B[k];
+      lt.cx[k] = kB25X[k];
+      lt.cy[k] = kB25X[k] + 1;
+    }
+  } else {
+    lt.nlimbs = 19;
+    lt.njoint = 19;
+    for (int k = 0; k < 19; ++k) {
+      lt.a[k] = kCocoA[k];
+      lt.b[k] = kCocoB[k];
+      lt.cx[k] = kCocoX[k];
+      lt.cy[k] = kCocoX[k] + 1;
+    }
+  }
+  return lt;
+}
+
+int fill_scales(const islpose_scale* scales, int n_scales, int channels, int H, int W, ScaleSet* ss) {
+  if (n_scales < 1 || n_scales > kMaxScales) return set_err("between 1 and %d scales are supported, got %d", kMaxScales, n_scales);
+  memset(ss, 0, sizeof(*ss));
+  ss->count = n_scales;
+  ss->channels = channels;
+  for (int s = 0; s < n_scales; ++s) {
+    const islpose_scale& in = scales[s];
+    if (in.lowres == nullptr || in.gh <= 0 || in.gw <= 0 || in.hc <= 0 || in.wc <= 0 || in.hc > in.gh * 8 || in.wc > in.gw * 8)
+      return set_err("scale %d: inconsistent geometry (grid %dx%d, crop %dx%d)", s, in.gh, in.gw, in.hc, in.wc);
+    ScaleGeom& g = ss->g[s];
+    g.low = in.lowres;
+    g.gh = in.gh;
+    g.gw = in.gw;
+    g.hc = in.hc;
+    g.wc = in.wc;
+    // cv2.resize with an explicit dsize: inv_scale = (double)dst / src; scale = 1. / inv_scale
+    g.sx = 1.0 / (static_cast<double>(W) / in.wc);
+    g.sy = 1.0 / (static_cast<double>(H) / in.hc);
+  }
+  return 0;
+}
+
+}  // namespace
+
+struct islpose_plan {
+  std::vector<Op> ops;
+  double flops = 0;
+};
+
+extern "C" {
+
+int islpose_abi_version(void) { return ISLPOSE_ABI_VERSION; }
+const char* islpose_last_error(void) { return g_err; }
+
+int islpose_plan_create(islpose_plan** out) {
+  if (out == nullptr) return set_err("plan_create: null output");
+  *out = new islpose_plan();
+  return 0;
+}
+
+int islpose_plan_destroy(islpose_plan* plan) {
+  delete plan;
+  return 0;
+}
+
+int islpose_plan_add_conv(islpose_plan* plan, const islpose_conv_desc* d) {
+  if (plan == nullptr || d == nullptr) return set_err("plan_add_conv: null argument");
+  ConvDesc c;
+  memset(&c, 0, sizeof(c));
+  c.in = static_cast<const __nv_bfloat16*>(d->in);
+  c.in_c = d->in_c;
+  c.in_cstride = d->in_cstride;
+  c.N = d->n;
+  c.H = d->h;
+  c.W = d->w;
+  c.w = static_cast<const __nv_bfloat16*>(d->weights);
+  c.cout = d->cout;
+  c.ksize = d->ksize;
+  c.bias = d->bias;
+  c.slope = d->slope;
+  c.out_bf16 = static_cast<__nv_bfloat16*>(d->out_bf16);
+  c.out_cstride = d->out_cstride;
+  c.out_f32 = d->out_f32;
+  c.out_f32_channels = d->out_f32_channels;
+  c.force_n_tile = d->n_tile;
+  c.force_stages = d->stages;
+  c.force_bw = d->tile_w;
+  c.force_bh = d->tile_h;
+  Op op;
+  memset(&op, 0, sizeof(op));
+  op.kind = kConv;
+  char err[256] = "";
+  if (conv_prepare(c, &op.conv, err, sizeof(err)) != 0) return set_err("%s", err);
+  plan->ops.push_back(op);
+  plan->flops += op.conv.flops;
+  return 0;
+}
+
+int islpose_plan_add_maxpool2x2(islpose_plan* plan, const void* in, void* out, int32_t n, int32_t h, int32_t w, int32_t c) {
+  if (plan == nullptr || in == nullptr || out == nullptr) return set_err("plan_add_maxpool2x2: null argument");
+  if (c % 8 != 0 || h % 2 != 0 || w % 2 != 0) return set_err("maxpool2x2: need C %% 8 == 0 and even H, W (got %d, %d, %d)", c, h, w);
+  Op op;
+  memset(&op, 0, sizeof(op));
+  op.kind = kPool;
+  op.in = in;
+  op.out = out;
+  op.n = n;
+  op.h = h;
+  op.w = w;
+  op.c = c;
+  plan->ops.push_back(op);
+  return 0;
+}
+
+int islpose_plan_add_im2col3x3(islpose_plan* plan, const float* in_nchw, void* out, int32_t n, int32_t h, int32_t w) {
+  if (plan == nullptr || in_nchw == nullptr || out == nullptr) return set_err("plan_add_im2col3x3: null argument");
+  Op op;
+  memset(&op, 0, sizeof(op));
+  op.kind = kIm2col;
+  op.in = in_nchw;
+  op.out = out;
+  op.n = n;
+  op.h = h;
+  op.w = w;
+  plan->ops.push_back(op);
+  return 0;
+}
+
+int islpose_plan_run(const islpose_plan* plan, void* stream) {
+  if (plan == nullptr) return set_err("plan_run: null plan");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (size_t i = 0; i < plan->ops.size(); ++i) {
+    const Op& op = plan->ops[i];
+    int rc = 0;
+    if (op.kind == kConv) {
+      rc = conv_run(op.conv, st);
+    } else if (op.kind == kPool) {
+      rc = launch_maxpool2x2(op.in, op.n, op.h, op.w, op.c, op.out, st);
+    } else {
+      rc = launch_im2col3x3(static_cast<const float*>(op.in), op.n, op.h, op.w, op.out, st);
+    }
+    if (rc != 0) {
+      check_cuda("plan_run");
+      return set_err("plan_run: launch %d of %d failed: %s", static_cast<int>(i), static_cast<int>(plan->ops.size()), g_err);
+    }
+  }
+  return 0;
+}
+
+int32_t islpose_plan_num_launches(const islpose_plan* plan) { return plan ? static_cast<int32_t>(plan->ops.size()) : 0; }
+double islpose_plan_conv_flops(const islpose_plan* plan) { return plan ? plan->flops : 0.0; }
+
+int islpose_resize_pad_normalize(const uint8_t* frames, int32_t n, int32_t H, int32_t W, double scale, int32_t rh,
+                                 int32_t rw, int32_t hp, int32_t wp, float* out_nchw, uint8_t* out_u8, void* stream) {
+  if (frames == nullptr || out_nchw == nullptr) return set_err("resize_pad_normalize: null pointer");
+  if (n <= 0 || H <= 0 || W <= 0 || rh <= 0 || rw <= 0 || hp < rh || wp < rw || hp % 8 != 0 || wp % 8 != 0 || !(scale > 0))
+    return set_err("resize_pad_normalize: bad geometry (%dx%d -> %dx%d padded %dx%d)", H, W, rh, rw, hp, wp);
+  if (launch_resize_pad_norm(frames, n, H, W, scale, rh, rw, hp, wp, out_nchw, out_u8, static_cast<cudaStream_t>(stream)) != 0)
+    return check_cuda("resize_pad_normalize") ? 1 : set_err("resize_pad_normalize: launch failed");
+  return 0;
+}
+
+int islpose_maps_accumulate(const islpose_scale* scales, int32_t n_scales, int32_t channels, int32_t n, int32_t H,
+                            int32_t W, int32_t parts, int32_t double_running_sum, double* out, void* stream) {
+  if (scales == nullptr || out == nullptr) return set_err("maps_accumulate: null pointer");
+  if (parts <= 0 || parts > channels || n <= 0 || H <= 0 || W <= 0) return set_err("maps_accumulate: bad sizes");
+  ScaleSet ss;
+  if (fill_scales(scales, n_scales, channels, H, W, &ss) != 0) return 1;
+  if (launch_heat_accumulate(ss, n, H, W, parts, double_running_sum, out, static_cast<cudaStream_t>(stream)) != 0)
+    return check_cuda("maps_accumulate") ? 1 : set_err("maps_accumulate: launch failed");
+  return 0;
+}
+
+int islpose_body_peaks(const double* heat, int32_t planes, int32_t H, int32_t W, const double* h_gauss, double thre1,
+                       int32_t cap, int32_t* counts, uint32_t* keys, double* scores, int32_t* overflow, void* stream) {
+  if (heat == nullptr || h_gauss == nullptr || counts == nullptr || keys == nullptr || scores == nullptr || overflow == nullptr)
+    return set_err("body_peaks: null pointer");
+  if (cap <= 0 || cap > 1024) return set_err("body_peaks: cap must be in 1..1024, got %d", cap);
+  GaussWeights gw;
+  memcpy(gw.w, h_gauss, sizeof(gw.w));
+  if (launch_gauss_nms(heat, planes, H, W, gw, thre1, cap, counts, keys, scores, overflow, static_cast<cudaStream_t>(stream)) != 0)
+    return check_cuda("body_peaks") ? 1 : set_err("body_peaks: launch failed");
+  return 0;
+}
+
+int islpose_body_group(const islpose_scale* paf_scales, int32_t n_scales, int32_t model_kind, int32_t n, int32_t H,
+                       int32_t W, double thre2, int32_t mid_num, const islpose_group_buffers* b, void* stream) {
+  if (paf_scales == nullptr || b == nullptr) return set_err("body_group: null pointer");
+  if (model_kind != 0 && model_kind != 1) return set_err("body_group: model_kind must be 0 (coco) or 1 (body25)");
+  if (mid_num != 10) return set_err("body_group: mid_num is fixed at 10 (body.py:130), got %d", mid_num);
+  const LimbTable lt = limb_table(model_kind);
+  ScaleSet ss;
+  if (fill_scales(paf_scales, n_scales, model_kind == 1 ? 52 : 38, H, W, &ss) != 0) return 1;
+  GroupBuffers gb;
+  gb.cap = b->cap;
+  gb.counts = b->counts;
+  gb.keys = b->keys;
+  gb.scores = b->scores;
+  gb.cand_cap = b->cand_cap;
+  gb.cand_count = b->cand_count;
+  gb.cand_pair = b->cand_pair;
+  gb.cand_score = b->cand_score;
+  gb.conn_count = b->conn_count;
+  gb.conn_ij = b->conn_ij;
+  gb.conn_score = b->conn_score;
+  gb.max_cand = b->max_cand;
+  gb.candidate = b->candidate;
+  gb.n_cand = b->n_cand;
+  gb.max_person = b->max_person;
+  gb.subset = b->subset;
+  gb.n_person = b->n_person;
+  gb.overflow = b->overflow;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (launch_paf_score(ss, lt, n, H, W, thre2, mid_num, gb, st) != 0)
+    return check_cuda("body_group/paf_score") ? 1 : set_err("body_group: capacities out of range (cap %d, cand_cap %d)", gb.cap, gb.cand_cap);
+  if (launch_group(lt, n, W, gb, st) != 0) return check_cuda("body_group/group") ? 1 : set_err("body_group: launch failed");
+  return 0;
+}
+
+int islpose_hand_peaks(const double* heat, int32_t planes, int32_t H, int32_t W, const double* h_gauss, double thre,
+                       double* smoothed, int32_t* labels, double* mass, int32_t* out_xy, void* stream) {
+  if (heat == nullptr || h_gauss == nullptr || smoothed == nullptr || labels == nullptr || mass == nullptr || out_xy == nullptr)
+    return set_err("hand_peaks: null pointer");
+  GaussWeights gw;
+  memcpy(gw.w, h_gauss, sizeof(gw.w));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (launch_gauss_smooth(heat, planes, H, W, gw, smoothed, st) != 0)
+    return check_cuda("hand_peaks/gauss") ? 1 : set_err("hand_peaks: launch failed");
+  if (launch_hand_peaks(heat, smoothed, planes, H, W, thre, labels, mass, out_xy, st) != 0)
+    return check_cuda("hand_peaks") ? 1 : set_err("hand_peaks: launch failed");
+  return 0;
+}
+
+}  // extern "C"

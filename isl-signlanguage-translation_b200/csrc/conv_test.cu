@@ -110,7 +110,7 @@ static int run_cfg(const Cfg& c, bool timing) {
   d.out_bf16 = c.bf16_out ? d_out16 + out_coff : nullptr;
   d.out_cstride = out_cstride;
   d.out_f32 = c.f32_out ? d_out32 : nullptr;
-  d.out_f32_cstride = c.cout;
+  d.out_f32_channels = c.cout;
   d.force_n_tile = c.force_n_tile;
   d.force_stages = c.force_stages;
 
@@ -147,7 +147,8 @@ static int run_cfg(const Cfg& c, bool timing) {
       const double r = h_ref[p * c.cout + co];
       if (fabs(r) > max_ref) max_ref = fabs(r);
       if (c.f32_out) {
-        const double dd = fabs(h_o32[p * c.cout + co] - r);
+        const long long hw = static_cast<long long>(c.H) * c.W;
+        const double dd = fabs(h_o32[((p / hw) * c.cout + co) * hw + p % hw] - r);
         if (!(dd <= err32)) err32 = dd;
       }
       if (c.bf16_out) {

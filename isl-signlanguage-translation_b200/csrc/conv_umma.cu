@@ -170,10 +170,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         if (a.out_f32 != nullptr) {
-          float* dst = a.out_f32 + pix * a.out_f32_pix_stride + n0 + c;
+          // planar NCHW: for a fixed channel the 32 lanes of a warp write neighbouring pixels
+          const long long plane = static_cast<long long>(a.H) * a.W;
+          float* dst = a.out_f32 + (static_cast<long long>(img) * a.out_f32_channels + n0 + c) * plane +
+                       static_cast<long long>(y) * a.W + x;
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            if (n0 + c + i < a.cout) dst[i] = v[i];
+            if (n0 + c + i < a.cout) dst[i * plane] = v[i];
           }
         }
       }
@@ -296,7 +299,7 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   a.out_bf16 = d.out_bf16;
   a.out_pix_stride = d.out_cstride;
   a.out_f32 = d.out_f32;
-  a.out_f32_pix_stride = d.out_f32_cstride;
+  a.out_f32_channels = d.out_f32_channels;
   a.bias = d.bias;
   a.slope = d.slope;
 

@@ -6,7 +6,8 @@
 //                 *slice* [c0, c0+Cin) of a buffer with `cstride` channels per pixel (this is how
 //                 torch.cat in model.py:177,190,199,308-324,397-405 disappears: producers write slices).
 //   weights     : bf16 [tap = ky*k+kx][Cout][Cin8]   (Cin8 = Cin rounded up to 8, zero padded)
-//   outputs     : bf16 slice of an NHWC buffer and/or fp32 NHWC [N,H,W,cout] (network heads)
+//   outputs     : bf16 slice of an NHWC buffer and/or fp32 planar NCHW (network heads; the layout
+//                 model.forward returns, model.py:207,329,407)
 //
 // GEMM view: D[128 pixels, Cout-tile] = sum over (tap, 64-channel block) A[128 pixels, 64] * B[Cout-tile, 64]^T
 //   A tile = one TMA box (64 ch, bw, bh, 1 image) fetched at pixel offset (kx-pad, ky-pad): TMA zero-fills
@@ -38,8 +39,8 @@ struct ConvDesc {
   // outputs (either may be null)
   __nv_bfloat16* out_bf16;  // points at channel offset of pixel 0
   int out_cstride;          // channels per pixel of the destination buffer (multiple of 8)
-  float* out_f32;           // [N,H,W,out_f32_cstride]
-  int out_f32_cstride;
+  float* out_f32;           // planar NCHW [N,out_f32_channels,H,W]; channel 0 of this layer's outputs
+  int out_f32_channels;
   // tuning overrides (0 = auto)
   int force_n_tile;
   int force_stages;
@@ -62,7 +63,7 @@ struct ConvArgs {
   __nv_bfloat16* out_bf16;
   long long out_pix_stride;
   float* out_f32;
-  long long out_f32_pix_stride;
+  int out_f32_channels;
   const float* bias;
   const float* slope;
 };

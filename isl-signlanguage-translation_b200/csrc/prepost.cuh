@@ -1,0 +1,65 @@
+// Launchers of the pre/post-processing kernels (prepost.cu, group.cu, hand.cu). Host-callable, no torch types.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "cubic.cuh"
+
+namespace islpose {
+
+struct GaussWeights {
+  double w[25];  // scipy _gaussian_kernel1d(sigma=3, radius=12), computed by the host in float64
+};
+
+// limbSeq / mapIdx of the body model (body.py:109-126)
+struct LimbTable {
+  int nlimbs;
+  int njoint;  // 19 (coco) or 26 (body25); subset rows have njoint+1 columns
+  int a[24], b[24];    // joint indices of each limb
+  int cx[24], cy[24];  // PAF channels of each limb
+};
+
+int launch_resize_pad_norm(const uint8_t* frames, int N, int H, int W, double scale, int rh, int rw, int hp, int wp,
+                           float* out_nchw, uint8_t* out_u8, cudaStream_t st);
+int launch_im2col3x3(const float* in, int N, int h, int w, void* out, cudaStream_t st);
+int launch_maxpool2x2(const void* in, int N, int H, int W, int C, void* out, cudaStream_t st);
+int launch_heat_accumulate(const ScaleSet& ss, int N, int H, int W, int parts, int q1, double* out, cudaStream_t st);
+int launch_gauss_nms(const double* heat, int planes_total, int H, int W, const GaussWeights& gw, double thre, int cap,
+                     int* counts, uint32_t* keys, double* scores, int* overflow, cudaStream_t st);
+int launch_gauss_smooth(const double* heat, int planes_total, int H, int W, const GaussWeights& gw, double* smoothed,
+                        cudaStream_t st);
+
+// group.cu
+struct GroupBuffers {
+  // inputs: sorted peak lists per (frame, part)
+  int cap;               // peak capacity per part (<= 1024)
+  const int* counts;     // [N*parts]
+  const uint32_t* keys;  // [N*parts*cap]  y*W+x
+  const double* scores;  // [N*parts*cap]  unsmoothed heat value
+  // scratch: connection candidates per (frame, limb)
+  int cand_cap;          // <= 2048
+  int* cand_count;       // [N*nlimbs]
+  uint32_t* cand_pair;   // [N*nlimbs*cand_cap]  i*nB+j
+  double* cand_score;    // [N*nlimbs*cand_cap]
+  // scratch: chosen connections per (frame, limb)
+  int* conn_count;       // [N*nlimbs]
+  int* conn_ij;          // [N*nlimbs*cap*2]
+  double* conn_score;    // [N*nlimbs*cap]
+  // outputs
+  int max_cand;          // rows available per frame in candidate
+  double* candidate;     // [N*max_cand*4]  x, y, score, id
+  int* n_cand;           // [N]
+  int max_person;
+  double* subset;        // [N*max_person*(njoint+1)]
+  int* n_person;         // [N]
+  int* overflow;         // [1] set to non-zero if any capacity was exceeded
+};
+int launch_paf_score(const ScaleSet& paf, const LimbTable& lt, int N, int H, int W, double thre2, int mid_num,
+                     const GroupBuffers& gb, cudaStream_t st);
+int launch_group(const LimbTable& lt, int N, int W, const GroupBuffers& gb, cudaStream_t st);
+
+// hand.cu
+int launch_hand_peaks(const double* heat, const double* smoothed, int planes_total, int H, int W, double thre,
+                      int* labels, double* mass, int32_t* out_xy, cudaStream_t st);
+
+}  // namespace islpose

@@ -1,0 +1,92 @@
+"""Hand estimator with the reference's call API (src/hand.py), running on the sm_100a kernels.
+
+    hand = Hand(model_path)                  # hand.py:16
+    peaks = hand(crop)                       # hand.py:24   crop: uint8 [h,w,3] -> int array [21,2] (x, y), [0,0] = missing
+    all_peaks = hand.batch([crop0, ...])     # new: the four network scales run once for all crops
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .body import _load_flat, scale_geometry
+from .nets import PoseNet
+from .util import gaussian_weights
+
+
+def _pow2_at_least(n):
+    p = 1
+    while p < n:
+        p <<= 1
+    return p
+
+
+class Hand(object):
+    def __init__(self, model_path, device=None, tuning=None):
+        self.model = PoseNet('hand', _load_flat(model_path), device=device, tuning=tuning)
+        self.device = self.model.device
+        self.scale_search = [0.5, 1.0, 1.5, 2.0]   # hand.py:25
+        self.boxsize, self.stride, self.padValue, self.thre = 368, 8, 128, 0.05
+        self._gauss = (C.c_double * 25)(*gaussian_weights().tolist())
+
+    def __call__(self, oriImg):
+        return self.batch([oriImg])[0]
+
+    def network_outputs(self, crops_dev):
+        """crops_dev: list of uint8 cuda tensors [h,w,3]. Crops whose network inputs have the same shape (all square
+        crops do: 184, 368, 552, 736) share a batched plan per scale. Returns per crop a list of
+        (heat tensor, plane offset in elements, geometry)."""
+        L = _lib.lib()
+        geoms = [scale_geometry(c.shape[0], c.shape[1], self.scale_search, self.boxsize) for c in crops_dev]
+        per_crop = [[] for _ in crops_dev]
+        for si in range(len(self.scale_search)):
+            groups = {}
+            for ci, g in enumerate(geoms):
+                groups.setdefault((g[si][3], g[si][4]), []).append(ci)
+            for (hp, wp), members in groups.items():
+                inst = self.model.instance(_pow2_at_least(len(members)), hp, wp)
+                for slot, ci in enumerate(members):
+                    m, rh, rw, _, _ = geoms[ci][si]
+                    c = crops_dev[ci]
+                    dst = C.c_void_p(inst.input.data_ptr() + slot * 3 * hp * wp * 4)
+                    _lib.check(L.islpose_resize_pad_normalize(_lib.ptr(c), 1, c.shape[0], c.shape[1], m, rh, rw, hp, wp,
+                                                              dst, None, _lib.stream_ptr()), "islpose_resize_pad_normalize")
+                inst.run()
+                plane = 22 * (hp // 8) * (wp // 8)
+                for slot, ci in enumerate(members):
+                    per_crop[ci].append((inst.outputs[0], slot * plane, (geoms[ci][si][1], geoms[ci][si][2], hp, wp)))
+        return per_crop
+
+    def postprocess(self, maps, h, w):
+        """maps: [(heat tensor, element offset, (rh, rw, hp, wp))] for one crop -> int array [21,2]."""
+        L = _lib.lib()
+        st = _lib.stream_ptr()
+        dev = self.device
+        arr = (_lib.Scale * len(maps))()
+        for i, (t, off, (rh, rw, hp, wp)) in enumerate(maps):
+            arr[i].lowres = t.data_ptr() + 4 * off
+            arr[i].gh, arr[i].gw, arr[i].hc, arr[i].wc = hp // 8, wp // 8, rh, rw
+        heat = torch.empty((21, h, w), dtype=torch.float64, device=dev)
+        smoothed = torch.empty((21, h, w), dtype=torch.float64, device=dev)
+        labels = torch.empty((21, h, w), dtype=torch.int32, device=dev)
+        mass = torch.empty((21, h, w), dtype=torch.float64, device=dev)
+        out = torch.zeros((21, 2), dtype=torch.int32, device=dev)
+        _lib.check(L.islpose_maps_accumulate(arr, len(maps), 22, 1, h, w, 21, 0, _lib.ptr(heat), st), "islpose_maps_accumulate")
+        _lib.check(L.islpose_hand_peaks(_lib.ptr(heat), 21, h, w, self._gauss, self.thre, _lib.ptr(smoothed),
+                                        _lib.ptr(labels), _lib.ptr(mass), _lib.ptr(out), st), "islpose_hand_peaks")
+        return out
+
+    def batch(self, crops):
+        crops = [np.ascontiguousarray(c) for c in crops]
+        for c in crops:
+            if c.ndim != 3 or c.shape[2] != 3 or c.dtype != np.uint8:
+                raise ValueError("Hand needs uint8 [h,w,3] crops, got %s %s" % (c.shape, c.dtype))
+        if not crops:
+            return []
+        with torch.cuda.device(self.device):
+            dev_crops = [torch.from_numpy(c).to(self.device, non_blocking=True) for c in crops]
+            per_crop = self.network_outputs(dev_crops)
+            outs = [self.postprocess(per_crop[i], crops[i].shape[0], crops[i].shape[1]) for i in range(len(crops))]
+            stacked = torch.stack(outs).cpu().numpy()
+        return [stacked[i].astype(np.int64) for i in range(len(crops))]

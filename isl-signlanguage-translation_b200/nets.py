@@ -1,0 +1,379 @@
+"""The three OpenPose networks as launch plans over NHWC bf16 buffers (reference: src/model.py).
+
+`PoseNet(kind, flat_weights)` is what `Body.model` / `Hand.model` hold. It keeps the reference module's calling
+convention - `model(data: float32 [N,3,h,w] cuda) -> (PAF, heat)` or `-> heat` as float32 NCHW tensors
+(model.py:207,329,407) - so the frame-level wrappers that take `body_estimation.model`
+(ISL_extract_features_videos.py:49-52, ISL_Model_parameter.py:44-47) keep working, but underneath every layer is
+one tcgen05 implicit-GEMM launch recorded in a C-side plan (include/islpose.h) and replayed per call.
+
+Layout decisions (DESIGN.md has the full table):
+  * conv1_1 (Cin=3) runs as a 1x1 GEMM over 3x3x3 patches gathered to 32 bf16 per pixel (K = 27 -> 32);
+  * torch.cat never happens: a stage input is one buffer [feat 128 | branch outputs, each padded to 8] and the
+    producers write their channel slices; weights are re-indexed to that channel order when they are packed;
+  * body25's dense blocks (model.py:171-177) write their three 3x3 outputs side by side in one 3w-wide buffer;
+  * the stage-output layers write bf16 into the next stage's input and/or float32 planar NCHW network outputs.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+RELU, NONE, PRELU = "relu", "none", "prelu"
+
+_VGG = [("conv1_1", 3, 64), ("conv1_2", 64, 64), "pool", ("conv2_1", 64, 128), ("conv2_2", 128, 128), "pool",
+        ("conv3_1", 128, 256), ("conv3_2", 256, 256), ("conv3_3", 256, 256), ("conv3_4", 256, 256), "pool",
+        ("conv4_1", 256, 512), ("conv4_2", 512, 512)]
+
+OUTPUT_CHANNELS = {"coco": (38, 19), "body25": (52, 26), "hand": (22,)}
+
+
+def _up8(c):
+    return (c + 7) // 8 * 8
+
+
+class _Program:
+    """Shape-independent description of one network: buffers (channels, pyramid level) and steps."""
+
+    def __init__(self, kind):
+        self.kind = kind
+        self.bufs = {}    # name -> (channels, level)
+        self.steps = []   # ("im2col", dst) | ("pool", src, dst) | ("conv", {...})
+        self.outputs = []  # float32 outputs: (name, channels)
+
+    def buf(self, name, channels, level):
+        prev = self.bufs.get(name)
+        if prev is not None and prev != (channels, level):
+            raise ValueError("buffer %s redefined" % name)
+        self.bufs[name] = (channels, level)
+        return name
+
+    def conv(self, layer, src, dst=None, cout=128, k=3, act=RELU, prelu=None, chan_map=None, f32=None, first=False):
+        """src = (buffer, channel offset, channels); dst = (buffer, channel offset) | None;
+        f32 = index into self.outputs | None; chan_map[i] = reference input channel read at slice channel i
+        (None = zero weight)."""
+        self.steps.append(("conv", dict(layer=layer, src=src, dst=dst, cout=cout, k=k, act=act, prelu=prelu,
+                                        chan_map=chan_map, f32=f32, first=first)))
+
+    def pool(self, src, dst):
+        self.steps.append(("pool", src, dst))
+
+
+def _backbone(p, tail, prelu_names=()):
+    """VGG-19 prefix + the net-specific tail; returns the name of the 128-channel feature layer's spec."""
+    p.buf("x32", 32, 0)
+    p.steps.append(("im2col", "x32"))
+    level = 0
+    cur = ("x32", 0, 32)
+    toggle = 0
+    layers = [l for l in _VGG] + list(tail)
+    for item in layers:
+        if item == "pool":
+            level += 1
+            name = p.buf("pool%d" % level, cur[2], level)
+            p.pool(cur[0], name)
+            cur = (name, 0, cur[2])
+            continue
+        lname, cin, cout = item
+        out = p.buf("L%d_%d_%s" % (level, cout, "ab"[toggle]), cout, level)
+        if out == cur[0]:
+            toggle ^= 1
+            out = p.buf("L%d_%d_%s" % (level, cout, "ab"[toggle]), cout, level)
+        toggle ^= 1
+        if lname in prelu_names:
+            p.conv(lname, cur, (out, 0), cout=cout, k=3, act=PRELU, prelu="prelu" + lname[4:], first=(lname == "conv1_1"))
+        else:
+            p.conv(lname, cur, (out, 0), cout=cout, k=3, act=RELU, first=(lname == "conv1_1"))
+        cur = (out, 0, cout)
+    return cur
+
+
+def _emit_feature(p, feat_spec, src, targets, prelu=None):
+    """The last backbone layer (-> 128 channels) is written once per buffer that needs `feat` as a slice."""
+    lname, cin, cout = feat_spec
+    for t in targets:
+        p.conv(lname, src, (t, 0), cout=cout, k=3, act=PRELU if prelu else RELU, prelu=prelu)
+
+
+def build_program(kind):
+    p = _Program(kind)
+    if kind == "coco":
+        src = _backbone(p, [("conv4_3_CPM", 512, 256)])
+        # stage input layout [feat 128 | L1 38->40 | L2 19->24]; reference order is cat[L1, L2, feat] (model.py:308)
+        for nm in ("catA", "catB"):
+            p.buf(nm, 192, 3)
+        _emit_feature(p, ("conv4_4_CPM", 256, 128), src, ["catA", "catB"])
+        cmap = [57 + i for i in range(128)] + list(range(38)) + [None, None] + [38 + i for i in range(19)] + [None] * 5
+        p.buf("t1", 128, 3), p.buf("t2", 128, 3), p.buf("u512", 512, 3)
+        p.outputs = [("paf", 38), ("heat", 19)]
+        slices = {1: (128, 38), 2: (168, 19)}
+        for br in (1, 2):
+            off, cout = slices[br]
+            p.conv("conv5_1_CPM_L%d" % br, ("catA", 0, 128), ("t1", 0))
+            p.conv("conv5_2_CPM_L%d" % br, ("t1", 0, 128), ("t2", 0))
+            p.conv("conv5_3_CPM_L%d" % br, ("t2", 0, 128), ("t1", 0))
+            p.conv("conv5_4_CPM_L%d" % br, ("t1", 0, 128), ("u512", 0), cout=512, k=1)
+            p.conv("conv5_5_CPM_L%d" % br, ("u512", 0, 512), ("catA", off), cout=cout, k=1, act=NONE)
+        cur, nxt = "catA", "catB"
+        for st in range(2, 7):
+            for br in (1, 2):
+                off, cout = slices[br]
+                tag = "stage%d_L%d" % (st, br)
+                p.conv("Mconv1_" + tag, (cur, 0, 192), ("t1", 0), k=7, chan_map=cmap)
+                p.conv("Mconv2_" + tag, ("t1", 0, 128), ("t2", 0), k=7)
+                p.conv("Mconv3_" + tag, ("t2", 0, 128), ("t1", 0), k=7)
+                p.conv("Mconv4_" + tag, ("t1", 0, 128), ("t2", 0), k=7)
+                p.conv("Mconv5_" + tag, ("t2", 0, 128), ("t1", 0), k=7)
+                p.conv("Mconv6_" + tag, ("t1", 0, 128), ("t2", 0), k=1)
+                # model.py:215-218 omits 'Mconv7_stage6_L2' from no_relu_layers: the final heat map keeps its ReLU
+                last = st == 6
+                act = RELU if (last and br == 2) else NONE
+                p.conv("Mconv7_" + tag, ("t2", 0, 128), None if last else (nxt, off), cout=cout, k=1, act=act,
+                       f32=(br - 1) if last else None)
+            cur, nxt = nxt, cur
+    elif kind == "hand":
+        src = _backbone(p, [("conv4_3", 512, 512), ("conv4_4", 512, 512), ("conv5_1", 512, 512), ("conv5_2", 512, 512)])
+        for nm in ("catA", "catB"):
+            p.buf(nm, 152, 3)  # [feat 128 | heat 22->24]; reference order cat[heat, feat] (model.py:397)
+        _emit_feature(p, ("conv5_3_CPM", 512, 128), src, ["catA", "catB"])
+        cmap = [22 + i for i in range(128)] + list(range(22)) + [None, None]
+        p.buf("t1", 128, 3), p.buf("t2", 128, 3), p.buf("u512", 512, 3)
+        p.outputs = [("heat", 22)]
+        p.conv("conv6_1_CPM", ("catA", 0, 128), ("u512", 0), cout=512, k=1)
+        p.conv("conv6_2_CPM", ("u512", 0, 512), ("catA", 128), cout=22, k=1, act=NONE)
+        cur, nxt = "catA", "catB"
+        for st in range(2, 7):
+            p.conv("Mconv1_stage%d" % st, (cur, 0, 152), ("t1", 0), k=7, chan_map=cmap)
+            p.conv("Mconv2_stage%d" % st, ("t1", 0, 128), ("t2", 0), k=7)
+            p.conv("Mconv3_stage%d" % st, ("t2", 0, 128), ("t1", 0), k=7)
+            p.conv("Mconv4_stage%d" % st, ("t1", 0, 128), ("t2", 0), k=7)
+            p.conv("Mconv5_stage%d" % st, ("t2", 0, 128), ("t1", 0), k=7)
+            p.conv("Mconv6_stage%d" % st, ("t1", 0, 128), ("t2", 0), k=1)
+            last = st == 6
+            p.conv("Mconv7_stage%d" % st, ("t2", 0, 128), None if last else (nxt, 128), cout=22, k=1, act=NONE,
+                   f32=0 if last else None)
+            cur, nxt = nxt, cur
+    elif kind == "body25":
+        src = _backbone(p, [("conv4_3_CPM", 512, 256)], prelu_names=("conv4_2", "conv4_3_CPM"))
+        # PAF-stage input [feat 128 | PAF 52->56] (reference cat[feat, PAF], model.py:190);
+        # last heat-stage input [feat 128 | heat 26->32 | PAF 52->56] (reference cat[feat, heat, PAF], model.py:199)
+        p.buf("catA", 184, 3), p.buf("catB", 184, 3), p.buf("catD", 216, 3)
+        _emit_feature(p, ("conv4_4_CPM", 256, 128), src, ["catA", "catB", "catD"], prelu="prelu4_4_CPM")
+        map184 = list(range(180)) + [None] * 4
+        map216 = list(range(128)) + [128 + i for i in range(26)] + [None] * 6 + [154 + i for i in range(52)] + [None] * 4
+        for w in (96, 128):
+            p.buf("dense%d_a" % w, 3 * w, 3), p.buf("dense%d_b" % w, 3 * w, 3)
+        p.buf("m256", 256, 3), p.buf("m512", 512, 3)
+        p.outputs = [("paf", 52), ("heat", 26)]
+
+        def stage(br, st, src_spec, cmap, width, mid, dsts, f32):
+            nout = 52 if br == 2 else 26
+            tag = "stage%d_L%d" % (st, br)
+            cur = src_spec
+            bufs = ["dense%d_a" % width, "dense%d_b" % width]
+            for blk in range(1, 6):
+                y = bufs[(blk - 1) % 2]
+                for j in range(3):
+                    name = "Mconv%d_%s_%d" % (blk, tag, j)
+                    pre = "Mprelu%d_%s_%d" % (blk, tag, j)
+                    s = cur if j == 0 else (y, (j - 1) * width, width)
+                    p.conv(name, s, (y, j * width), cout=width, k=3, act=PRELU, prelu=pre,
+                           chan_map=cmap if (blk == 1 and j == 0) else None)
+                cur = (y, 0, 3 * width)
+            mbuf = "m%d" % mid
+            p.conv("Mconv6_" + tag, cur, (mbuf, 0), cout=mid, k=1, act=PRELU, prelu="Mprelu6_" + tag)
+            if not dsts:
+                p.conv("Mconv7_" + tag, (mbuf, 0, mid), None, cout=nout, k=1, act=NONE, f32=f32)
+            for i, d in enumerate(dsts):
+                p.conv("Mconv7_" + tag, (mbuf, 0, mid), d, cout=nout, k=1, act=NONE, f32=f32 if i == 0 else None)
+
+        stage(2, 0, ("catA", 0, 128), None, 96, 256, [("catA", 128)], None)
+        stage(2, 1, ("catA", 0, 184), map184, 128, 512, [("catB", 128)], None)
+        stage(2, 2, ("catB", 0, 184), map184, 128, 512, [("catA", 128)], None)
+        stage(2, 3, ("catA", 0, 184), map184, 128, 512, [("catB", 128), ("catD", 160)], 0)
+        stage(1, 0, ("catB", 0, 184), map184, 96, 256, [("catD", 128)], None)
+        stage(1, 1, ("catD", 0, 216), map216, 128, 512, [], 1)
+    else:
+        raise ValueError("unknown network kind %r" % (kind,))
+    return p
+
+
+def _pack_weight(w, chan_map, in_c, first):
+    """nn.Conv2d weight [cout, cin, k, k] float32 -> bf16 [k*k, cout, in_c] in the buffer's channel order."""
+    cout, cin, k, _ = w.shape
+    if first:  # conv1_1 as a 1x1 GEMM over gathered patches: K index = (ky*3+kx)*3 + c
+        packed = torch.zeros((1, cout, in_c), dtype=torch.float32)
+        packed[0, :, :27] = w.permute(0, 2, 3, 1).reshape(cout, 27)
+        return packed.to(torch.bfloat16).contiguous()
+    taps = w.permute(2, 3, 0, 1).reshape(k * k, cout, cin)  # [tap, cout, cin]
+    if chan_map is None:
+        if cin != in_c:
+            raise ValueError("slice width %d does not match Cin %d" % (in_c, cin))
+        return taps.to(torch.bfloat16).contiguous()
+    packed = torch.zeros((k * k, cout, in_c), dtype=torch.float32)
+    idx = [(i, c) for i, c in enumerate(chan_map) if c is not None]
+    dst = torch.tensor([i for i, _ in idx], dtype=torch.long)
+    srcc = torch.tensor([c for _, c in idx], dtype=torch.long)
+    if sorted(srcc.tolist()) != list(range(cin)):
+        raise ValueError("channel map does not cover Cin=%d exactly once" % cin)
+    packed[:, :, dst] = taps[:, :, srcc]
+    return packed.to(torch.bfloat16).contiguous()
+
+
+class _Instance:
+    """One (batch, h, w) instantiation: device buffers + the C launch plan."""
+
+    def __init__(self, net, n, h, w):
+        L = _lib.lib()
+        dev = net.device
+        self.n, self.h, self.w = n, h, w
+        self.input = torch.empty((n, 3, h, w), dtype=torch.float32, device=dev)
+        self.bufs = {}
+        for name, (ch, level) in net.program.bufs.items():
+            self.bufs[name] = torch.zeros((n, h >> level, w >> level, ch), dtype=torch.bfloat16, device=dev)
+        gh, gw = h // 8, w // 8
+        self.outputs = [torch.empty((n, ch, gh, gw), dtype=torch.float32, device=dev) for _, ch in net.program.outputs]
+        handle = C.c_void_p()
+        _lib.check(L.islpose_plan_create(C.byref(handle)), "islpose_plan_create")
+        self.handle = handle
+        ci = 0
+        for step in net.program.steps:
+            if step[0] == "im2col":
+                _lib.check(L.islpose_plan_add_im2col3x3(handle, _lib.ptr(self.input), _lib.ptr(self.bufs[step[1]]), n, h, w),
+                           "islpose_plan_add_im2col3x3")
+            elif step[0] == "pool":
+                src, dst = self.bufs[step[1]], self.bufs[step[2]]
+                _lib.check(L.islpose_plan_add_maxpool2x2(handle, _lib.ptr(src), _lib.ptr(dst), n, src.shape[1], src.shape[2],
+                                                         src.shape[3]), "islpose_plan_add_maxpool2x2")
+            else:
+                s = step[1]
+                wt, bias, slope = net.packed[ci]
+                ci += 1
+                sb = self.bufs[s["src"][0]]
+                d = _lib.ConvDesc()
+                d.in_ = sb.data_ptr() + 2 * s["src"][1]
+                d.in_c = s["src"][2]
+                d.in_cstride = sb.shape[3]
+                d.n, d.h, d.w = n, sb.shape[1], sb.shape[2]
+                d.weights = wt.data_ptr()
+                d.cout = wt.shape[1]
+                d.ksize = 1 if s["first"] else s["k"]
+                d.bias = bias.data_ptr()
+                d.slope = slope.data_ptr()
+                if s["dst"] is not None:
+                    db = self.bufs[s["dst"][0]]
+                    d.out_bf16 = db.data_ptr() + 2 * s["dst"][1]
+                    d.out_cstride = db.shape[3]
+                if s["f32"] is not None:
+                    o = self.outputs[s["f32"]]
+                    d.out_f32 = o.data_ptr()
+                    d.out_f32_channels = o.shape[1]
+                cfg = net.tuning
+                d.n_tile, d.stages = cfg.get("n_tile", 0), cfg.get("stages", 0)
+                _lib.check(L.islpose_plan_add_conv(handle, C.byref(d)), "islpose_plan_add_conv(%s)" % s["layer"])
+        self.flops = L.islpose_plan_conv_flops(handle)
+        self.launches = L.islpose_plan_num_launches(handle)
+
+    def run(self):
+        _lib.check(_lib.lib().islpose_plan_run(self.handle, _lib.stream_ptr()), "islpose_plan_run")
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _lib.lib().islpose_plan_destroy(self.handle)
+        except Exception:
+            pass
+
+
+def algorithmic_flops(kind, n, h, w):
+    """sum over layers of 2*Cin*Cout*k*k*Hout*Wout on the unpadded channel counts."""
+    p = build_program(kind)
+    seen = set()
+    total = 0
+    for step in p.steps:
+        if step[0] != "conv":
+            continue
+        s = step[1]
+        if s["layer"] in seen:
+            continue  # a layer written to several buffers is one layer of the network
+        seen.add(s["layer"])
+        level = p.bufs[s["src"][0]][1]
+        cin = 3 if s["first"] else (sum(1 for c in s["chan_map"] if c is not None) if s["chan_map"] else s["src"][2])
+        total += 2 * cin * s["cout"] * s["k"] ** 2 * (h >> level) * (w >> level) * n
+    return total
+
+
+class PoseNet:
+    """Callable network with the reference nn.Module's interface surface (model.py), backed by launch plans."""
+
+    def __init__(self, kind, flat_weights, device=None, tuning=None):
+        if not torch.cuda.is_available():
+            raise _lib.IslposeError("PoseNet needs a CUDA device (sm_100a); there is no CPU path")
+        _lib.lib()
+        self.kind = kind
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.program = build_program(kind)
+        self.tuning = dict(tuning or {})
+        self._flat = {k: v.detach().to(torch.float32).cpu() for k, v in flat_weights.items()}
+        self.packed = []
+        for step in self.program.steps:
+            if step[0] != "conv":
+                continue
+            s = step[1]
+            w = self._flat[s["layer"] + ".weight"]
+            b = self._flat[s["layer"] + ".bias"]
+            cout = w.shape[0]
+            if cout != s["cout"] or w.shape[2] != s["k"]:
+                raise ValueError("%s: weight shape %s does not match the %s network" % (s["layer"], tuple(w.shape), kind))
+            wt = _pack_weight(w, s["chan_map"], s["src"][2], s["first"]).to(self.device)
+            bias = torch.zeros(512, dtype=torch.float32)
+            bias[:cout] = b
+            slope = torch.zeros(512, dtype=torch.float32)
+            if s["act"] == NONE:
+                slope[:cout] = 1.0
+            elif s["act"] == PRELU:
+                slope[:cout] = self._flat[s["prelu"] + ".weight"]
+            self.packed.append((wt, bias.to(self.device), slope.to(self.device)))
+        self._instances = {}
+
+    # ---- reference nn.Module surface -------------------------------------------------------------------
+    def parameters(self):
+        return iter(self._flat.values())
+
+    def state_dict(self):
+        return dict(self._flat)
+
+    def eval(self):
+        return self
+
+    def cuda(self, device=None):
+        return self
+
+    def to(self, *args, **kwargs):
+        return self
+
+    def instance(self, n, h, w):
+        if h % 8 or w % 8:
+            raise ValueError("network input must be a multiple of 8 in both dimensions, got %dx%d" % (h, w))
+        key = (n, h, w)
+        inst = self._instances.get(key)
+        if inst is None:
+            with torch.cuda.device(self.device):
+                inst = _Instance(self, n, h, w)
+            self._instances[key] = inst
+        return inst
+
+    def forward_into(self, data):
+        """Runs the plan for `data`'s shape; returns the plan's own float32 output tensors (overwritten by the
+        next call with the same shape)."""
+        n, c, h, w = data.shape
+        inst = self.instance(n, h, w)
+        inst.input.copy_(data)
+        inst.run()
+        return inst.outputs
+
+    def __call__(self, data):
+        outs = [o.clone() for o in self.forward_into(data.to(self.device, torch.float32))]
+        return outs[0] if self.kind == "hand" else (outs[0], outs[1])
+
+    forward = __call__
