@@ -1,0 +1,273 @@
+#!/usr/bin/env python
+"""Benchmark of the OpenPose keypoint-extraction hot path (body + hand) - one JSON line on stdout.
+
+    python bench.py --gpus N --steps K --warmup W [--workload C2|C3] [--batch B] [--impl reference]
+
+A step = one pass of body + hand extraction over one batch of synthetic frames per rank (frames shard across ranks,
+no collective on the data path; scaling is weak). Workloads (BASELINE.json configs):
+  C2  coco body + hand, 640x480, scale_search [0.5,1,1.5,2], two fixed hand boxes per frame      (default)
+  C3  body25 + hand, 1280x720, same scales, two 128-px hand boxes per frame
+Hand boxes are fixed per workload because random-init weights never produce a person for util.handDetect.
+
+value   frames/s with the frames already resident in HBM (device-timed, max over ranks)
+e2e     frames/s through the public host API (numpy frames in, numpy results out; H2D from pinned memory and the
+        D2H of candidate / subset / hand peaks inside the timed region)
+roofline     the tcgen05 conv kernel: algorithmic FLOPs of all network replays in the timed steps / their CUDA-event time
+cpu_baseline the oracle (restated reference, calling cv2 / scipy / torch-CPU where the reference does) on the host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "frames/sec body+hand keypoints @368 4-scale"
+SCALES = [0.5, 1.0, 1.5, 2.0]
+WORKLOADS = {
+    # name: (model_type, H, W, hand boxes [x, y, w, is_left], default batch per rank)
+    "C2": ("coco", 480, 640, [[400, 250, 109, True], [22, 246, 90, False]], 8),
+    "C3": ("body25", 720, 1280, [[800, 300, 128, True], [300, 300, 128, False]], 8),
+}
+
+
+def workload_name(wl, batch):
+    mt, H, W, boxes, _ = WORKLOADS[wl]
+    return "%s: %s body + hand, %dx%d, scale_search %s, %d hand boxes/frame (%s), batch %d frames/step/rank" % (
+        wl, mt, W, H, SCALES, len(boxes), ",".join("%dpx" % b[2] for b in boxes), batch)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        p = json.load(open(path))
+        return p.get("bf16_tflops_sustained", 1379.5), p.get("bf16_tflops", 1636.0), "measured"
+    return 1400.0, 1590.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.rows = []
+        self.stop_flag = False
+        self.index = index
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_reference_frame(wl, seed, nets=None):
+    """One frame of the workload through the oracle port of the reference (backend 'lib': cv2 / scipy / torch CPU
+    exactly where the reference calls them). Returns (seconds, nets) so repeated calls reuse the weights."""
+    import torch
+
+    from isl_b200 import synth
+    from oracle import openpose_oracle as O
+
+    mt, H, W, boxes, _ = WORKLOADS[wl]
+    if nets is None:
+        torch.set_num_threads(os.cpu_count() or 1)
+        nets = (O.make_net_fn(mt, O.make_flat_weights(mt, seed=0)), O.make_net_fn("hand", O.make_flat_weights("hand", seed=0)))
+    frame = synth.synth_frame(H, W, seed)
+    t0 = time.perf_counter()
+    try:
+        O.body_call(nets[0], frame, mt, tuple(SCALES), backend="lib", strict=False)
+    except IndexError:
+        pass
+    for (x, y, w, _) in boxes:
+        O.hand_call(nets[1], np.ascontiguousarray(frame[y:y + w, x:x + w, :]), backend="lib")
+    return time.perf_counter() - t0, nets
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the Python reference cannot
+    travel to the GPU box) on all host threads, one frame of the workload per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = args.workload
+    budget_s = 240.0
+    warm, nets = cpu_reference_frame(wl, 999)
+    times = []
+    spent = warm
+    for w in range(max(args.warmup - 1, 0)):
+        if spent + warm > budget_s * 0.4:
+            break
+        t, nets = cpu_reference_frame(wl, 998 - w, nets)
+        spent += t
+    for k in range(args.steps):
+        if times and spent + max(times) > budget_s:
+            break
+        t, nets = cpu_reference_frame(wl, k, nets)
+        times.append(t)
+        spent += t
+    fps = len(times) / sum(times)
+    cores = os.cpu_count() or 1
+    sample = "1 frame of the workload per step on %d host threads; %d of %d requested steps timed inside a %.0f s budget" % (
+        cores, len(times), args.steps, budget_s)
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": len(times),
+            "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(wl, 1), "timing": "host wall clock around each step (CPU only, no device work)"},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="frames per step per rank (0 = workload default)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+
+    import isl_b200
+    from isl_b200 import synth
+    from isl_b200.extract import KeypointExtractor
+    from oracle import openpose_oracle as O  # weights generator only on this path; the oracle runs in cpu_baseline
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    mt, H, W, boxes, default_batch = WORKLOADS[args.workload]
+    B = args.batch or default_batch
+    body = isl_b200.Body(O.make_flat_weights(mt, seed=0), mt, scale_search=SCALES)
+    hand = isl_b200.Hand(O.make_flat_weights("hand", seed=0))
+    ex = KeypointExtractor(body, hand)
+    hand_boxes = [boxes] * B
+
+    def frames_for(step):
+        return [synth.synth_frame(H, W, (rank * 100003 + step * B + i) % (2 ** 31)) for i in range(B)]
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB of L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- leg 1: device-resident inputs (value) + conv roofline -----------------------------------------------
+    total_steps = args.warmup + args.steps
+    dev_frames = [torch.from_numpy(np.stack(frames_for(s))).cuda() for s in range(min(total_steps, 4))]
+    for s in range(args.warmup):
+        flush.zero_()
+        ex.batch_device(dev_frames[s % len(dev_frames)], hand_boxes)
+    body.model.timing, hand.model.timing = [], []
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    step_events = []
+    for s in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ex.batch_device(dev_frames[(args.warmup + s) % len(dev_frames)], hand_boxes)
+        e1.record()
+        step_events.append((e0, e1))
+    barrier()
+    sampler.stop_flag = True
+    dev_ms = sum(a.elapsed_time(b) for a, b in step_events)
+    conv_ms = sum(a.elapsed_time(b) for a, b, _, _ in body.model.timing + hand.model.timing)
+    conv_flops = sum(f for _, _, f, _ in body.model.timing + hand.model.timing)
+    net_launches = sum(l for _, _, _, l in body.model.timing + hand.model.timing)
+    body.model.timing, hand.model.timing = None, None
+    n_hand_crops = B * len(boxes)
+    other_launches = args.steps * (len(SCALES) * 1 + 1 + 2 + 2 + n_hand_crops * (len(SCALES) + 1 + 2))
+    gpu_launches = net_launches + other_launches
+
+    # ---- leg 2: host API end to end (e2e) ------------------------------------------------------------------
+    host_frames = [frames_for(1000 + s) for s in range(min(args.steps, 4))]
+    for s in range(2):
+        ex.batch(host_frames[s % len(host_frames)], hand_boxes)
+    barrier()
+    e2e_events = []
+    d2h = 0
+    for s in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = ex.batch(host_frames[s % len(host_frames)], hand_boxes)
+        e1.record()
+        e2e_events.append((e0, e1))
+        d2h = sum(c.nbytes + sb.nbytes + sum(p.nbytes for p in hp) for c, sb, hp in res)
+    barrier()
+    e2e_ms = sum(a.elapsed_time(b) for a, b in e2e_events)
+    h2d = B * H * W * 3 + sum(b[2] * b[2] * 3 for b in boxes) * B
+
+    times = torch.tensor([dev_ms, e2e_ms, conv_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms, conv_ms_max = [float(x) for x in times.cpu()]
+
+    if rank == 0:
+        sustained, burst, src = peaks()
+        achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        frames_total = world * B * args.steps
+        line = {
+            "metric": METRIC, "value": frames_total / (dev_ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload_name(args.workload, B), "weights": "seeded random init (no trained weights ship with the reference)",
+                       "l2": "flushed with a 256 MiB write before every timed step",
+                       "timing": "CUDA events on the launching stream per step, summed; max over ranks"},
+            "clocks": sampler.summary(),
+            "e2e": {"value": frames_total / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(gpu_launches),
+            "roofline": {"bound": "tensor", "kernel": "conv_umma_kernel (all network replays of the timed steps; im2col and max-pool launches are inside the same events)",
+                         "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
+                         "peak_source": "%s bf16_tflops_sustained (burst %.1f)" % (src, burst), "traffic": None,
+                         "conv_share_of_step": conv_ms / (dev_ms if world == 1 else max(dev_ms, 1e-9))},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            t, _ = cpu_reference_frame(args.workload, 0)
+            line["cpu_baseline"] = {"value": 1.0 / t, "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                    "sample": "1 frame of the workload (body 4 scales + %d hands), %.1f s" % (len(boxes), t)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -97,20 +97,19 @@ typedef struct islpose_group_buffers {
   const int32_t* counts;
   const uint32_t* keys;
   const double* scores;
-  int32_t cand_cap;        /* <= 2048 connection candidates per limb */
-  int32_t* cand_count;     /* [n*nlimbs] */
-  uint32_t* cand_pair;     /* [n*nlimbs*cand_cap] */
-  double* cand_score;      /* [n*nlimbs*cand_cap] */
+  int64_t pair_cap;        /* scratch elements per (frame, limb); needs nA*nB <= pair_cap, else overflow = 3 */
+  double* pair_score;      /* [n*nlimbs*pair_cap] dense nA x nB connection scores (-1 = rejected pair) */
   int32_t* conn_count;     /* [n*nlimbs] */
   int32_t* conn_ij;        /* [n*nlimbs*cap*2] */
   double* conn_score;      /* [n*nlimbs*cap] */
+  int32_t* owner;          /* [n*max_cand*2] scratch */
   int32_t max_cand;
   double* candidate;       /* out [n][max_cand][4]: x, y, score, id */
   int32_t* n_cand;         /* out [n] */
-  int32_t max_person;
+  int32_t max_person;      /* row slots per frame: every row ever created, merged-away ones included (<= 65536) */
   double* subset;          /* out [n][max_person][njoint+1] */
   int32_t* n_person;       /* out [n] */
-  int32_t* overflow;       /* out [1]: non-zero if a capacity was exceeded */
+  int32_t* overflow;       /* out [1]: non-zero if a capacity was exceeded (1 peaks, 2 candidates, 3 pairs, 4 persons) */
 } islpose_group_buffers;
 
 int islpose_body_group(const islpose_scale* paf_scales, int32_t n_scales, int32_t model_kind, int32_t n, int32_t H,

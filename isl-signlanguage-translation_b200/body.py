@@ -17,9 +17,9 @@ from .nets import PoseNet
 from .tables import model_dims
 from .util import gaussian_weights
 
-PEAK_CAP = 1024     # peaks per (frame, part)
-CAND_CAP = 2048     # accepted connection candidates per (frame, limb)
-MAX_PERSON = 512
+PEAK_CAP = 1024        # peaks per (frame, part): the kernels' hard limit
+PAIR_CAP = 128 * 1024  # initial nA*nB capacity per (frame, limb); grows (x4) when a frame needs more
+MAX_PERSON = 4096      # initial row slots per frame (rows ever created); grows (x4) up to 65536
 
 
 def _load_flat(model_path):
@@ -77,12 +77,13 @@ class Body(object):
                 counts=torch.zeros((n * parts,), **i32),
                 keys=torch.zeros((n * parts, PEAK_CAP), dtype=torch.int32, device=dev),
                 scores=torch.zeros((n * parts, PEAK_CAP), **f64),
-                cand_count=torch.zeros((n * nl,), **i32),
-                cand_pair=torch.zeros((n * nl, CAND_CAP), **i32),
-                cand_score=torch.zeros((n * nl, CAND_CAP), **f64),
+                pair_cap=PAIR_CAP,
+                pair_score=torch.empty((n * nl, PAIR_CAP), **f64),
                 conn_count=torch.zeros((n * nl,), **i32),
                 conn_ij=torch.zeros((n * nl, PEAK_CAP, 2), **i32),
                 conn_score=torch.zeros((n * nl, PEAK_CAP), **f64),
+                owner=torch.zeros((n, parts * PEAK_CAP, 2), **i32),
+                max_person=MAX_PERSON,
                 candidate=torch.zeros((n, parts * PEAK_CAP, 4), **f64),
                 n_cand=torch.zeros((n,), **i32),
                 subset=torch.zeros((n, MAX_PERSON, self.njoint + 1), **f64),
@@ -128,20 +129,32 @@ class Body(object):
         _lib.check(L.islpose_body_peaks(_lib.ptr(ws["heat"]), n * parts, H, W, self._gauss, self.thre1, PEAK_CAP,
                                         _lib.ptr(ws["counts"]), _lib.ptr(ws["keys"]), _lib.ptr(ws["scores"]),
                                         _lib.ptr(ws["overflow"]), st), "islpose_body_peaks")
-        gb = _lib.GroupBuffers()
-        gb.cap, gb.cand_cap, gb.max_cand, gb.max_person = PEAK_CAP, CAND_CAP, parts * PEAK_CAP, MAX_PERSON
-        for f in ("counts", "keys", "scores", "cand_count", "cand_pair", "cand_score", "conn_count", "conn_ij",
-                  "conn_score", "candidate", "n_cand", "subset", "n_person", "overflow"):
-            setattr(gb, f, ws[f].data_ptr())
-        _lib.check(L.islpose_body_group(paf_scales, len(maps), 1 if self._kind == 'body25' else 0, n, H, W, self.thre2,
-                                        self.mid_num, C.byref(gb), st), "islpose_body_group")
-        n_cand = ws["n_cand"].cpu().numpy()
-        n_person = ws["n_person"].cpu().numpy()
-        self.last_overflow = int(ws["overflow"].cpu().item())
-        if self.last_overflow:
+        while True:
+            gb = _lib.GroupBuffers()
+            gb.cap, gb.pair_cap, gb.max_cand, gb.max_person = PEAK_CAP, ws["pair_cap"], parts * PEAK_CAP, ws["max_person"]
+            for f in ("counts", "keys", "scores", "pair_score", "conn_count", "conn_ij", "conn_score", "owner", "candidate",
+                      "n_cand", "subset", "n_person", "overflow"):
+                setattr(gb, f, ws[f].data_ptr())
+            _lib.check(L.islpose_body_group(paf_scales, len(maps), 1 if self._kind == 'body25' else 0, n, H, W, self.thre2,
+                                            self.mid_num, C.byref(gb), st), "islpose_body_group")
+            n_cand = ws["n_cand"].cpu().numpy()
+            n_person = ws["n_person"].cpu().numpy()
+            self.last_overflow = int(ws["overflow"].cpu().item())
+            if self.last_overflow == 0:
+                break
             ws["overflow"].zero_()
-            raise _lib.IslposeError("body grouping exceeded a fixed capacity (code %d: peaks per part > %d, candidates per "
-                                    "limb > %d or persons > %d)" % (self.last_overflow, PEAK_CAP, CAND_CAP, MAX_PERSON))
+            if self.last_overflow == 3 and ws["pair_cap"] < PEAK_CAP * PEAK_CAP:
+                # a limb has more candidate pairs than the scratch matrix holds: enlarge it and redo the grouping
+                ws["pair_cap"] = min(ws["pair_cap"] * 4, PEAK_CAP * PEAK_CAP)
+                ws["pair_score"] = torch.empty((ws["conn_count"].numel(), ws["pair_cap"]), dtype=torch.float64,
+                                               device=self.device)
+                continue
+            if self.last_overflow == 4 and ws["max_person"] < 65536:
+                ws["max_person"] *= 4
+                ws["subset"] = torch.zeros((n, ws["max_person"], self.njoint + 1), dtype=torch.float64, device=self.device)
+                continue
+            raise _lib.IslposeError("body grouping exceeded a fixed capacity (code %d: 1 = more than %d peaks in one part, "
+                                    "2 = candidate table, 4 = more than 65536 person rows)" % (self.last_overflow, PEAK_CAP))
         max_c, max_p = int(n_cand.max()) if n else 0, int(n_person.max()) if n else 0
         cand = ws["candidate"][:, :max(max_c, 1)].cpu().numpy()
         sub = ws["subset"][:, :max(max_p, 1)].cpu().numpy()
@@ -152,19 +165,29 @@ class Body(object):
             results.append((c, s))
         return results
 
-    def batch(self, frames):
-        """frames: list of uint8 [H,W,3] BGR arrays of one size -> list of (candidate, subset)."""
+    def upload(self, frames):
+        """Host frames -> this call's device staging buffer [n,H,W,3] (through pinned memory)."""
         frames = [np.asarray(f) for f in frames]
         H, W = frames[0].shape[:2]
         for f in frames:
             if f.shape != (H, W, 3) or f.dtype != np.uint8:
                 raise ValueError("Body.batch needs uint8 [H,W,3] frames of one size, got %s %s" % (f.shape, f.dtype))
-        n = len(frames)
+        ws = self._workspace(len(frames), H, W)
+        host = ws["pinned"].numpy()
+        for i, f in enumerate(frames):
+            host[i] = f   # also resolves negative-stride views such as frame[:, :, ::-1]
+        ws["frames"].copy_(ws["pinned"], non_blocking=True)
+        return ws["frames"]
+
+    def batch_device(self, frames_dev):
+        """frames_dev: uint8 cuda tensor [n,H,W,3] (contiguous) -> list of (candidate, subset)."""
+        n, H, W, _ = frames_dev.shape
         with torch.cuda.device(self.device):
             ws = self._workspace(n, H, W)
-            host = ws["pinned"].numpy()
-            for i, f in enumerate(frames):
-                host[i] = f   # also resolves negative-stride views such as frame[:, :, ::-1]
-            ws["frames"].copy_(ws["pinned"], non_blocking=True)
-            maps = self.network_outputs(ws["frames"], H, W)
+            maps = self.network_outputs(frames_dev, H, W)
             return self.postprocess(maps, n, H, W, ws)
+
+    def batch(self, frames):
+        """frames: list of uint8 [H,W,3] BGR arrays of one size -> list of (candidate, subset)."""
+        with torch.cuda.device(self.device):
+            return self.batch_device(self.upload(frames))

@@ -249,13 +249,12 @@ int islpose_body_group(const islpose_scale* paf_scales, int32_t n_scales, int32_
   gb.counts = b->counts;
   gb.keys = b->keys;
   gb.scores = b->scores;
-  gb.cand_cap = b->cand_cap;
-  gb.cand_count = b->cand_count;
-  gb.cand_pair = b->cand_pair;
-  gb.cand_score = b->cand_score;
+  gb.pair_cap = b->pair_cap;
+  gb.pair_score = b->pair_score;
   gb.conn_count = b->conn_count;
   gb.conn_ij = b->conn_ij;
   gb.conn_score = b->conn_score;
+  gb.owner = b->owner;
   gb.max_cand = b->max_cand;
   gb.candidate = b->candidate;
   gb.n_cand = b->n_cand;
@@ -265,7 +264,7 @@ int islpose_body_group(const islpose_scale* paf_scales, int32_t n_scales, int32_
   gb.overflow = b->overflow;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (launch_paf_score(ss, lt, n, H, W, thre2, mid_num, gb, st) != 0)
-    return check_cuda("body_group/paf_score") ? 1 : set_err("body_group: capacities out of range (cap %d, cand_cap %d)", gb.cap, gb.cand_cap);
+    return check_cuda("body_group/paf_score") ? 1 : set_err("body_group: peak capacity out of range (cap %d)", gb.cap);
   if (launch_group(lt, n, W, gb, st) != 0) return check_cuda("body_group/group") ? 1 : set_err("body_group: launch failed");
   return 0;
 }

@@ -183,7 +183,7 @@ static int run_cfg(const Cfg& c, bool timing) {
     CK(cudaEventElapsedTime(&ms, e0, e1));
     ms /= reps;
   }
-  printf("%s %-28s tile %dx%d n_tile %d stages %d grid %ux%u  max|ref| %.3f  err32 %.2e  err16 %.2e  badpad %lld",
+  printf("%s %-32s tile %dx%d n_tile %d stages %d grid %ux%u  max|ref| %.3f  err32 %.2e  err16 %.2e  badpad %lld",
          ok ? "PASS" : "FAIL", c.name, L.args.bw, L.args.bh, L.args.n_tile, L.args.stages, L.grid.x, L.grid.y,
          max_ref, err32, err16, bad_pad);
   if (ms > 0.f) printf("  %.3f ms  %.1f TFLOP/s", ms, L.flops / (ms * 1e-3) / 1e12);
@@ -219,6 +219,21 @@ int main(int argc, char** argv) {
       {"7x7 128->128 92x164 b2", 2, 92, 164, 128, 128, 0, 128, 7, false, true, 0, 0},
       {"7x7 128->128 92x164 s3", 2, 92, 164, 128, 128, 0, 128, 7, false, true, 0, 3},
       {"3x3 64->64 368x656", 1, 368, 656, 64, 64, 0, 64, 3, false, true, 0, 0},
+      // tiling comparisons on the heavy layers (auto = n_tile 128, 3 stages, two CTAs per SM)
+      {"3x3 256->256 46x82 b4 nt256s4", 4, 46, 82, 256, 256, 0, 256, 3, false, true, 256, 4},
+      {"3x3 256->256 46x82 b4 nt256s2", 4, 46, 82, 256, 256, 0, 256, 3, false, true, 256, 2},
+      {"3x3 512->512 92x164 nt256s4", 1, 92, 164, 512, 512, 0, 512, 3, false, true, 256, 4},
+      {"3x3 512->512 92x164 nt128s6", 1, 92, 164, 512, 512, 0, 512, 3, false, true, 128, 6},
+      {"7x7 128->128 92x164 b2 s6", 2, 92, 164, 128, 128, 0, 128, 7, false, true, 0, 6},
+      {"7x7 128->128 92x164 b2 s2", 2, 92, 164, 128, 128, 0, 128, 7, false, true, 0, 2},
+      {"7x7 128->128 23x41 b8", 8, 23, 41, 128, 128, 0, 128, 7, false, true, 0, 0},
+      {"7x7 128->128 23x41 b8 nt64", 8, 23, 41, 128, 128, 0, 128, 7, false, true, 64, 0},
+      {"7x7 192->128 60x80 b8", 8, 60, 80, 192, 192, 0, 128, 7, false, true, 0, 0},
+      {"3x3 128->128 184x248 b8", 8, 184, 248, 128, 128, 0, 128, 3, false, true, 0, 0},
+      {"3x3 64->64 368x496 b8", 8, 368, 496, 64, 64, 0, 64, 3, false, true, 0, 0},
+      {"1x1 32->64 368x496 b8", 8, 368, 496, 32, 32, 0, 64, 1, false, true, 0, 0},
+      {"3x3 96->96 slice 92x164 b2", 2, 92, 164, 96, 288, 96, 96, 3, false, true, 0, 0},
+      {"3x3 288->96 92x164 b2", 2, 92, 164, 288, 288, 0, 96, 3, false, true, 0, 0},
   };
   const int n = sizeof(cfgs) / sizeof(cfgs[0]);
   int fails = 0;

@@ -263,16 +263,11 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   a.tiles_y = (d.H + bh - 1) / bh;
   const long long m_tiles = static_cast<long long>(a.tiles_x) * a.tiles_y * d.N;
 
-  // Channel tile (UMMA N): multiple of 16, at most 256.
+  // Channel tile (UMMA N): multiple of 16, at most 256. 128 keeps a stage at 32 KB so that two CTAs fit on one SM
+  // with a 3-deep ring each: the second CTA's main loop hides the first one's epilogue and pipeline fill.
   const int cout16 = (d.cout + 15) / 16 * 16;
   int n_tile = d.force_n_tile;
-  if (n_tile <= 0) {
-    if (cout16 <= 256) {
-      n_tile = cout16;
-    } else {
-      n_tile = (m_tiles >= 148) ? 256 : 128;
-    }
-  }
+  if (n_tile <= 0) n_tile = cout16 <= 128 ? cout16 : 128;
   if (n_tile % 16 != 0 || n_tile > 256 || n_tile < 16) return fail(err, errlen, "conv: bad channel tile %lld", n_tile);
   const int n_tiles = (cout16 + n_tile - 1) / n_tile;
   a.n_tile = n_tile;
@@ -286,7 +281,8 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   const uint32_t per_stage = kASlotBytes + a.b_stage_bytes;
   int stages = d.force_stages;
   if (stages <= 0) {
-    stages = static_cast<int>((200u * 1024u) / per_stage);
+    stages = static_cast<int>((110u * 1024u - kCtrlBytes - 1024u) / per_stage);  // two CTAs per SM
+    if (stages < 2) stages = 2;
     const int iters = d.ksize * d.ksize * ((a.cin_k16 + 3) / 4);
     if (stages > iters) stages = iters;
   }

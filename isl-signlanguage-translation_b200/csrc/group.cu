@@ -2,9 +2,13 @@
 //   paf_score   body.py:142-164  one warp per (limb, candA i, candB j): 10 line samples x 2 PAF channels, each
 //               sampled lazily from the stride-8 PAF maps through both cubic stages and the scale mean
 //               (paf_avg is never materialised), float64 scalar math in the reference's operation order
-//   group       body.py:166-231  one CTA per frame: per limb a bitonic sort by (score desc, pair index asc)
-//               = Python's stable sorted(reverse=True), greedy one-to-one matching, then the serial person
-//               assembly and pruning carried out by one warp (row scans ballot-parallel, order preserved)
+//               and writes the score (or -1 when the pair fails criterion1/criterion2) into a dense nA x nB matrix
+//   match       body.py:166-173  one CTA per (frame, limb). Walking the candidates in stable descending score
+//               order and taking a pair when both ends are free is the same as repeatedly taking the arg-max over
+//               the still-free pairs (ties: lowest i*nB+j = the order the reference enumerated them in), so no
+//               sort is needed: per-row best partners are cached and only rows that lose their partner rescan
+//   assemble    body.py:180-231  one CTA per frame: candidate table, then the serial person assembly and pruning
+//               carried out by one warp (row scans ballot-parallel, order preserved)
 #include "prepost.cuh"
 
 namespace islpose {
@@ -19,6 +23,10 @@ paf_score_kernel(const ScaleSet ss, const LimbTable lt, int H, int W, int parts,
   const int nA = gb.counts[n * parts + pa];
   const int nB = gb.counts[n * parts + pb];
   const long long total = static_cast<long long>(nA) * nB;
+  if (total > gb.pair_cap) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) atomicMax(gb.overflow, 3);
+    return;
+  }
   const uint32_t* keyA = gb.keys + static_cast<long long>(n * parts + pa) * gb.cap;
   const uint32_t* keyB = gb.keys + static_cast<long long>(n * parts + pb) * gb.cap;
   const int C = ss.channels;
@@ -69,26 +77,130 @@ paf_score_kernel(const ScaleSet ss, const LimbTable lt, int H, int W, int parts,
     if (lane == 0) {
       const double prior = __dadd_rn(__ddiv_rn(sum, 10.0),
                                      fmin(__dsub_rn(__ddiv_rn(__dmul_rn(0.5, static_cast<double>(H)), norm), 1.0), 0.0));
-      if (__popc(above) > 8 && prior > 0.0) {  // > 0.8 * mid_num samples above thre2, positive score
-        const int slot = atomicAdd(gb.cand_count + slot_base, 1);
-        if (slot < gb.cand_cap) {
-          gb.cand_pair[static_cast<long long>(slot_base) * gb.cand_cap + slot] = static_cast<uint32_t>(pair);
-          gb.cand_score[static_cast<long long>(slot_base) * gb.cand_cap + slot] = prior;
-        }
-      }
+      // > 0.8 * mid_num samples above thre2 and a positive score, else the pair is not a candidate
+      gb.pair_score[static_cast<long long>(slot_base) * gb.pair_cap + pair] = (__popc(above) > 8 && prior > 0.0) ? prior : -1.0;
     }
   }
 }
 
-constexpr int kCandCap = 2048;
 constexpr int kPeakCap = 1024;
 
+struct RowBest {
+  double v;
+  int i, j;
+};
+// larger score first; equal scores resolve to the smaller i*nB+j (rows differ -> smaller i; same row -> smaller j)
+__device__ __forceinline__ RowBest pick(RowBest a, RowBest b) {
+  if (b.v > a.v) return b;
+  if (b.v == a.v && (b.i < a.i || (b.i == a.i && b.j < a.j))) return b;
+  return a;
+}
+__device__ __forceinline__ RowBest warp_pick(RowBest r) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    RowBest t;
+    t.v = __shfl_xor_sync(0xffffffffu, r.v, o);
+    t.i = __shfl_xor_sync(0xffffffffu, r.i, o);
+    t.j = __shfl_xor_sync(0xffffffffu, r.j, o);
+    r = pick(r, t);
+  }
+  return r;
+}
+
 __global__ void __launch_bounds__(256)
-group_kernel(const LimbTable lt, int W, const GroupBuffers gb) {
-  __shared__ double s_score[kCandCap];
-  __shared__ uint32_t s_pair[kCandCap];
-  __shared__ uint32_t s_usedA[kPeakCap / 32], s_usedB[kPeakCap / 32];
+match_kernel(const LimbTable lt, const GroupBuffers gb) {
+  __shared__ double s_best[kPeakCap];
+  __shared__ int s_bestj[kPeakCap];
+  __shared__ uint32_t s_usedB[kPeakCap / 32];
+  __shared__ RowBest s_red[8];
+  __shared__ RowBest s_win;
+  const int k = blockIdx.x, n = blockIdx.y;
+  const int parts = lt.njoint - 1;
+  const int slot = n * lt.nlimbs + k;
+  const int nA = gb.counts[n * parts + lt.a[k]];
+  const int nB = gb.counts[n * parts + lt.b[k]];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (nA == 0 || nB == 0) {
+    if (threadIdx.x == 0) gb.conn_count[slot] = -1;  // the limb is in special_k (body.py:174-176)
+    return;
+  }
+  if (static_cast<long long>(nA) * nB > gb.pair_cap) {
+    if (threadIdx.x == 0) gb.conn_count[slot] = 0;
+    return;
+  }
+  const double* sc = gb.pair_score + static_cast<long long>(slot) * gb.pair_cap;
+  for (int i = threadIdx.x; i < kPeakCap / 32; i += blockDim.x) s_usedB[i] = 0;
+  __syncthreads();
+
+  auto scan_row = [&](int i) {  // whole warp: best free partner of row i
+    RowBest r;
+    r.v = -1.0;
+    r.i = i;
+    r.j = 0x7fffffff;
+    for (int j = lane; j < nB; j += 32) {
+      if ((s_usedB[j >> 5] >> (j & 31)) & 1u) continue;
+      RowBest c;
+      c.v = sc[static_cast<long long>(i) * nB + j];
+      c.i = i;
+      c.j = j;
+      r = pick(r, c);
+    }
+    r = warp_pick(r);
+    if (lane == 0) {
+      s_best[i] = r.v;
+      s_bestj[i] = r.j;
+    }
+  };
+  for (int i = warp; i < nA; i += 8) scan_row(i);
+  __syncthreads();
+
+  const int limit = nA < nB ? nA : nB;
+  int made = 0;
+  while (made < limit) {
+    RowBest r;
+    r.v = -1.0;
+    r.i = 0x7fffffff;
+    r.j = 0x7fffffff;
+    for (int i = threadIdx.x; i < nA; i += blockDim.x) {
+      RowBest c;
+      c.v = s_best[i];
+      c.i = i;
+      c.j = s_bestj[i];
+      r = pick(r, c);
+    }
+    r = warp_pick(r);
+    if (lane == 0) s_red[warp] = r;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      RowBest w = s_red[0];
+      for (int q = 1; q < 8; ++q) w = pick(w, s_red[q]);
+      s_win = w;
+      if (w.v > 0.0) {
+        gb.conn_ij[(static_cast<long long>(slot) * gb.cap + made) * 2 + 0] = w.i;
+        gb.conn_ij[(static_cast<long long>(slot) * gb.cap + made) * 2 + 1] = w.j;
+        gb.conn_score[static_cast<long long>(slot) * gb.cap + made] = w.v;
+        s_best[w.i] = -2.0;  // row taken
+        s_usedB[w.j >> 5] |= 1u << (w.j & 31);
+      }
+    }
+    __syncthreads();
+    const RowBest w = s_win;
+    if (!(w.v > 0.0)) break;  // no candidate left among the free pairs
+    ++made;
+    for (int i = warp; i < nA; i += 8) {
+      if (s_best[i] > 0.0 && s_bestj[i] == w.j) scan_row(i);  // this row just lost its cached partner
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) gb.conn_count[slot] = made;
+}
+
+constexpr int kMaxSlots = 65536;  // row slots an assembly may create (dead ones included)
+
+__global__ void __launch_bounds__(256)
+assemble_kernel(const LimbTable lt, int W, const GroupBuffers gb) {
   __shared__ int s_off[32];
+  __shared__ uint32_t s_alive[kMaxSlots / 32];
   const int n = blockIdx.x;
   const int parts = lt.njoint - 1;
   const int cols = lt.njoint + 1;
@@ -104,7 +216,7 @@ group_kernel(const LimbTable lt, int W, const GroupBuffers gb) {
     }
     s_off[parts] = run;
     gb.n_cand[n] = run < gb.max_cand ? run : gb.max_cand;
-    if (run > gb.max_cand) atomicExch(gb.overflow, 2);
+    if (run > gb.max_cand) atomicMax(gb.overflow, 2);
   }
   __syncthreads();
   double* cand = gb.candidate + static_cast<long long>(n) * gb.max_cand * 4;
@@ -121,80 +233,29 @@ group_kernel(const LimbTable lt, int W, const GroupBuffers gb) {
       }
     }
   }
-
-  // ---- per limb: stable descending sort + greedy one-to-one matching (body.py:166-173)
-  for (int k = 0; k < lt.nlimbs; ++k) {
-    const int slot = n * lt.nlimbs + k;
-    const int nA = gb.counts[n * parts + lt.a[k]];
-    const int nB = gb.counts[n * parts + lt.b[k]];
-    int m = gb.cand_count[slot];
-    if (m > gb.cand_cap) {
-      if (threadIdx.x == 0) atomicExch(gb.overflow, 3);
-      m = gb.cand_cap;
-    }
-    __syncthreads();
-    if (nA == 0 || nB == 0 || m == 0) {
-      if (threadIdx.x == 0) gb.conn_count[slot] = (nA == 0 || nB == 0) ? -1 : 0;  // -1: limb is in special_k
-      continue;
-    }
-    int m2 = 1;
-    while (m2 < m) m2 <<= 1;
-    for (int i = threadIdx.x; i < m2; i += blockDim.x) {
-      s_score[i] = i < m ? gb.cand_score[static_cast<long long>(slot) * gb.cand_cap + i] : -1.0;  // scores are > 0
-      s_pair[i] = i < m ? gb.cand_pair[static_cast<long long>(slot) * gb.cand_cap + i] : 0xffffffffu;
-    }
-    for (int i = threadIdx.x; i < kPeakCap / 32; i += blockDim.x) {
-      s_usedA[i] = 0;
-      s_usedB[i] = 0;
-    }
-    __syncthreads();
-    for (int size = 2; size <= m2; size <<= 1) {
-      for (int stride = size >> 1; stride > 0; stride >>= 1) {
-        for (int i = threadIdx.x; i < m2; i += blockDim.x) {
-          const int j = i ^ stride;
-          if (j > i) {
-            const bool up = (i & size) == 0;
-            const double a = s_score[i], b = s_score[j];
-            const uint32_t pa = s_pair[i], pb = s_pair[j];
-            // "i before j" order: higher score first, ties by original (i, j) enumeration order
-            const bool j_first = (b > a) || (b == a && pb < pa);
-            if (j_first == up) {
-              s_score[i] = b;
-              s_score[j] = a;
-              s_pair[i] = pb;
-              s_pair[j] = pa;
-            }
-          }
-        }
-        __syncthreads();
-      }
-    }
-    if (threadIdx.x == 0) {
-      const int limit = nA < nB ? nA : nB;
-      int made = 0;
-      for (int c = 0; c < m && made < limit; ++c) {
-        const uint32_t pr = s_pair[c];
-        const int i = pr / nB, j = pr % nB;
-        if ((s_usedA[i >> 5] >> (i & 31)) & 1u) continue;
-        if ((s_usedB[j >> 5] >> (j & 31)) & 1u) continue;
-        s_usedA[i >> 5] |= 1u << (i & 31);
-        s_usedB[j >> 5] |= 1u << (j & 31);
-        gb.conn_ij[(static_cast<long long>(slot) * gb.cap + made) * 2 + 0] = i;
-        gb.conn_ij[(static_cast<long long>(slot) * gb.cap + made) * 2 + 1] = j;
-        gb.conn_score[static_cast<long long>(slot) * gb.cap + made] = s_score[c];
-        ++made;
-      }
-      gb.conn_count[slot] = made;
-    }
-    __syncthreads();
-  }
+  // owner[id] = the (at most two) row slots that currently hold candidate `id`. Every id belongs to one part,
+  // i.e. one column, and the reference's own two-slot subset_idx (body.py:193-197) implies an id never sits in
+  // more than two rows, so "rows with partA at indexA or partB at indexB" is a lookup instead of a scan.
+  int* owner = gb.owner + static_cast<long long>(n) * gb.max_cand * 2;
+  const int ncand = s_off[parts] < gb.max_cand ? s_off[parts] : gb.max_cand;
+  for (int i = threadIdx.x; i < ncand * 2; i += blockDim.x) owner[i] = -1;
+  for (int i = threadIdx.x; i < kMaxSlots / 32; i += blockDim.x) s_alive[i] = 0;
   __threadfence_block();
   __syncthreads();
   if (warp != 0) return;
 
-  // ---- person assembly (body.py:180-225), one warp; `sub` rows live in the output buffer
+  // ---- person assembly (body.py:180-225), one warp. Rows live in stable slots of the output buffer in creation
+  // order; np.delete marks a slot dead, so "row order" is slot order and nothing is shifted until the end.
   double* sub = gb.subset + static_cast<long long>(n) * gb.max_person * cols;
-  int rows = 0;
+  int slots = 0;
+  auto owner_add = [&](int id, int slot) {
+    if (owner[id * 2] == slot || owner[id * 2 + 1] == slot) return;
+    if (owner[id * 2] < 0) owner[id * 2] = slot; else if (owner[id * 2 + 1] < 0) owner[id * 2 + 1] = slot;
+  };
+  auto owner_remove = [&](int id, int slot) {
+    if (owner[id * 2] == slot) { owner[id * 2] = owner[id * 2 + 1]; owner[id * 2 + 1] = -1; }
+    else if (owner[id * 2 + 1] == slot) owner[id * 2 + 1] = -1;
+  };
   for (int k = 0; k < lt.nlimbs; ++k) {
     const int slot = n * lt.nlimbs + k;
     const int cc = gb.conn_count[slot];
@@ -205,25 +266,26 @@ group_kernel(const LimbTable lt, int W, const GroupBuffers gb) {
       const int cj = gb.conn_ij[(static_cast<long long>(slot) * gb.cap + c) * 2 + 1];
       const double cs = gb.conn_score[static_cast<long long>(slot) * gb.cap + c];
       const int idA = s_off[ia] + ci, idB = s_off[ib] + cj;
+      if (idA >= ncand || idB >= ncand) continue;  // only after a candidate-table overflow (already flagged)
       const double partA = static_cast<double>(idA), partB = static_cast<double>(idB);
-      // rows that already hold partA at indexA or partB at indexB, first two in row order
-      int found = 0, j1 = -1, j2 = -1;
-      for (int base = 0; base < rows && found < 2; base += 32) {
-        const int r = base + lane;
-        const bool hit = r < rows && (sub[r * cols + ia] == partA || sub[r * cols + ib] == partB);
-        unsigned mask = __ballot_sync(0xffffffffu, hit);
-        while (mask != 0 && found < 2) {
-          const int b = __ffs(mask) - 1;
-          mask &= mask - 1;
-          if (found == 0) j1 = base + b; else j2 = base + b;
-          ++found;
-        }
+      // rows holding partA at indexA or partB at indexB: the two smallest slots (a third would make the reference
+      // raise IndexError, body.py:193-197; the first two are used here)
+      int o[4] = {owner[idA * 2], owner[idA * 2 + 1], owner[idB * 2], owner[idB * 2 + 1]};
+      int j1 = 0x7fffffff, j2 = 0x7fffffff;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int v = o[q];
+        if (v < 0 || v == j1 || v == j2) continue;
+        if (v < j1) { j2 = j1; j1 = v; } else if (v < j2) { j2 = v; }
       }
-      // (a third match would make the reference raise IndexError, body.py:193-197; the first two are used)
-      const double sB = cand[(idB < gb.max_cand ? idB : 0) * 4 + 2];
-      const double sA = cand[(idA < gb.max_cand ? idA : 0) * 4 + 2];
+      const int found = (j1 != 0x7fffffff) + (j2 != 0x7fffffff);
+      const double sB = cand[idB * 4 + 2];
+      const double sA = cand[idA * 4 + 2];
       if (found == 1) {
         if (lane == 0 && sub[j1 * cols + ib] != partB) {
+          const double old = sub[j1 * cols + ib];
+          if (old >= 0.0) owner_remove(static_cast<int>(old), j1);
+          owner_add(idB, j1);
           sub[j1 * cols + ib] = partB;
           sub[j1 * cols + cols - 1] = __dadd_rn(sub[j1 * cols + cols - 1], 1.0);
           sub[j1 * cols + cols - 2] = __dadd_rn(sub[j1 * cols + cols - 2], __dadd_rn(sB, cs));
@@ -233,47 +295,59 @@ group_kernel(const LimbTable lt, int W, const GroupBuffers gb) {
         const unsigned overlap = __ballot_sync(0xffffffffu, both);
         if (overlap == 0) {
           if (lane < parts) {
-            sub[j1 * cols + lane] = __dadd_rn(sub[j1 * cols + lane], __dadd_rn(sub[j2 * cols + lane], 1.0));
+            const double moved = sub[j2 * cols + lane];
+            if (moved >= 0.0) {  // this id now lives in j1 instead of j2
+              const int id = static_cast<int>(moved);
+              if (owner[id * 2] == j2) owner[id * 2] = j1; else if (owner[id * 2 + 1] == j2) owner[id * 2 + 1] = j1;
+            }
+            sub[j1 * cols + lane] = __dadd_rn(sub[j1 * cols + lane], __dadd_rn(moved, 1.0));
           } else if (lane == parts) {
             sub[j1 * cols + cols - 2] = __dadd_rn(__dadd_rn(sub[j1 * cols + cols - 2], sub[j2 * cols + cols - 2]), cs);
           } else if (lane == parts + 1) {
             sub[j1 * cols + cols - 1] = __dadd_rn(sub[j1 * cols + cols - 1], sub[j2 * cols + cols - 1]);
           }
-          __syncwarp();
-          if (lane < cols) {  // np.delete(subset, j2, 0): every lane shifts its own column upwards
-            for (int r = j2; r < rows - 1; ++r) sub[r * cols + lane] = sub[(r + 1) * cols + lane];
-          }
-          --rows;
+          if (lane == 0) s_alive[j2 >> 5] &= ~(1u << (j2 & 31));  // np.delete(subset, j2, 0)
         } else if (lane == 0) {
+          const double old = sub[j1 * cols + ib];
+          if (old != partB) {
+            if (old >= 0.0) owner_remove(static_cast<int>(old), j1);
+            owner_add(idB, j1);
+          }
           sub[j1 * cols + ib] = partB;
           sub[j1 * cols + cols - 1] = __dadd_rn(sub[j1 * cols + cols - 1], 1.0);
           sub[j1 * cols + cols - 2] = __dadd_rn(sub[j1 * cols + cols - 2], __dadd_rn(sB, cs));
         }
       } else if (k < lt.njoint - 2) {
-        if (rows < gb.max_person) {
+        if (slots < gb.max_person && slots < kMaxSlots) {
           if (lane < cols) {
             double v = -1.0;
             if (lane == ia) v = partA;
             if (lane == ib) v = partB;
             if (lane == cols - 1) v = 2.0;
             if (lane == cols - 2) v = __dadd_rn(__dadd_rn(__dadd_rn(0.0, sA), sB), cs);
-            sub[rows * cols + lane] = v;
+            sub[slots * cols + lane] = v;
           }
-          ++rows;
+          if (lane == 0) {
+            owner_add(idA, slots);
+            owner_add(idB, slots);
+            s_alive[slots >> 5] |= 1u << (slots & 31);
+          }
+          ++slots;
         } else if (lane == 0) {
-          atomicExch(gb.overflow, 4);
+          atomicMax(gb.overflow, 4);
         }
       }
       __syncwarp();
     }
   }
-  // ---- pruning (body.py:227-231), order preserved
+  // ---- np.delete + pruning (body.py:227-231): compact the live rows that pass, order preserved
   int kept = 0;
-  for (int r = 0; r < rows; ++r) {
+  for (int r = 0; r < slots; ++r) {
+    const bool alive = (s_alive[r >> 5] >> (r & 31)) & 1u;
     const double cnt = sub[r * cols + cols - 1];
     const double sc = sub[r * cols + cols - 2];
-    const bool drop = cnt < 4.0 || __ddiv_rn(sc, cnt) < 0.4;
-    if (!drop) {
+    const bool keep = alive && !(cnt < 4.0 || __ddiv_rn(sc, cnt) < 0.4);
+    if (keep) {
       if (kept != r && lane < cols) sub[kept * cols + lane] = sub[r * cols + lane];
       ++kept;
     }
@@ -284,16 +358,16 @@ group_kernel(const LimbTable lt, int W, const GroupBuffers gb) {
 
 int launch_paf_score(const ScaleSet& paf, const LimbTable& lt, int N, int H, int W, double thre2, int mid_num,
                      const GroupBuffers& gb, cudaStream_t st) {
-  if (mid_num != 10 || gb.cap > kPeakCap || gb.cand_cap > kCandCap) return 1;
-  if (cudaMemsetAsync(gb.cand_count, 0, sizeof(int) * N * lt.nlimbs, st) != cudaSuccess) return 1;
-  const dim3 grid(32, lt.nlimbs, N);
+  if (mid_num != 10 || gb.cap > kPeakCap) return 1;
+  const dim3 grid(48, lt.nlimbs, N);
   paf_score_kernel<<<grid, 256, 0, st>>>(paf, lt, H, W, lt.njoint - 1, thre2, gb);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
 int launch_group(const LimbTable& lt, int N, int W, const GroupBuffers& gb, cudaStream_t st) {
-  if (gb.cap > kPeakCap || gb.cand_cap > kCandCap || lt.njoint + 1 > 32) return 1;
-  group_kernel<<<N, 256, 0, st>>>(lt, W, gb);
+  if (gb.cap > kPeakCap || lt.njoint + 1 > 32) return 1;
+  match_kernel<<<dim3(lt.nlimbs, N), 256, 0, st>>>(lt, gb);
+  assemble_kernel<<<N, 256, 0, st>>>(lt, W, gb);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 

@@ -36,20 +36,19 @@ struct GroupBuffers {
   const int* counts;     // [N*parts]
   const uint32_t* keys;  // [N*parts*cap]  y*W+x
   const double* scores;  // [N*parts*cap]  unsmoothed heat value
-  // scratch: connection candidates per (frame, limb)
-  int cand_cap;          // <= 2048
-  int* cand_count;       // [N*nlimbs]
-  uint32_t* cand_pair;   // [N*nlimbs*cand_cap]  i*nB+j
-  double* cand_score;    // [N*nlimbs*cand_cap]
+  // scratch: dense connection scores per (frame, limb): [i*nB+j] = score, or -1 when the pair is rejected
+  long long pair_cap;    // elements available per (frame, limb); nA*nB above this raises overflow code 3
+  double* pair_score;    // [N*nlimbs*pair_cap]
   // scratch: chosen connections per (frame, limb)
   int* conn_count;       // [N*nlimbs]
   int* conn_ij;          // [N*nlimbs*cap*2]
   double* conn_score;    // [N*nlimbs*cap]
+  int* owner;            // [N*max_cand*2] scratch: row slots holding each candidate id
   // outputs
   int max_cand;          // rows available per frame in candidate
   double* candidate;     // [N*max_cand*4]  x, y, score, id
   int* n_cand;           // [N]
-  int max_person;
+  int max_person;        // row slots available per frame (rows ever created, dead ones included)
   double* subset;        // [N*max_person*(njoint+1)]
   int* n_person;         // [N]
   int* overflow;         // [1] set to non-zero if any capacity was exceeded

@@ -65,6 +65,27 @@ class KeypointExtractor(object):
             per_frame[fi].append(p)
         return [(c, s, per_frame[i]) for i, (c, s) in enumerate(bodies)]
 
+    def batch_device(self, frames_dev, hand_boxes):
+        """Same as batch() for frames already resident on the device (uint8 cuda tensor [n,H,W,3]); the hand boxes
+        must be given because util.handDetect needs the host copy of candidate/subset either way."""
+        bodies = self.body.batch_device(frames_dev)
+        if self.hand is None:
+            return [(c, s, []) for c, s in bodies]
+        crops, owner = [], []
+        for fi, (cand, sub) in enumerate(bodies):
+            boxes = hand_boxes[fi] if hand_boxes is not None else util.handDetect(cand, sub, frames_dev[fi])
+            for (x, y, w, is_left) in boxes:
+                crops.append(frames_dev[fi, y:y + w, x:x + w, :].contiguous())
+                owner.append((fi, x, y))
+        peaks = self.hand.batch_device(crops) if crops else []
+        per_frame = [[] for _ in range(frames_dev.shape[0])]
+        for (fi, x, y), p in zip(owner, peaks):
+            p = p.copy()
+            p[:, 0] = np.where(p[:, 0] == 0, p[:, 0], p[:, 0] + x)
+            p[:, 1] = np.where(p[:, 1] == 0, p[:, 1], p[:, 1] + y)
+            per_frame[fi].append(p)
+        return [(c, s, per_frame[i]) for i, (c, s) in enumerate(bodies)]
+
     def run_sharded(self, frames, rank, world_size, batch_size=8, hand_boxes=None):
         """Processes this rank's shard of `frames` in batches; returns results in shard order."""
         idx = shard_indices(len(frames), rank, world_size)

@@ -85,8 +85,14 @@ class Hand(object):
         if not crops:
             return []
         with torch.cuda.device(self.device):
-            dev_crops = [torch.from_numpy(c).to(self.device, non_blocking=True) for c in crops]
+            return self.batch_device([torch.from_numpy(c).to(self.device, non_blocking=True) for c in crops])
+
+    def batch_device(self, dev_crops):
+        """dev_crops: list of contiguous uint8 cuda tensors [h,w,3] -> list of int64 arrays [21,2]."""
+        if not dev_crops:
+            return []
+        with torch.cuda.device(self.device):
             per_crop = self.network_outputs(dev_crops)
-            outs = [self.postprocess(per_crop[i], crops[i].shape[0], crops[i].shape[1]) for i in range(len(crops))]
+            outs = [self.postprocess(per_crop[i], dev_crops[i].shape[0], dev_crops[i].shape[1]) for i in range(len(dev_crops))]
             stacked = torch.stack(outs).cpu().numpy()
-        return [stacked[i].astype(np.int64) for i in range(len(crops))]
+        return [stacked[i].astype(np.int64) for i in range(len(dev_crops))]

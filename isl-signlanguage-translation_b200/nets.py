@@ -226,7 +226,9 @@ class _Instance:
     def __init__(self, net, n, h, w):
         L = _lib.lib()
         dev = net.device
+        self.net = net
         self.n, self.h, self.w = n, h, w
+        self.flops_algorithmic = algorithmic_flops(net.kind, n, h, w)
         self.input = torch.empty((n, 3, h, w), dtype=torch.float32, device=dev)
         self.bufs = {}
         for name, (ch, level) in net.program.bufs.items():
@@ -275,7 +277,14 @@ class _Instance:
         self.launches = L.islpose_plan_num_launches(handle)
 
     def run(self):
+        timing = self.net.timing
+        if timing is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         _lib.check(_lib.lib().islpose_plan_run(self.handle, _lib.stream_ptr()), "islpose_plan_run")
+        if timing is not None:
+            e1.record()
+            timing.append((e0, e1, self.flops_algorithmic, self.launches))
 
     def __del__(self):
         try:
@@ -335,6 +344,7 @@ class PoseNet:
                 slope[:cout] = self._flat[s["prelu"] + ".weight"]
             self.packed.append((wt, bias.to(self.device), slope.to(self.device)))
         self._instances = {}
+        self.timing = None   # set to a list to collect (start, end, flops) CUDA-event pairs around every plan replay
 
     # ---- reference nn.Module surface -------------------------------------------------------------------
     def parameters(self):
