@@ -36,8 +36,11 @@ typedef struct islpose_conv_desc {
   const void* in;       /* bf16 NHWC, points at the first channel of the input slice at pixel 0 */
   int32_t in_c;         /* channels of the slice (multiple of 8) */
   int32_t in_cstride;   /* channels per pixel of the buffer holding the slice (multiple of 8) */
+  int32_t in_c_readable;/* channels readable from the slice start (>= in_c, 0 = in_c); if the next multiple of 64 fits,
+                           all TMA boxes stay in bounds (faster); channels past in_c must be finite and meet zero weights */
+  int32_t w_cin;        /* Cin stride of the packed weights (>= in_c, multiple of 8; 0 = in_c), zero padded */
   int32_t n, h, w;      /* batch and spatial size (stride 1, "same" padding: output has the same size) */
-  const void* weights;  /* bf16 [k*k][cout][in_c]: nn.Conv2d weight [cout][cin][ky][kx] re-packed tap-major */
+  const void* weights;  /* bf16 [k*k][cout][w_cin]: nn.Conv2d weight [cout][cin][ky][kx] re-packed tap-major */
   int32_t cout;
   int32_t ksize;        /* 1, 3 or 7 (src/model.py:35-37) */
   const float* bias;    /* fp32, at least 512 entries, zero padded */

@@ -12,7 +12,8 @@ MAX_SCALES = 8
 
 
 class ConvDesc(C.Structure):
-    _fields_ = [("in_", C.c_void_p), ("in_c", C.c_int32), ("in_cstride", C.c_int32), ("n", C.c_int32), ("h", C.c_int32),
+    _fields_ = [("in_", C.c_void_p), ("in_c", C.c_int32), ("in_cstride", C.c_int32), ("in_c_readable", C.c_int32),
+                ("w_cin", C.c_int32), ("n", C.c_int32), ("h", C.c_int32),
                 ("w", C.c_int32), ("weights", C.c_void_p), ("cout", C.c_int32), ("ksize", C.c_int32),
                 ("bias", C.c_void_p), ("slope", C.c_void_p), ("out_bf16", C.c_void_p), ("out_cstride", C.c_int32),
                 ("out_f32", C.c_void_p), ("out_f32_channels", C.c_int32), ("n_tile", C.c_int32), ("stages", C.c_int32),

@@ -56,6 +56,7 @@ class Body(object):
         self.device = self.model.device
         self._gauss = (C.c_double * 25)(*gaussian_weights().tolist())
         self._work = {}
+        self._streams = []
         self.last_overflow = 0
 
     # ------------------------------------------------------------------------------------------------
@@ -95,17 +96,39 @@ class Body(object):
         return ws
 
     def network_outputs(self, frames_dev, H, W):
-        """Runs every scale; returns [(paf, heat, geometry)] with the plans' float32 NCHW output tensors."""
+        """Runs every scale; returns [(paf, heat, geometry)] with the plans' float32 NCHW output tensors.
+        The scales are independent (body.py:51 loops over them sequentially), so each runs on its own stream: the
+        small-scale networks are latency-bound (a few dozen CTAs per layer) and hide under the large ones."""
         L = _lib.lib()
         n = frames_dev.shape[0]
+        geoms = scale_geometry(H, W, self.scale_search, self.boxsize)
+        insts = [self.model.instance(n, hp, wp) for (_, _, _, hp, wp) in geoms]
+        main = torch.cuda.current_stream()
+        while len(self._streams) < len(geoms):
+            self._streams.append(torch.cuda.Stream(device=self.device))
+        timing = self.model.timing
+        if timing is not None:
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record(main)
+        fork = torch.cuda.Event()
+        fork.record(main)
         outs = []
-        for (m, rh, rw, hp, wp) in scale_geometry(H, W, self.scale_search, self.boxsize):
-            inst = self.model.instance(n, hp, wp)
-            _lib.check(L.islpose_resize_pad_normalize(_lib.ptr(frames_dev), n, H, W, m, rh, rw, hp, wp,
-                                                      _lib.ptr(inst.input), None, _lib.stream_ptr()),
-                       "islpose_resize_pad_normalize")
-            inst.run()
+        for i, ((m, rh, rw, hp, wp), inst) in enumerate(zip(geoms, insts)):
+            side = self._streams[i] if len(geoms) > 1 else main
+            with torch.cuda.stream(side):
+                side.wait_event(fork)
+                _lib.check(L.islpose_resize_pad_normalize(_lib.ptr(frames_dev), n, H, W, m, rh, rw, hp, wp,
+                                                          _lib.ptr(inst.input), None, _lib.stream_ptr()),
+                           "islpose_resize_pad_normalize")
+                inst.run()
+                if side is not main:
+                    done = torch.cuda.Event()
+                    done.record(side)
+                    main.wait_event(done)
             outs.append((inst.outputs[0], inst.outputs[1], (rh, rw, hp, wp)))
+        if timing is not None:
+            t1.record(main)
+            timing.append((t0, t1, sum(i.flops_algorithmic for i in insts), sum(i.launches for i in insts) + len(insts)))
         return outs
 
     def _scales_struct(self, maps, which):

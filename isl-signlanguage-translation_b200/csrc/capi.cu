@@ -123,6 +123,8 @@ int islpose_plan_add_conv(islpose_plan* plan, const islpose_conv_desc* d) {
   c.in = static_cast<const __nv_bfloat16*>(d->in);
   c.in_c = d->in_c;
   c.in_cstride = d->in_cstride;
+  c.in_c_readable = d->in_c_readable;
+  c.w_cin = d->w_cin;
   c.N = d->n;
   c.H = d->h;
   c.W = d->w;

@@ -301,7 +301,10 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
 
   // Tensor maps. A: (C, W, H, N) over the NHWC slice; B: (Cin, Cout, taps) over the packed weights.
   {
-    cuuint64_t gdim[4] = {static_cast<cuuint64_t>(d.in_c), static_cast<cuuint64_t>(d.W),
+    int c_dim = d.in_c;
+    const int c64 = (d.in_c + 63) / 64 * 64;
+    if (d.in_c_readable >= c64) c_dim = c64;
+    cuuint64_t gdim[4] = {static_cast<cuuint64_t>(c_dim), static_cast<cuuint64_t>(d.W),
                           static_cast<cuuint64_t>(d.H), static_cast<cuuint64_t>(d.N)};
     cuuint64_t gstr[3] = {static_cast<cuuint64_t>(d.in_cstride) * 2,
                           static_cast<cuuint64_t>(d.in_cstride) * 2 * d.W,
@@ -314,9 +317,11 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
     if (r != CUDA_SUCCESS) return fail(err, errlen, "conv: activation tensor map rejected (CUresult %lld)", r);
   }
   {
-    cuuint64_t gdim[3] = {static_cast<cuuint64_t>(d.in_c), static_cast<cuuint64_t>(d.cout),
+    const int w_cin = d.w_cin > 0 ? d.w_cin : d.in_c;
+    if (w_cin < d.in_c || w_cin % 8 != 0) return fail(err, errlen, "conv: bad weight Cin stride %lld", w_cin);
+    cuuint64_t gdim[3] = {static_cast<cuuint64_t>(w_cin), static_cast<cuuint64_t>(d.cout),
                           static_cast<cuuint64_t>(d.ksize * d.ksize)};
-    cuuint64_t gstr[2] = {static_cast<cuuint64_t>(d.in_c) * 2, static_cast<cuuint64_t>(d.in_c) * 2 * d.cout};
+    cuuint64_t gstr[2] = {static_cast<cuuint64_t>(w_cin) * 2, static_cast<cuuint64_t>(w_cin) * 2 * d.cout};
     cuuint32_t box[3] = {64, static_cast<cuuint32_t>(n_tile), 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = encode(&out->tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(d.w), gdim, gstr,

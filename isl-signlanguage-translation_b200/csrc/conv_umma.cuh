@@ -29,6 +29,10 @@ struct ConvDesc {
   const __nv_bfloat16* in;  // points at channel c0 of pixel (0,0,0)
   int in_c;                 // channels in the slice (multiple of 8)
   int in_cstride;           // channels per pixel of the underlying buffer (multiple of 8)
+  int in_c_readable;        // channels that may be read from the slice start (>= in_c; 0 = in_c). When the next
+                            // multiple of 64 fits, every TMA box is fully in bounds (partially out-of-bounds boxes
+                            // in the innermost dimension were measured ~2x slower); the extra channels meet zero weights
+  int w_cin;                // Cin stride of the packed weights (>= in_c, multiple of 8; 0 = in_c)
   int N, H, W;
   // weights
   const __nv_bfloat16* w;  // [k*k][cout][in_c]

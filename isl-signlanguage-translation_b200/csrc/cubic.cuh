@@ -66,8 +66,25 @@ struct Axis2 {
   int lo[5];       // clamped stride-8 indices of the 5-wide window
 };
 
+// Stage 1 is an exact x8 up-sampling (scale 0.125), so the source fraction of up-sampled index u depends on
+// u mod 8 only and the integer part is ((u + 4) >> 3) - 1. The 8 weight sets are computed once per block with the
+// very same float code (bit-identical to evaluating them per tap) and kept in shared memory.
+__device__ __forceinline__ void fill_phase_table(float (*tab)[4]) {
+  if (threadIdx.x < 8) {
+    int su;
+    float g;
+    cubic_src(static_cast<int>(threadIdx.x), 0.125, su, g);
+    float c[4];
+    cubic_coeffs(g, c);
+    tab[threadIdx.x][0] = c[0];
+    tab[threadIdx.x][1] = c[1];
+    tab[threadIdx.x][2] = c[2];
+    tab[threadIdx.x][3] = c[3];
+  }
+}
+
 // d: output coordinate; scale2: stage-2 src/dst ratio; n_mid: cropped up-sampled extent; n_low: stride-8 extent.
-__device__ __forceinline__ void make_axis2(int d, double scale2, int n_mid, int n_low, Axis2& a) {
+__device__ __forceinline__ void make_axis2(int d, double scale2, int n_mid, int n_low, const float (*tab)[4], Axis2& a) {
   int s;
   float frac;
   cubic_src(d, scale2, s, frac);
@@ -76,10 +93,12 @@ __device__ __forceinline__ void make_axis2(int d, double scale2, int n_mid, int 
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int u = clampi(s - 1 + i, 0, n_mid - 1);
-    int su;
-    float g;
-    cubic_src(u, 0.125, su, g);
-    cubic_coeffs(g, a.w1[i]);
+    const int su = ((u + 4) >> 3) - 1;
+    const float* w = tab[u & 7];
+    a.w1[i][0] = w[0];
+    a.w1[i][1] = w[1];
+    a.w1[i][2] = w[2];
+    a.w1[i][3] = w[3];
     if (i == 0) first = su - 1;
     a.off[i] = su - 1 - first;  // 0 or 1: the four taps span at most 3 up-sampled pixels = < 1 cell
   }

@@ -15,6 +15,9 @@ namespace islpose {
 
 __global__ void __launch_bounds__(256)
 paf_score_kernel(const ScaleSet ss, const LimbTable lt, int H, int W, int parts, double thre2, const GroupBuffers gb) {
+  __shared__ float s_tab[8][4];
+  fill_phase_table(s_tab);
+  __syncthreads();
   const int n = blockIdx.z;
   const int k = blockIdx.y;
   const int lane = threadIdx.x & 31;
@@ -33,23 +36,27 @@ paf_score_kernel(const ScaleSet ss, const LimbTable lt, int H, int W, int parts,
   const long long tail_start = (static_cast<long long>(W) * C) / 4 * 4;
   const float fS = static_cast<float>(ss.count);
   const int slot_base = n * lt.nlimbs + k;
+  const int chx = lt.cx[k], chy = lt.cy[k];
 
-  for (long long pair = blockIdx.x * 8 + warp; pair < total; pair += static_cast<long long>(gridDim.x) * 8) {
-    const int i = static_cast<int>(pair / nB);
-    const int j = static_cast<int>(pair - static_cast<long long>(i) * nB);
-    const uint32_t ka = keyA[i], kb = keyB[j];
-    const int ax = ka % W, ay = ka / W, bx = kb % W, by = kb / W;
-    const long long dxi = bx - ax, dyi = by - ay;
-    double norm = sqrt(static_cast<double>(dxi * dxi + dyi * dyi));
-    norm = fmax(0.001, norm);
-    const double ux = __ddiv_rn(static_cast<double>(dxi), norm);
-    const double uy = __ddiv_rn(static_cast<double>(dyi), norm);
-
-    // lanes 0..9: x channel of sample t, lanes 10..19: y channel
-    double val = 0.0;
-    if (lane < 20) {
-      const int t = lane % 10;
-      const int ch = lane < 10 ? lt.cx[k] : lt.cy[k];
+  // three pairs per warp: lane = 10 * group + sample; one lane evaluates both PAF channels of its sample
+  // (they share the cubic taps of the sample position)
+  const int grp = lane / 10;
+  const int t = lane - grp * 10;
+  const int gbase = grp * 10;
+  for (long long base = (static_cast<long long>(blockIdx.x) * 8 + warp) * 3; base < total;
+       base += static_cast<long long>(gridDim.x) * 8 * 3) {
+    const long long pair = base + grp;
+    const bool live = grp < 3 && pair < total;
+    double mid = 0.0, norm = 1.0;
+    if (live) {
+      const int i = static_cast<int>(pair / nB);
+      const int j = static_cast<int>(pair - static_cast<long long>(i) * nB);
+      const uint32_t ka = keyA[i], kb = keyB[j];
+      const int ax = ka % W, ay = ka / W, bx = kb % W, by = kb / W;
+      const long long dxi = bx - ax, dyi = by - ay;
+      norm = fmax(0.001, sqrt(static_cast<double>(dxi * dxi + dyi * dyi)));
+      const double ux = __ddiv_rn(static_cast<double>(dxi), norm);
+      const double uy = __ddiv_rn(static_cast<double>(dyi), norm);
       // np.linspace(a, b, 10): t * ((b - a) / 9) + a, last sample forced to b
       const double stepx = __ddiv_rn(static_cast<double>(dxi), 9.0);
       const double stepy = __ddiv_rn(static_cast<double>(dyi), 9.0);
@@ -57,63 +64,55 @@ paf_score_kernel(const ScaleSet ss, const LimbTable lt, int H, int W, int parts,
       const double ys = t == 9 ? static_cast<double>(by) : __dadd_rn(__dmul_rn(static_cast<double>(t), stepy), static_cast<double>(ay));
       const int rx = static_cast<int>(rint(xs));  // int(round()) = round half to even
       const int ry = static_cast<int>(rint(ys));
-      const bool tail = static_cast<long long>(rx) * C + ch >= tail_start;
+      const bool tailx = static_cast<long long>(rx) * C + chx >= tail_start;
+      const bool taily = static_cast<long long>(rx) * C + chy >= tail_start;
+      double vx = 0.0, vy = 0.0;
       for (int s = 0; s < ss.count; ++s) {
         const ScaleGeom& g = ss.g[s];
         Axis2 sx, sy;
-        make_axis2(rx, g.sx, g.wc, g.gw, sx);
-        make_axis2(ry, g.sy, g.hc, g.gh, sy);
-        const float v = sample2(g.low + (static_cast<long long>(n) * C + ch) * g.gh * g.gw, g.gw, sx, sy, tail);
-        val = __dadd_rn(val, static_cast<double>(__fdiv_rn(v, fS)));  // paf_avg += paf / S  (body.py:81)
+        make_axis2(rx, g.sx, g.wc, g.gw, s_tab, sx);
+        make_axis2(ry, g.sy, g.hc, g.gh, s_tab, sy);
+        const float* img = g.low + static_cast<long long>(n) * C * g.gh * g.gw;
+        const long long plane = static_cast<long long>(g.gh) * g.gw;
+        // paf_avg += paf / S  (body.py:81): float32 division, float64 accumulation
+        vx = __dadd_rn(vx, static_cast<double>(__fdiv_rn(sample2(img + chx * plane, g.gw, sx, sy, tailx), fS)));
+        vy = __dadd_rn(vy, static_cast<double>(__fdiv_rn(sample2(img + chy * plane, g.gw, sx, sy, taily), fS)));
       }
+      mid = __dadd_rn(__dmul_rn(vx, ux), __dmul_rn(vy, uy));
     }
-    const double vx = __shfl_sync(0xffffffffu, val, lane % 10);
-    const double vy = __shfl_sync(0xffffffffu, val, lane % 10 + 10);
-    const double mid = __dadd_rn(__dmul_rn(vx, ux), __dmul_rn(vy, uy));
-    const unsigned above = __ballot_sync(0xffffffffu, lane < 10 && mid > thre2);
+    const unsigned above = __ballot_sync(0xffffffffu, live && mid > thre2);
     double sum = 0.0;  // Python sum(): left to right from 0
 #pragma unroll
-    for (int t = 0; t < 10; ++t) sum = __dadd_rn(sum, __shfl_sync(0xffffffffu, mid, t));
-    if (lane == 0) {
+    for (int q = 0; q < 10; ++q) sum = __dadd_rn(sum, __shfl_sync(0xffffffffu, mid, (gbase + q) & 31));
+    if (live && t == 0) {
       const double prior = __dadd_rn(__ddiv_rn(sum, 10.0),
                                      fmin(__dsub_rn(__ddiv_rn(__dmul_rn(0.5, static_cast<double>(H)), norm), 1.0), 0.0));
+      const int cnt = __popc((above >> gbase) & 0x3ffu);
       // > 0.8 * mid_num samples above thre2 and a positive score, else the pair is not a candidate
-      gb.pair_score[static_cast<long long>(slot_base) * gb.pair_cap + pair] = (__popc(above) > 8 && prior > 0.0) ? prior : -1.0;
+      gb.pair_score[static_cast<long long>(slot_base) * gb.pair_cap + pair] = (cnt > 8 && prior > 0.0) ? prior : -1.0;
     }
   }
 }
 
 constexpr int kPeakCap = 1024;
 
-struct RowBest {
-  double v;
-  int i, j;
-};
-// larger score first; equal scores resolve to the smaller i*nB+j (rows differ -> smaller i; same row -> smaller j)
-__device__ __forceinline__ RowBest pick(RowBest a, RowBest b) {
-  if (b.v > a.v) return b;
-  if (b.v == a.v && (b.i < a.i || (b.i == a.i && b.j < a.j))) return b;
-  return a;
-}
-__device__ __forceinline__ RowBest warp_pick(RowBest r) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    RowBest t;
-    t.v = __shfl_xor_sync(0xffffffffu, r.v, o);
-    t.i = __shfl_xor_sync(0xffffffffu, r.i, o);
-    t.j = __shfl_xor_sync(0xffffffffu, r.j, o);
-    r = pick(r, t);
-  }
-  return r;
-}
-
+// Greedy matching in parallel rounds. With a strict total order on the candidate pairs (score descending, then
+// i*nB+j ascending = the reference's enumeration order, which Python's stable sort preserves for equal scores),
+// "walk the sorted list and take a pair when both ends are free" (body.py:166-173) yields the same set as:
+// repeat { accept every free pair that is the best of its row AND the best of its column among the free pairs }.
+// (The best free pair overall is always such a pair, an accepted pair can never be blocked by a better one, and
+// accepting it blocks exactly the pairs the sequential walk would skip.) The walk stops at min(nA, nB) connections,
+// which is also when no free row or no free column is left. Accepted connections are finally sorted into the
+// order the walk would have produced them in, because the person assembly consumes them in that order.
 __global__ void __launch_bounds__(256)
 match_kernel(const LimbTable lt, const GroupBuffers gb) {
-  __shared__ double s_best[kPeakCap];
-  __shared__ int s_bestj[kPeakCap];
-  __shared__ uint32_t s_usedB[kPeakCap / 32];
-  __shared__ RowBest s_red[8];
-  __shared__ RowBest s_win;
+  __shared__ double s_rowv[kPeakCap];
+  __shared__ int s_rowj[kPeakCap];
+  __shared__ int s_coli[kPeakCap];
+  __shared__ uint32_t s_usedA[kPeakCap / 32], s_usedB[kPeakCap / 32];
+  __shared__ double s_cv[kPeakCap];   // accepted connections: score, i, j
+  __shared__ int s_ci[kPeakCap], s_cj[kPeakCap];
+  __shared__ int s_made, s_round;
   const int k = blockIdx.x, n = blockIdx.y;
   const int parts = lt.njoint - 1;
   const int slot = n * lt.nlimbs + k;
@@ -129,68 +128,117 @@ match_kernel(const LimbTable lt, const GroupBuffers gb) {
     return;
   }
   const double* sc = gb.pair_score + static_cast<long long>(slot) * gb.pair_cap;
-  for (int i = threadIdx.x; i < kPeakCap / 32; i += blockDim.x) s_usedB[i] = 0;
+  for (int i = threadIdx.x; i < kPeakCap / 32; i += blockDim.x) {
+    s_usedA[i] = 0;
+    s_usedB[i] = 0;
+  }
+  if (threadIdx.x == 0) s_made = 0;
   __syncthreads();
 
-  auto scan_row = [&](int i) {  // whole warp: best free partner of row i
-    RowBest r;
-    r.v = -1.0;
-    r.i = i;
-    r.j = 0x7fffffff;
-    for (int j = lane; j < nB; j += 32) {
-      if ((s_usedB[j >> 5] >> (j & 31)) & 1u) continue;
-      RowBest c;
-      c.v = sc[static_cast<long long>(i) * nB + j];
-      c.i = i;
-      c.j = j;
-      r = pick(r, c);
+  while (true) {
+    // best free column of every free row (one warp per row, lanes across columns: coalesced)
+    for (int i = warp; i < nA; i += 8) {
+      if ((s_usedA[i >> 5] >> (i & 31)) & 1u) continue;
+      double bv = -1.0;
+      int bj = 0x7fffffff;
+      const double* row = sc + static_cast<long long>(i) * nB;
+      for (int j = lane; j < nB; j += 32) {
+        if ((s_usedB[j >> 5] >> (j & 31)) & 1u) continue;
+        const double v = row[j];
+        if (v > bv) {  // ascending j inside a lane: strict > keeps the smallest j among equals
+          bv = v;
+          bj = j;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+        if (ov > bv || (ov == bv && oj < bj)) {
+          bv = ov;
+          bj = oj;
+        }
+      }
+      if (lane == 0) {
+        s_rowv[i] = bv;
+        s_rowj[i] = bj;
+      }
     }
-    r = warp_pick(r);
-    if (lane == 0) {
-      s_best[i] = r.v;
-      s_bestj[i] = r.j;
+    // best free row of every free column (one thread per column, adjacent lanes read adjacent addresses)
+    for (int j = threadIdx.x; j < nB; j += blockDim.x) {
+      int bi = -1;
+      if (!((s_usedB[j >> 5] >> (j & 31)) & 1u)) {
+        double bv = -1.0;
+        for (int i = 0; i < nA; ++i) {
+          if ((s_usedA[i >> 5] >> (i & 31)) & 1u) continue;
+          const double v = sc[static_cast<long long>(i) * nB + j];
+          if (v > bv) {  // ascending i: strict > keeps the smallest i among equals
+            bv = v;
+            bi = i;
+          }
+        }
+        if (!(bv > 0.0)) bi = -1;
+      }
+      s_coli[j] = bi;
     }
-  };
-  for (int i = warp; i < nA; i += 8) scan_row(i);
-  __syncthreads();
-
-  const int limit = nA < nB ? nA : nB;
-  int made = 0;
-  while (made < limit) {
-    RowBest r;
-    r.v = -1.0;
-    r.i = 0x7fffffff;
-    r.j = 0x7fffffff;
-    for (int i = threadIdx.x; i < nA; i += blockDim.x) {
-      RowBest c;
-      c.v = s_best[i];
-      c.i = i;
-      c.j = s_bestj[i];
-      r = pick(r, c);
-    }
-    r = warp_pick(r);
-    if (lane == 0) s_red[warp] = r;
+    if (threadIdx.x == 0) s_round = 0;
     __syncthreads();
-    if (threadIdx.x == 0) {
-      RowBest w = s_red[0];
-      for (int q = 1; q < 8; ++q) w = pick(w, s_red[q]);
-      s_win = w;
-      if (w.v > 0.0) {
-        gb.conn_ij[(static_cast<long long>(slot) * gb.cap + made) * 2 + 0] = w.i;
-        gb.conn_ij[(static_cast<long long>(slot) * gb.cap + made) * 2 + 1] = w.j;
-        gb.conn_score[static_cast<long long>(slot) * gb.cap + made] = w.v;
-        s_best[w.i] = -2.0;  // row taken
-        s_usedB[w.j >> 5] |= 1u << (w.j & 31);
+    for (int i = threadIdx.x; i < nA; i += blockDim.x) {
+      if ((s_usedA[i >> 5] >> (i & 31)) & 1u) continue;
+      const double v = s_rowv[i];
+      const int j = s_rowj[i];
+      if (v > 0.0 && s_coli[j] == i) {
+        const int pos = atomicAdd(&s_made, 1);
+        s_cv[pos] = v;
+        s_ci[pos] = i;
+        s_cj[pos] = j;
+        atomicOr(&s_usedA[i >> 5], 1u << (i & 31));
+        atomicOr(&s_usedB[j >> 5], 1u << (j & 31));
+        s_round = 1;
       }
     }
     __syncthreads();
-    const RowBest w = s_win;
-    if (!(w.v > 0.0)) break;  // no candidate left among the free pairs
-    ++made;
-    for (int i = warp; i < nA; i += 8) {
-      if (s_best[i] > 0.0 && s_bestj[i] == w.j) scan_row(i);  // this row just lost its cached partner
-    }
+    if (s_round == 0) break;
     __syncthreads();
+  }
+  // order of the sequential walk: score descending, pair index ascending
+  const int made = s_made;
+  int m2 = 1;
+  while (m2 < made) m2 <<= 1;
+  for (int i = made + threadIdx.x; i < m2; i += blockDim.x) {
+    s_cv[i] = -1.0;
+    s_ci[i] = 0x7fffffff;
+    s_cj[i] = 0;
+  }
+  __syncthreads();
+  for (int size = 2; size <= m2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = threadIdx.x; i < m2; i += blockDim.x) {
+        const int j = i ^ stride;
+        if (j > i) {
+          const bool up = (i & size) == 0;
+          const double a = s_cv[i], b = s_cv[j];
+          const long long pa = static_cast<long long>(s_ci[i]) * nB + s_cj[i];
+          const long long pb = static_cast<long long>(s_ci[j]) * nB + s_cj[j];
+          const bool j_first = (b > a) || (b == a && pb < pa);
+          if (j_first == up) {
+            s_cv[i] = b;
+            s_cv[j] = a;
+            const int ti = s_ci[i], tj = s_cj[i];
+            s_ci[i] = s_ci[j];
+            s_cj[i] = s_cj[j];
+            s_ci[j] = ti;
+            s_cj[j] = tj;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int c = threadIdx.x; c < made; c += blockDim.x) {
+    gb.conn_ij[(static_cast<long long>(slot) * gb.cap + c) * 2 + 0] = s_ci[c];
+    gb.conn_ij[(static_cast<long long>(slot) * gb.cap + c) * 2 + 1] = s_cj[c];
+    gb.conn_score[static_cast<long long>(slot) * gb.cap + c] = s_cv[c];
   }
   if (threadIdx.x == 0) gb.conn_count[slot] = made;
 }

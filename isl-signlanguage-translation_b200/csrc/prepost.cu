@@ -133,6 +133,9 @@ __global__ void maxpool2x2_kernel(const __nv_bfloat16* __restrict__ in, int N, i
 constexpr int kChunk = 4;
 __global__ void __launch_bounds__(256)
 heat_accumulate_kernel(const ScaleSet ss, int N, int H, int W, int parts, int q1, double* __restrict__ out) {
+  __shared__ float s_tab[8][4];
+  fill_phase_table(s_tab);
+  __syncthreads();
   const int x = blockIdx.x * 32 + (threadIdx.x & 31);
   const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
   const int chunks = (parts + kChunk - 1) / kChunk;
@@ -148,8 +151,8 @@ heat_accumulate_kernel(const ScaleSet ss, int N, int H, int W, int parts, int q1
   for (int s = 0; s < ss.count; ++s) {
     const ScaleGeom& g = ss.g[s];
     Axis2 ax, ay;
-    make_axis2(x, g.sx, g.wc, g.gw, ax);
-    make_axis2(y, g.sy, g.hc, g.gh, ay);
+    make_axis2(x, g.sx, g.wc, g.gw, s_tab, ax);
+    make_axis2(y, g.sy, g.hc, g.gh, s_tab, ay);
     const long long plane = static_cast<long long>(g.gh) * g.gw;
 #pragma unroll
     for (int i = 0; i < kChunk; ++i) {

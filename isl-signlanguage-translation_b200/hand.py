@@ -29,6 +29,7 @@ class Hand(object):
         self.scale_search = [0.5, 1.0, 1.5, 2.0]   # hand.py:25
         self.boxsize, self.stride, self.padValue, self.thre = 368, 8, 128, 0.05
         self._gauss = (C.c_double * 25)(*gaussian_weights().tolist())
+        self._streams = []
 
     def __call__(self, oriImg):
         return self.batch([oriImg])[0]
@@ -40,22 +41,46 @@ class Hand(object):
         L = _lib.lib()
         geoms = [scale_geometry(c.shape[0], c.shape[1], self.scale_search, self.boxsize) for c in crops_dev]
         per_crop = [[] for _ in crops_dev]
+        main = torch.cuda.current_stream()
+        timing = self.model.timing
+        if timing is not None:
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record(main)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        flops = launches = 0
+        lane = 0
         for si in range(len(self.scale_search)):
             groups = {}
             for ci, g in enumerate(geoms):
                 groups.setdefault((g[si][3], g[si][4]), []).append(ci)
             for (hp, wp), members in groups.items():
+                # every (scale, input shape) group is an independent network replay: one stream each
+                while len(self._streams) <= lane:
+                    self._streams.append(torch.cuda.Stream(device=self.device))
+                side = self._streams[lane]
+                lane += 1
                 inst = self.model.instance(_pow2_at_least(len(members)), hp, wp)
-                for slot, ci in enumerate(members):
-                    m, rh, rw, _, _ = geoms[ci][si]
-                    c = crops_dev[ci]
-                    dst = C.c_void_p(inst.input.data_ptr() + slot * 3 * hp * wp * 4)
-                    _lib.check(L.islpose_resize_pad_normalize(_lib.ptr(c), 1, c.shape[0], c.shape[1], m, rh, rw, hp, wp,
-                                                              dst, None, _lib.stream_ptr()), "islpose_resize_pad_normalize")
-                inst.run()
+                with torch.cuda.stream(side):
+                    side.wait_event(fork)
+                    for slot, ci in enumerate(members):
+                        m, rh, rw, _, _ = geoms[ci][si]
+                        c = crops_dev[ci]
+                        dst = C.c_void_p(inst.input.data_ptr() + slot * 3 * hp * wp * 4)
+                        _lib.check(L.islpose_resize_pad_normalize(_lib.ptr(c), 1, c.shape[0], c.shape[1], m, rh, rw, hp, wp,
+                                                                  dst, None, _lib.stream_ptr()), "islpose_resize_pad_normalize")
+                    inst.run()
+                    done = torch.cuda.Event()
+                    done.record(side)
+                    main.wait_event(done)
+                flops += inst.flops_algorithmic * len(members) // inst.n
+                launches += inst.launches + len(members)
                 plane = 22 * (hp // 8) * (wp // 8)
                 for slot, ci in enumerate(members):
                     per_crop[ci].append((inst.outputs[0], slot * plane, (geoms[ci][si][1], geoms[ci][si][2], hp, wp)))
+        if timing is not None:
+            t1.record(main)
+            timing.append((t0, t1, flops, launches))
         return per_crop
 
     def postprocess(self, maps, h, w):
@@ -93,6 +118,23 @@ class Hand(object):
             return []
         with torch.cuda.device(self.device):
             per_crop = self.network_outputs(dev_crops)
-            outs = [self.postprocess(per_crop[i], dev_crops[i].shape[0], dev_crops[i].shape[1]) for i in range(len(dev_crops))]
+            # a crop's post-processing launches only 21 CTAs per kernel: spread the crops over a few streams
+            main = torch.cuda.current_stream()
+            fork = torch.cuda.Event()
+            fork.record(main)
+            lanes = min(len(dev_crops), 8)
+            while len(self._streams) < lanes:
+                self._streams.append(torch.cuda.Stream(device=self.device))
+            outs = []
+            for i in range(len(dev_crops)):
+                side = self._streams[i % lanes] if lanes > 1 else main
+                with torch.cuda.stream(side):
+                    side.wait_event(fork)
+                    outs.append(self.postprocess(per_crop[i], dev_crops[i].shape[0], dev_crops[i].shape[1]))
+            if lanes > 1:
+                for j in range(lanes):
+                    done = torch.cuda.Event()
+                    done.record(self._streams[j])
+                    main.wait_event(done)
             stacked = torch.stack(outs).cpu().numpy()
         return [stacked[i].astype(np.int64) for i in range(len(dev_crops))]

@@ -198,8 +198,22 @@ def build_program(kind):
     return p
 
 
+def _up64(c):
+    return (c + 63) // 64 * 64
+
+
 def _pack_weight(w, chan_map, in_c, first):
-    """nn.Conv2d weight [cout, cin, k, k] float32 -> bf16 [k*k, cout, in_c] in the buffer's channel order."""
+    """nn.Conv2d weight [cout, cin, k, k] float32 -> bf16 [k*k, cout, up64(in_c)] in the buffer's channel order
+    (zero beyond in_c, so that a 64-channel TMA box never leaves the tensor)."""
+    packed = _pack_weight_exact(w, chan_map, in_c, first)
+    if packed.shape[2] % 64 == 0 or first:
+        return packed
+    out = torch.zeros((packed.shape[0], packed.shape[1], _up64(in_c)), dtype=packed.dtype)
+    out[:, :, :in_c] = packed
+    return out.contiguous()
+
+
+def _pack_weight_exact(w, chan_map, in_c, first):
     cout, cin, k, _ = w.shape
     if first:  # conv1_1 as a 1x1 GEMM over gathered patches: K index = (ky*3+kx)*3 + c
         packed = torch.zeros((1, cout, in_c), dtype=torch.float32)
@@ -232,7 +246,9 @@ class _Instance:
         self.input = torch.empty((n, 3, h, w), dtype=torch.float32, device=dev)
         self.bufs = {}
         for name, (ch, level) in net.program.bufs.items():
-            self.bufs[name] = torch.zeros((n, h >> level, w >> level, ch), dtype=torch.bfloat16, device=dev)
+            # physical width rounded up to 64 channels (zeros, never written): every 64-channel box is in bounds
+            self.bufs[name] = torch.zeros((n, h >> level, w >> level, _up64(ch) if ch > 32 else ch), dtype=torch.bfloat16,
+                                          device=dev)
         gh, gw = h // 8, w // 8
         self.outputs = [torch.empty((n, ch, gh, gw), dtype=torch.float32, device=dev) for _, ch in net.program.outputs]
         handle = C.c_void_p()
@@ -256,6 +272,8 @@ class _Instance:
                 d.in_ = sb.data_ptr() + 2 * s["src"][1]
                 d.in_c = s["src"][2]
                 d.in_cstride = sb.shape[3]
+                d.in_c_readable = sb.shape[3] - s["src"][1]
+                d.w_cin = wt.shape[2]
                 d.n, d.h, d.w = n, sb.shape[1], sb.shape[2]
                 d.weights = wt.data_ptr()
                 d.cout = wt.shape[1]
@@ -277,14 +295,7 @@ class _Instance:
         self.launches = L.islpose_plan_num_launches(handle)
 
     def run(self):
-        timing = self.net.timing
-        if timing is not None:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
         _lib.check(_lib.lib().islpose_plan_run(self.handle, _lib.stream_ptr()), "islpose_plan_run")
-        if timing is not None:
-            e1.record()
-            timing.append((e0, e1, self.flops_algorithmic, self.launches))
 
     def __del__(self):
         try:
@@ -344,7 +355,7 @@ class PoseNet:
                 slope[:cout] = self._flat[s["prelu"] + ".weight"]
             self.packed.append((wt, bias.to(self.device), slope.to(self.device)))
         self._instances = {}
-        self.timing = None   # set to a list to collect (start, end, flops) CUDA-event pairs around every plan replay
+        self.timing = None   # set to a list: Body / Hand append (start, end, flops, launches) per network phase (fork to join)
 
     # ---- reference nn.Module surface -------------------------------------------------------------------
     def parameters(self):
