@@ -30,6 +30,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "frames/sec body+hand keypoints @368 4-scale"
 SCALES = [0.5, 1.0, 1.5, 2.0]
+WEIGHT_INIT = "torch"   # nn.Conv2d's default init distribution; "he" = noisy-map stress
 WORKLOADS = {
     # name: (model_type, H, W, hand boxes [x, y, w, is_left], default batch per rank)
     "C2": ("coco", 480, 640, [[400, 250, 109, True], [22, 246, 90, False]], 8),
@@ -93,7 +94,8 @@ def cpu_reference_frame(wl, seed, nets=None):
     mt, H, W, boxes, _ = WORKLOADS[wl]
     if nets is None:
         torch.set_num_threads(os.cpu_count() or 1)
-        nets = (O.make_net_fn(mt, O.make_flat_weights(mt, seed=0)), O.make_net_fn("hand", O.make_flat_weights("hand", seed=0)))
+        nets = (O.make_net_fn(mt, O.make_flat_weights(mt, seed=0, init=WEIGHT_INIT)),
+                O.make_net_fn("hand", O.make_flat_weights("hand", seed=0, init=WEIGHT_INIT)))
     frame = synth.synth_frame(H, W, seed)
     t0 = time.perf_counter()
     try:
@@ -150,7 +152,10 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="frames per step per rank (0 = workload default)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--weights", default="torch", choices=["torch", "he"], help="random-init distribution (he = noisy-map stress)")
     args = ap.parse_args()
+    global WEIGHT_INIT
+    WEIGHT_INIT = args.weights
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
@@ -172,8 +177,8 @@ def main():
 
     mt, H, W, boxes, default_batch = WORKLOADS[args.workload]
     B = args.batch or default_batch
-    body = isl_b200.Body(O.make_flat_weights(mt, seed=0), mt, scale_search=SCALES)
-    hand = isl_b200.Hand(O.make_flat_weights("hand", seed=0))
+    body = isl_b200.Body(O.make_flat_weights(mt, seed=0, init=WEIGHT_INIT), mt, scale_search=SCALES)
+    hand = isl_b200.Hand(O.make_flat_weights("hand", seed=0, init=WEIGHT_INIT))
     ex = KeypointExtractor(body, hand)
     hand_boxes = [boxes] * B
 
@@ -249,7 +254,8 @@ def main():
             "metric": METRIC, "value": frames_total / (dev_ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload_name(args.workload, B), "weights": "seeded random init (no trained weights ship with the reference)",
+            "config": {"workload": workload_name(args.workload, B), "weights": "seeded random init, %s (no trained weights ship with the reference)" % (
+                           "nn.Conv2d default distribution" if WEIGHT_INIT == "torch" else "He-uniform (noisy maps: thousands of peaks)"),
                        "l2": "flushed with a 256 MiB write before every timed step",
                        "timing": "CUDA events on the launching stream per step, summed; max over ranks"},
             "clocks": sampler.summary(),

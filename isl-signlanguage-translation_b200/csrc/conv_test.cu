@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <string>
 #include <vector>
 
 #include "conv_umma.cuh"
@@ -60,6 +61,7 @@ struct Cfg {
   int N, H, W, in_c, in_cstride, coff, cout, k;
   bool f32_out, bf16_out;
   int force_n_tile, force_stages;
+  int variant, msub;
 };
 
 static int run_cfg(const Cfg& c, bool timing) {
@@ -113,6 +115,8 @@ static int run_cfg(const Cfg& c, bool timing) {
   d.out_f32_channels = c.cout;
   d.force_n_tile = c.force_n_tile;
   d.force_stages = c.force_stages;
+  d.variant = c.variant;
+  d.msub = c.msub;
 
   ConvLaunch L;
   char err[256];
@@ -183,8 +187,8 @@ static int run_cfg(const Cfg& c, bool timing) {
     CK(cudaEventElapsedTime(&ms, e0, e1));
     ms /= reps;
   }
-  printf("%s %-32s tile %dx%d n_tile %d stages %d grid %ux%u  max|ref| %.3f  err32 %.2e  err16 %.2e  badpad %lld",
-         ok ? "PASS" : "FAIL", c.name, L.args.bw, L.args.bh, L.args.n_tile, L.args.stages, L.grid.x, L.grid.y,
+  printf("%s %-32s v%d msub %d tile %dx%d n_tile %d stages %d grid %ux%u  max|ref| %.3f  err32 %.2e  err16 %.2e  badpad %lld",
+         ok ? "PASS" : "FAIL", c.name, L.variant, L.args.msub, L.args.bw, L.args.bh, L.args.n_tile, L.args.stages, L.grid.x, L.grid.y,
          max_ref, err32, err16, bad_pad);
   if (ms > 0.f) printf("  %.3f ms  %.1f TFLOP/s", ms, L.flops / (ms * 1e-3) / 1e12);
   printf("\n");
@@ -197,6 +201,52 @@ static int run_cfg(const Cfg& c, bool timing) {
   cudaFree(d_bias);
   cudaFree(d_slope);
   return ok ? 0 : 1;
+}
+
+static int run_v2_suite() {
+  // persistent variant: correctness on awkward shapes, then head-to-head timings against v1
+  const Cfg cfgs[] = {
+      {"v2 1x1 64->64 16x8", 1, 8, 16, 64, 64, 0, 64, 1, true, true, 0, 0, 2, 1},
+      {"v2 3x3 128->128 23x41 b2", 2, 23, 41, 128, 128, 0, 128, 3, true, true, 0, 0, 2, 1},
+      {"v2 3x3 128->128 23x41 b3 m2", 3, 23, 41, 128, 128, 0, 128, 3, true, true, 0, 0, 2, 2},
+      {"v2 7x7 192->128 23x41 b2 m2", 2, 23, 41, 192, 192, 0, 128, 7, true, true, 0, 0, 2, 2},
+      {"v2 1x1 128->512 46x62 m2", 1, 46, 62, 128, 128, 0, 512, 1, true, true, 0, 0, 2, 2},
+      {"v2 1x1 512->38 head f32", 2, 23, 41, 512, 512, 0, 38, 1, true, true, 0, 0, 2, 1},
+      {"v2 3x3 slice 96/288->96 m2", 2, 23, 41, 96, 288, 96, 96, 3, true, true, 0, 0, 2, 2},
+      {"v1 7x7 128->128 92x164 b8", 8, 92, 164, 128, 128, 0, 128, 7, false, true, 0, 0, 1, 0},
+      {"v2 7x7 128->128 92x164 b8 m1", 8, 92, 164, 128, 128, 0, 128, 7, false, true, 0, 0, 2, 1},
+      {"v2 7x7 128->128 92x164 b8 m2", 8, 92, 164, 128, 128, 0, 128, 7, false, true, 0, 0, 2, 2},
+      {"v2 7x7 128->128 92x164 b8 m2s3", 8, 92, 164, 128, 128, 0, 128, 7, false, true, 0, 3, 2, 2},
+      {"v1 3x3 512->512 92x164 b2", 2, 92, 164, 512, 512, 0, 512, 3, false, true, 0, 0, 1, 0},
+      {"v2 3x3 512->512 92x164 b2 m1", 2, 92, 164, 512, 512, 0, 512, 3, false, true, 0, 0, 2, 1},
+      {"v2 3x3 512->512 92x164 b2 m2", 2, 92, 164, 512, 512, 0, 512, 3, false, true, 0, 0, 2, 2},
+      {"v1 3x3 256->256 184x328 b2", 2, 184, 328, 256, 256, 0, 256, 3, false, true, 0, 0, 1, 0},
+      {"v2 3x3 256->256 184x328 b2 m2", 2, 184, 328, 256, 256, 0, 256, 3, false, true, 0, 0, 2, 2},
+      {"v1 3x3 128->128 368x496 b2", 2, 368, 496, 128, 128, 0, 128, 3, false, true, 0, 0, 1, 0},
+      {"v2 3x3 128->128 368x496 b2 m2", 2, 368, 496, 128, 128, 0, 128, 3, false, true, 0, 0, 2, 2},
+      {"v1 3x3 64->64 736x984 b2", 2, 736, 984, 64, 64, 0, 64, 3, false, true, 0, 0, 1, 0},
+      {"v2 3x3 64->64 736x984 b2 m1", 2, 736, 984, 64, 64, 0, 64, 3, false, true, 0, 0, 2, 1},
+      {"v2 3x3 64->64 736x984 b2 m2", 2, 736, 984, 64, 64, 0, 64, 3, false, true, 0, 0, 2, 2},
+      {"v1 1x1 32->64 736x984 b2", 2, 736, 984, 32, 32, 0, 64, 1, false, true, 0, 0, 1, 0},
+      {"v2 1x1 32->64 736x984 b2 m2", 2, 736, 984, 32, 32, 0, 64, 1, false, true, 0, 0, 2, 2},
+      {"v1 7x7 192->128 60x80 b8", 8, 60, 80, 192, 192, 0, 128, 7, false, true, 0, 0, 1, 0},
+      {"v2 7x7 192->128 60x80 b8 m2", 8, 60, 80, 192, 192, 0, 128, 7, false, true, 0, 0, 2, 2},
+      {"v1 7x7 128->128 23x31 b8", 8, 23, 31, 128, 128, 0, 128, 7, false, true, 0, 0, 1, 0},
+      {"v2 7x7 128->128 23x31 b8 m1", 8, 23, 31, 128, 128, 0, 128, 7, false, true, 0, 0, 2, 1},
+      {"v1 3x3 288->96 92x164 b8", 8, 92, 164, 288, 288, 0, 96, 3, false, true, 0, 0, 1, 0},
+      {"v2 3x3 288->96 92x164 b8 m2", 8, 92, 164, 288, 288, 0, 96, 3, false, true, 0, 0, 2, 2},
+  };
+  int fails = 0;
+  for (const Cfg& c : cfgs) {
+    const int r = run_cfg(c, true);
+    if (r == 3) {
+      printf("context lost, stopping\n");
+      return 3;
+    }
+    fails += r;
+  }
+  printf("%s: %d failing configuration(s)\n", fails ? "FAILED" : "ALL PASS", fails);
+  return fails ? 1 : 0;
 }
 
 int main(int argc, char** argv) {
@@ -236,6 +286,7 @@ int main(int argc, char** argv) {
       {"3x3 288->96 92x164 b2", 2, 92, 164, 288, 288, 0, 96, 3, false, true, 0, 0},
   };
   const int n = sizeof(cfgs) / sizeof(cfgs[0]);
+  if (argc > 1 && std::string(argv[1]) == "v2") return run_v2_suite();
   int fails = 0;
   for (int i = 0; i < n; ++i) {
     if (argc > 1 && atoi(argv[1]) != i) continue;

@@ -190,6 +190,225 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ v2
+// Persistent variant: one CTA per SM walks work items (msub pixel tiles x one channel tile) round-robin.
+//   * the accumulator is double buffered in TMEM (2 x msub x n_tile columns), so the epilogue of work item w
+//     overlaps the main loop of w+1 and the per-tile set-up (barrier init, TMEM allocation) is paid once per CTA;
+//   * with msub = 2 one weight stage feeds two 128-pixel MMAs: half the weight traffic from L2 per FLOP.
+__global__ void __launch_bounds__(kThreads, 1)
+conv_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                            const ConvArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* const gbase = smem_raw + (base - raw);
+
+  const uint32_t a_stage_bytes = a.msub * kASlotBytes;
+  const uint32_t sA0 = base;
+  const uint32_t sB0 = base + a.stages * a_stage_bytes;
+  const uint32_t ctrl = sB0 + a.stages * a.b_stage_bytes;
+  uint8_t* const gctrl = gbase + (ctrl - base);
+  const uint32_t bar_full = ctrl;            // kMaxStages x 8 B
+  const uint32_t bar_empty = ctrl + 64;      // kMaxStages x 8 B
+  const uint32_t bar_acc_full = ctrl + 128;  // 2 x 8 B: accumulator buffer written
+  const uint32_t bar_acc_empty = ctrl + 144; // 2 x 8 B: accumulator buffer drained
+  const uint32_t tmem_slot = ctrl + 160;
+  volatile uint32_t* const tmem_slot_g = reinterpret_cast<volatile uint32_t*>(gctrl + 160);
+  float* const s_bias = reinterpret_cast<float*>(gctrl + 256);
+  float* const s_slope = s_bias + 256;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int cblocks = (a.cin_k16 + 3) >> 2;
+  const int taps = a.ksize * a.ksize;
+  const int tiles_per_img = a.tiles_x * a.tiles_y;
+  const int m_groups = (a.m_tiles + a.msub - 1) / a.msub;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < a.stages; ++s) {
+      ptx::mbar_init(bar_full + 8 * s, 1);
+      ptx::mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(bar_acc_full + 8 * b, 1);
+      ptx::mbar_init(bar_acc_empty + 8 * b, 4);  // one arrival per epilogue warp
+    }
+    ptx::mbar_fence_init();
+    ptx::prefetch_tensormap(&tmA);
+    ptx::prefetch_tensormap(&tmB);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, a.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_g;
+  const uint32_t acc_cols = a.msub * a.n_tile;  // columns of one accumulator buffer
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int it = 0;
+      for (int w = blockIdx.x; w < a.work_items; w += gridDim.x) {
+        const int mg = w % m_groups;
+        const int n0 = (w / m_groups) * a.n_tile;
+        int x0[2], y0[2], img[2];
+        int live = 0;
+        for (int sub = 0; sub < a.msub; ++sub) {
+          const int t = mg * a.msub + sub;
+          if (t < a.m_tiles) {
+            img[sub] = t / tiles_per_img;
+            const int r = t - img[sub] * tiles_per_img;
+            y0[sub] = (r / a.tiles_x) * a.bh;
+            x0[sub] = (r % a.tiles_x) * a.bw;
+            ++live;
+          }
+        }
+        const uint32_t tx_bytes = 128u * a.bw * a.bh * live + 128u * a.n_tile;
+        for (int tap = 0; tap < taps; ++tap) {
+          const int ky = tap / a.ksize;
+          const int kx = tap - ky * a.ksize;
+          for (int cb = 0; cb < cblocks; ++cb, ++it) {
+            const int s = it % a.stages;
+            const uint32_t ph = (it / a.stages) & 1;
+            ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1);
+            ptx::mbar_arrive_expect_tx(bar_full + 8 * s, tx_bytes);
+            for (int sub = 0; sub < live; ++sub) {
+              ptx::tma_load_4d(sA0 + s * a_stage_bytes + sub * kASlotBytes, &tmA, bar_full + 8 * s, cb * 64,
+                               x0[sub] + kx - a.pad, y0[sub] + ky - a.pad, img[sub]);
+            }
+            ptx::tma_load_3d(sB0 + s * a.b_stage_bytes, &tmB, bar_full + 8 * s, cb * 64, n0, tap);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = ptx::umma_idesc_bf16(128, a.n_tile);
+      int it = 0;
+      int local = 0;
+      for (int w = blockIdx.x; w < a.work_items; w += gridDim.x, ++local) {
+        const int mg = w % m_groups;
+        const int live = min(a.msub, a.m_tiles - mg * a.msub);
+        const int buf = local & 1;
+        ptx::mbar_wait(bar_acc_empty + 8 * buf, ((local >> 1) & 1) ^ 1);  // epilogue has drained this buffer
+        ptx::tc_fence_after();
+        const uint32_t acc = tmem_base + buf * acc_cols;
+        int kb = 0;
+        for (int tap = 0; tap < taps; ++tap) {
+          for (int cb = 0; cb < cblocks; ++cb, ++it, ++kb) {
+            const int s = it % a.stages;
+            const uint32_t ph = (it / a.stages) & 1;
+            ptx::mbar_wait(bar_full + 8 * s, ph);
+            ptx::tc_fence_after();
+            const uint64_t db = ptx::umma_desc_sw128(sB0 + s * a.b_stage_bytes);
+            const int ksteps = min(4, a.cin_k16 - cb * 4);
+            for (int sub = 0; sub < live; ++sub) {
+              const uint64_t da = ptx::umma_desc_sw128(sA0 + s * a_stage_bytes + sub * kASlotBytes);
+              for (int k = 0; k < ksteps; ++k) {
+                ptx::umma_bf16(acc + sub * a.n_tile, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              }
+            }
+            ptx::umma_commit(bar_empty + 8 * s);
+          }
+        }
+        ptx::umma_commit(bar_acc_full + 8 * buf);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5 = 128 threads)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int py = row / a.bw;
+    const int px = row - py * a.bw;
+    const int et = threadIdx.x - 64;
+    int local = 0;
+    int cur_n0 = -1;
+    for (int w = blockIdx.x; w < a.work_items; w += gridDim.x, ++local) {
+      const int mg = w % m_groups;
+      const int n0 = (w / m_groups) * a.n_tile;
+      const int live = min(a.msub, a.m_tiles - mg * a.msub);
+      const int buf = local & 1;
+      if (n0 != cur_n0) {  // (re)load this channel tile's bias / slope; named barrier 1 = the 4 epilogue warps
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int i = et; i < a.n_tile; i += 128) {
+          s_bias[i] = a.bias[n0 + i];
+          s_slope[i] = a.slope[n0 + i];
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        cur_n0 = n0;
+      }
+      ptx::mbar_wait(bar_acc_full + 8 * buf, (local >> 1) & 1);
+      ptx::tc_fence_after();
+      for (int sub = 0; sub < live; ++sub) {
+        const int t = mg * a.msub + sub;
+        const int img = t / tiles_per_img;
+        const int r = t - img * tiles_per_img;
+        const int y = (r / a.tiles_x) * a.bh + py;
+        const int x = (r % a.tiles_x) * a.bw + px;
+        const bool valid = (row < a.bw * a.bh) && (x < a.W) && (y < a.H);
+        const long long pix = (static_cast<long long>(img) * a.H + y) * a.W + x;
+        const uint32_t acc = tmem_base + buf * acc_cols + sub * a.n_tile + (static_cast<uint32_t>(q * 32) << 16);
+        for (int c = 0; c < a.n_tile; c += 32) {
+          uint32_t rr[32];
+          ptx::tmem_ld_32x32(acc + c, rr);
+          ptx::tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float accv = __uint_as_float(rr[i]) + s_bias[c + i];
+            v[i] = accv > 0.f ? accv : accv * s_slope[c + i];
+          }
+          if (valid) {
+            if (a.out_bf16 != nullptr) {
+              __nv_bfloat16* dst = a.out_bf16 + pix * a.out_pix_stride + n0 + c;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (n0 + c + 8 * j < a.cout_store) {
+                  uint4 pk;
+                  __nv_bfloat162 h;
+                  h = __floats2bfloat162_rn(v[8 * j + 0], v[8 * j + 1]);
+                  pk.x = *reinterpret_cast<uint32_t*>(&h);
+                  h = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+                  pk.y = *reinterpret_cast<uint32_t*>(&h);
+                  h = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
+                  pk.z = *reinterpret_cast<uint32_t*>(&h);
+                  h = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+                  pk.w = *reinterpret_cast<uint32_t*>(&h);
+                  *reinterpret_cast<uint4*>(dst + 8 * j) = pk;
+                }
+              }
+            }
+            if (a.out_f32 != nullptr) {
+              const long long plane = static_cast<long long>(a.H) * a.W;
+              float* dst = a.out_f32 + (static_cast<long long>(img) * a.out_f32_channels + n0 + c) * plane +
+                           static_cast<long long>(y) * a.W + x;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                if (n0 + c + i < a.cout) dst[i * plane] = v[i];
+              }
+            }
+          }
+        }
+      }
+      // this warp has finished reading the buffer: hand it back to the MMA issuer
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar_acc_empty + 8 * buf);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tmem_dealloc(tmem_base, a.tmem_cols);
+  }
+}
+
 // ------------------------------------------------------------------ host side
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -278,13 +497,31 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   while (cols < (n_tile + 31) / 32 * 32) cols <<= 1;
   a.tmem_cols = cols;
 
-  const uint32_t per_stage = kASlotBytes + a.b_stage_bytes;
+  // Variant: persistent CTAs pay off once every SM gets at least a couple of tiles.
+  int variant = d.variant;
+  if (variant <= 0) variant = 1;
+  int msub = 1;
+  if (variant == 2) {
+    msub = d.msub > 0 ? d.msub : ((m_tiles * n_tiles >= 4 * 148 && n_tile <= 128) ? 2 : 1);
+    if (msub < 1 || msub > 2 || 2 * msub * n_tile > 512) return fail(err, errlen, "conv: bad sub-tile count %lld", msub);
+    int cols2 = 32;
+    while (cols2 < 2 * msub * ((n_tile + 31) / 32 * 32)) cols2 <<= 1;
+    a.tmem_cols = cols2;
+  }
+  a.msub = msub;
+  a.m_tiles = static_cast<int>(m_tiles);
+  a.n_tiles = n_tiles;
+  a.work_items = static_cast<int>((m_tiles + msub - 1) / msub) * n_tiles;
+  out->variant = variant;
+
+  const uint32_t per_stage = msub * kASlotBytes + a.b_stage_bytes;
   int stages = d.force_stages;
   if (stages <= 0) {
-    stages = static_cast<int>((110u * 1024u - kCtrlBytes - 1024u) / per_stage);  // two CTAs per SM
+    const uint32_t budget = variant == 2 ? 200u * 1024u : 110u * 1024u - kCtrlBytes - 1024u;  // v1: two CTAs per SM
+    stages = static_cast<int>(budget / per_stage);
     if (stages < 2) stages = 2;
     const int iters = d.ksize * d.ksize * ((a.cin_k16 + 3) / 4);
-    if (stages > iters) stages = iters;
+    if (stages > iters && variant == 1) stages = iters;
   }
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 1) stages = 1;
@@ -330,12 +567,19 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
     if (r != CUDA_SUCCESS) return fail(err, errlen, "conv: weight tensor map rejected (CUresult %lld)", r);
   }
 
-  out->grid = dim3(static_cast<unsigned>(m_tiles), static_cast<unsigned>(n_tiles), 1);
+  if (variant == 2) {
+    const int ctas = a.work_items < 148 ? a.work_items : 148;
+    out->grid = dim3(static_cast<unsigned>(ctas), 1, 1);
+  } else {
+    out->grid = dim3(static_cast<unsigned>(m_tiles), static_cast<unsigned>(n_tiles), 1);
+  }
   out->flops = 2.0 * d.in_c * d.cout * d.ksize * d.ksize * static_cast<double>(d.H) * d.W * d.N;
 
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_umma_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail(err, errlen, "conv: cannot raise dynamic shared memory limit (%lld)", e);
     attr_set = true;
   }
@@ -343,7 +587,11 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
 }
 
 int conv_run(const ConvLaunch& l, cudaStream_t stream) {
-  conv_umma_kernel<<<l.grid, kThreads, l.smem_bytes, stream>>>(l.tmA, l.tmB, l.args);
+  if (l.variant == 2) {
+    conv_umma_persistent_kernel<<<l.grid, kThreads, l.smem_bytes, stream>>>(l.tmA, l.tmB, l.args);
+  } else {
+    conv_umma_kernel<<<l.grid, kThreads, l.smem_bytes, stream>>>(l.tmA, l.tmB, l.args);
+  }
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 

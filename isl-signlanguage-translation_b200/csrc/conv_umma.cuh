@@ -49,6 +49,8 @@ struct ConvDesc {
   int force_n_tile;
   int force_stages;
   int force_bw, force_bh;
+  int variant;  // 0 = automatic, 1 = one tile per CTA (v1), 2 = persistent CTAs with double-buffered TMEM (v2)
+  int msub;     // v2: pixel sub-tiles per work item sharing one weight stage (0 = automatic, 1 or 2)
 };
 
 // A fully resolved launch (tensor maps built once, reusable for every replay).
@@ -64,6 +66,11 @@ struct ConvArgs {
   int stages;
   int tmem_cols;
   uint32_t b_stage_bytes;
+  // persistent variant
+  int msub;        // pixel sub-tiles per work item
+  int m_tiles;     // pixel tiles in total (tiles_x * tiles_y * N)
+  int n_tiles;     // channel tiles
+  int work_items;  // ceil(m_tiles / msub) * n_tiles
   __nv_bfloat16* out_bf16;
   long long out_pix_stride;
   float* out_f32;
@@ -78,6 +85,7 @@ struct ConvLaunch {
   ConvArgs args;
   dim3 grid;
   uint32_t smem_bytes;
+  int variant;
   double flops;  // algorithmic: 2*Cin*Cout*k*k*H*W*N on the unpadded slice width the caller states
 };
 

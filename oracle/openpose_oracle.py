@@ -390,23 +390,32 @@ _BODY25_STAGES = [(2, 0, 128, 96, 256, 52), (2, 1, 180, 128, 512, 52), (2, 2, 18
                   (2, 3, 180, 128, 512, 52), (1, 0, 180, 96, 256, 26), (1, 1, 206, 128, 512, 26)]
 
 
-def make_flat_weights(kind, seed=0, gain=1.0, head_gain=1.0):
+def make_flat_weights(kind, seed=0, gain=1.0, head_gain=1.0, init="he"):
     """Seeded random weights in the reference's on-disk format: a flat dict of Caffe layer names
     ('conv1_1.weight', 'Mprelu1_stage0_L2_0.weight', ...) -> float32 tensors (util.py:35-44 maps these onto
-    the module's state-dict keys). He-uniform scaled by `gain` keeps activations from collapsing through ~30
-    ReLU layers; `head_gain` additionally scales the stage-output layers."""
+    the module's state-dict keys).
+      init="he":    He-uniform scaled by `gain` (keeps activations alive through ~30 ReLU layers, so the maps cross
+                    the thresholds and peak finding / grouping get exercised); `head_gain` scales the stage outputs.
+      init="torch": the distribution nn.Conv2d / nn.PReLU are constructed with (kaiming_uniform(a=sqrt(5)):
+                    U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for weight and bias, PReLU slope 0.25) - the "random-init
+                    weights" of SURVEY.md section 8d; produces (almost) no peaks, like the reference does untrained."""
     import torch
 
     g = torch.Generator().manual_seed(seed)
     w = {}
     for (name, cin, cout, k, act, prelu) in net_layers(kind):
-        bound = gain * math.sqrt(6.0 / (cin * k * k))
-        if name.startswith("Mconv7") or name in ("conv5_5_CPM_L1", "conv5_5_CPM_L2", "conv6_2_CPM"):
-            bound *= head_gain
+        if init == "torch":
+            bound = 1.0 / math.sqrt(cin * k * k)
+            bias_bound = bound
+        else:
+            bound = gain * math.sqrt(6.0 / (cin * k * k))
+            bias_bound = 0.05
+            if name.startswith("Mconv7") or name in ("conv5_5_CPM_L1", "conv5_5_CPM_L2", "conv6_2_CPM"):
+                bound *= head_gain
         w[name + ".weight"] = (torch.rand((cout, cin, k, k), generator=g) * 2 - 1) * bound
-        w[name + ".bias"] = (torch.rand((cout,), generator=g) * 2 - 1) * 0.05
+        w[name + ".bias"] = (torch.rand((cout,), generator=g) * 2 - 1) * bias_bound
         if prelu is not None:
-            w[prelu + ".weight"] = torch.rand((cout,), generator=g) * 0.3
+            w[prelu + ".weight"] = torch.full((cout,), 0.25) if init == "torch" else torch.rand((cout,), generator=g) * 0.3
     return w
 
 
