@@ -61,7 +61,7 @@ struct Cfg {
   int N, H, W, in_c, in_cstride, coff, cout, k;
   bool f32_out, bf16_out;
   int force_n_tile, force_stages;
-  int variant, msub;
+  int variant, msub, acc_bufs;
 };
 
 static int run_cfg(const Cfg& c, bool timing) {
@@ -117,6 +117,7 @@ static int run_cfg(const Cfg& c, bool timing) {
   d.force_stages = c.force_stages;
   d.variant = c.variant;
   d.msub = c.msub;
+  d.acc_bufs = c.acc_bufs;
 
   ConvLaunch L;
   char err[256];
@@ -187,8 +188,8 @@ static int run_cfg(const Cfg& c, bool timing) {
     CK(cudaEventElapsedTime(&ms, e0, e1));
     ms /= reps;
   }
-  printf("%s %-32s v%d msub %d tile %dx%d n_tile %d stages %d grid %ux%u  max|ref| %.3f  err32 %.2e  err16 %.2e  badpad %lld",
-         ok ? "PASS" : "FAIL", c.name, L.variant, L.args.msub, L.args.bw, L.args.bh, L.args.n_tile, L.args.stages, L.grid.x, L.grid.y,
+  printf("%s %-34s v%d msub %d acc %d tile %dx%d n_tile %d stages %d grid %ux%u  max|ref| %.3f  err32 %.2e  err16 %.2e  badpad %lld",
+         ok ? "PASS" : "FAIL", c.name, L.variant, L.args.msub, L.args.acc_bufs, L.args.bw, L.args.bh, L.args.n_tile, L.args.stages, L.grid.x, L.grid.y,
          max_ref, err32, err16, bad_pad);
   if (ms > 0.f) printf("  %.3f ms  %.1f TFLOP/s", ms, L.flops / (ms * 1e-3) / 1e12);
   printf("\n");
@@ -205,36 +206,51 @@ static int run_cfg(const Cfg& c, bool timing) {
 
 static int run_v2_suite() {
   // persistent variant: correctness on awkward shapes, then head-to-head timings against v1
+  // name, N, H, W, in_c, cstride, coff, cout, k, f32, bf16, n_tile, stages, variant, msub, acc_bufs
   const Cfg cfgs[] = {
-      {"v2 1x1 64->64 16x8", 1, 8, 16, 64, 64, 0, 64, 1, true, true, 0, 0, 2, 1},
-      {"v2 3x3 128->128 23x41 b2", 2, 23, 41, 128, 128, 0, 128, 3, true, true, 0, 0, 2, 1},
-      {"v2 3x3 128->128 23x41 b3 m2", 3, 23, 41, 128, 128, 0, 128, 3, true, true, 0, 0, 2, 2},
-      {"v2 7x7 192->128 23x41 b2 m2", 2, 23, 41, 192, 192, 0, 128, 7, true, true, 0, 0, 2, 2},
-      {"v2 1x1 128->512 46x62 m2", 1, 46, 62, 128, 128, 0, 512, 1, true, true, 0, 0, 2, 2},
-      {"v2 1x1 512->38 head f32", 2, 23, 41, 512, 512, 0, 38, 1, true, true, 0, 0, 2, 1},
-      {"v2 3x3 slice 96/288->96 m2", 2, 23, 41, 96, 288, 96, 96, 3, true, true, 0, 0, 2, 2},
-      {"v1 7x7 128->128 92x164 b8", 8, 92, 164, 128, 128, 0, 128, 7, false, true, 0, 0, 1, 0},
-      {"v2 7x7 128->128 92x164 b8 m1", 8, 92, 164, 128, 128, 0, 128, 7, false, true, 0, 0, 2, 1},
-      {"v2 7x7 128->128 92x164 b8 m2", 8, 92, 164, 128, 128, 0, 128, 7, false, true, 0, 0, 2, 2},
-      {"v2 7x7 128->128 92x164 b8 m2s3", 8, 92, 164, 128, 128, 0, 128, 7, false, true, 0, 3, 2, 2},
-      {"v1 3x3 512->512 92x164 b2", 2, 92, 164, 512, 512, 0, 512, 3, false, true, 0, 0, 1, 0},
-      {"v2 3x3 512->512 92x164 b2 m1", 2, 92, 164, 512, 512, 0, 512, 3, false, true, 0, 0, 2, 1},
-      {"v2 3x3 512->512 92x164 b2 m2", 2, 92, 164, 512, 512, 0, 512, 3, false, true, 0, 0, 2, 2},
-      {"v1 3x3 256->256 184x328 b2", 2, 184, 328, 256, 256, 0, 256, 3, false, true, 0, 0, 1, 0},
-      {"v2 3x3 256->256 184x328 b2 m2", 2, 184, 328, 256, 256, 0, 256, 3, false, true, 0, 0, 2, 2},
-      {"v1 3x3 128->128 368x496 b2", 2, 368, 496, 128, 128, 0, 128, 3, false, true, 0, 0, 1, 0},
-      {"v2 3x3 128->128 368x496 b2 m2", 2, 368, 496, 128, 128, 0, 128, 3, false, true, 0, 0, 2, 2},
-      {"v1 3x3 64->64 736x984 b2", 2, 736, 984, 64, 64, 0, 64, 3, false, true, 0, 0, 1, 0},
-      {"v2 3x3 64->64 736x984 b2 m1", 2, 736, 984, 64, 64, 0, 64, 3, false, true, 0, 0, 2, 1},
-      {"v2 3x3 64->64 736x984 b2 m2", 2, 736, 984, 64, 64, 0, 64, 3, false, true, 0, 0, 2, 2},
-      {"v1 1x1 32->64 736x984 b2", 2, 736, 984, 32, 32, 0, 64, 1, false, true, 0, 0, 1, 0},
-      {"v2 1x1 32->64 736x984 b2 m2", 2, 736, 984, 32, 32, 0, 64, 1, false, true, 0, 0, 2, 2},
-      {"v1 7x7 192->128 60x80 b8", 8, 60, 80, 192, 192, 0, 128, 7, false, true, 0, 0, 1, 0},
-      {"v2 7x7 192->128 60x80 b8 m2", 8, 60, 80, 192, 192, 0, 128, 7, false, true, 0, 0, 2, 2},
-      {"v1 7x7 128->128 23x31 b8", 8, 23, 31, 128, 128, 0, 128, 7, false, true, 0, 0, 1, 0},
-      {"v2 7x7 128->128 23x31 b8 m1", 8, 23, 31, 128, 128, 0, 128, 7, false, true, 0, 0, 2, 1},
-      {"v1 3x3 288->96 92x164 b8", 8, 92, 164, 288, 288, 0, 96, 3, false, true, 0, 0, 1, 0},
-      {"v2 3x3 288->96 92x164 b8 m2", 8, 92, 164, 288, 288, 0, 96, 3, false, true, 0, 0, 2, 2},
+      {"v2 1x1 64->64 16x8", 1, 8, 16, 64, 64, 0, 64, 1, true, true, 0, 0, 2, 1, 0},
+      {"v2 3x3 128->128 23x41 b3 m2", 3, 23, 41, 128, 128, 0, 128, 3, true, true, 0, 0, 2, 2, 0},
+      {"v2 7x7 192->128 23x41 b2 m2 a1", 2, 23, 41, 192, 192, 0, 128, 7, true, true, 0, 2, 2, 2, 1},
+      {"v2 1x1 128->512 46x62 m2", 1, 46, 62, 128, 128, 0, 512, 1, true, true, 0, 0, 2, 2, 0},
+      {"v2 1x1 512->38 head f32", 2, 23, 41, 512, 512, 0, 38, 1, true, true, 0, 0, 2, 1, 0},
+      {"v2 3x3 slice 96/288->96 m2", 2, 23, 41, 96, 288, 96, 96, 3, true, true, 0, 0, 2, 2, 0},
+      {"v1 7x7 128->128 92x164 b8", 8, 92, 164, 128, 128, 0, 128, 7, false, true, 0, 0, 1, 0, 0},
+      {"v1 7x7 128->128 92x164 b8 s2", 8, 92, 164, 128, 128, 0, 128, 7, false, true, 0, 2, 1, 0, 0},
+      {"v2 7x7 .. b8 m1 s3 a2 (2/SM)", 8, 92, 164, 128, 128, 0, 128, 7, false, true, 0, 3, 2, 1, 2},
+      {"v2 7x7 .. b8 m1 s2 a1 (3/SM)", 8, 92, 164, 128, 128, 0, 128, 7, false, true, 0, 2, 2, 1, 1},
+      {"v2 7x7 .. b8 m2 s2 a1 (2/SM)", 8, 92, 164, 128, 128, 0, 128, 7, false, true, 0, 2, 2, 2, 1},
+      {"v1 3x3 512->512 92x164 b2", 2, 92, 164, 512, 512, 0, 512, 3, false, true, 0, 0, 1, 0, 0},
+      {"v2 3x3 512 .. m1 s2 a1 (3/SM)", 2, 92, 164, 512, 512, 0, 512, 3, false, true, 0, 2, 2, 1, 1},
+      {"v2 3x3 512 .. m2 s2 a1 (2/SM)", 2, 92, 164, 512, 512, 0, 512, 3, false, true, 0, 2, 2, 2, 1},
+      {"v1 3x3 256->256 184x328 b2", 2, 184, 328, 256, 256, 0, 256, 3, false, true, 0, 0, 1, 0, 0},
+      {"v2 3x3 256 .. m2 s2 a1 (2/SM)", 2, 184, 328, 256, 256, 0, 256, 3, false, true, 0, 2, 2, 2, 1},
+      {"v2 3x3 256 .. m1 s2 a1 (3/SM)", 2, 184, 328, 256, 256, 0, 256, 3, false, true, 0, 2, 2, 1, 1},
+      {"v1 3x3 128->128 368x496 b2", 2, 368, 496, 128, 128, 0, 128, 3, false, true, 0, 0, 1, 0, 0},
+      {"v2 3x3 128 .. m2 s2 a1 (2/SM)", 2, 368, 496, 128, 128, 0, 128, 3, false, true, 0, 2, 2, 2, 1},
+      {"v2 3x3 128 .. m1 s2 a1 (3/SM)", 2, 368, 496, 128, 128, 0, 128, 3, false, true, 0, 2, 2, 1, 1},
+      {"v1 3x3 64->64 736x984 b2", 2, 736, 984, 64, 64, 0, 64, 3, false, true, 0, 0, 1, 0, 0},
+      {"v2 3x3 64 .. m2 s2 a2 (2/SM)", 2, 736, 984, 64, 64, 0, 64, 3, false, true, 0, 2, 2, 2, 2},
+      {"v2 3x3 64 .. m2 s2 a1 (2/SM)", 2, 736, 984, 64, 64, 0, 64, 3, false, true, 0, 2, 2, 2, 1},
+      {"v2 3x3 64 .. m1 s2 a2 (4/SM)", 2, 736, 984, 64, 64, 0, 64, 3, false, true, 0, 2, 2, 1, 2},
+      {"v2 3x3 64 .. m2 s1 a2 (4/SM?)", 2, 736, 984, 64, 64, 0, 64, 3, false, true, 0, 1, 2, 2, 2},
+      {"v1 1x1 32->64 736x984 b2", 2, 736, 984, 32, 32, 0, 64, 1, false, true, 0, 0, 1, 0, 0},
+      {"v2 1x1 32->64 .. m2 s2 a2", 2, 736, 984, 32, 32, 0, 64, 1, false, true, 0, 2, 2, 2, 2},
+      {"v2 1x1 32->64 .. m1 s2 a2 (4/SM)", 2, 736, 984, 32, 32, 0, 64, 1, false, true, 0, 2, 2, 1, 2},
+      {"v1 7x7 192->128 60x80 b8", 8, 60, 80, 192, 192, 0, 128, 7, false, true, 0, 0, 1, 0, 0},
+      {"v2 7x7 192 60x80 m1 s2 a1 (3/SM)", 8, 60, 80, 192, 192, 0, 128, 7, false, true, 0, 2, 2, 1, 1},
+      {"v1 3x3 288->96 92x164 b8", 8, 92, 164, 288, 288, 0, 96, 3, false, true, 0, 0, 1, 0, 0},
+      {"v2 3x3 288->96 m2 s2 a1", 8, 92, 164, 288, 288, 0, 96, 3, false, true, 0, 2, 2, 2, 1},
+      {"v2 3x3 288->96 m1 s2 a1 (3/SM)", 8, 92, 164, 288, 288, 0, 96, 3, false, true, 0, 2, 2, 1, 1},
+      {"v1 3x3 512->512 92x164 nt256 s2", 2, 92, 164, 512, 512, 0, 512, 3, false, true, 256, 2, 1, 0, 0},
+      {"v1 3x3 256->256 184x328 nt256s2", 2, 184, 328, 256, 256, 0, 256, 3, false, true, 256, 2, 1, 0, 0},
+      {"auto 3x3 64->64 736x984 b2", 2, 736, 984, 64, 64, 0, 64, 3, false, true, 0, 0, 0, 0, 0},
+      {"auto 3x3 288->96 92x164 b8", 8, 92, 164, 288, 288, 0, 96, 3, false, true, 0, 0, 0, 0, 0},
+      {"auto 3x3 96->96 slice 92x164 b8", 8, 92, 164, 96, 288, 96, 96, 3, false, true, 0, 0, 0, 0, 0},
+      {"v1 3x3 96->96 slice 92x164 b8", 8, 92, 164, 96, 288, 96, 96, 3, false, true, 0, 0, 1, 0, 0},
+      {"auto 1x1 32->64 736x984 b2", 2, 736, 984, 32, 32, 0, 64, 1, false, true, 0, 0, 0, 0, 0},
+      {"auto 3x3 64->128 368x496 b2", 2, 368, 496, 64, 64, 0, 128, 3, false, true, 0, 0, 0, 0, 0},
+      {"v1 1x1 128->512 92x124 b8", 8, 92, 124, 128, 128, 0, 512, 1, false, true, 0, 0, 1, 0, 0},
+      {"v2 1x1 128->512 92x124 b8 m2", 8, 92, 124, 128, 128, 0, 512, 1, false, true, 0, 2, 2, 2, 1},
   };
   int fails = 0;
   for (const Cfg& c : cfgs) {

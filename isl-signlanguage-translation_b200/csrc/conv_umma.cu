@@ -196,7 +196,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 //   * the accumulator is double buffered in TMEM (2 x msub x n_tile columns), so the epilogue of work item w
 //     overlaps the main loop of w+1 and the per-tile set-up (barrier init, TMEM allocation) is paid once per CTA;
 //   * with msub = 2 one weight stage feeds two 128-pixel MMAs: half the weight traffic from L2 per FLOP.
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 3)
 conv_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                             const ConvArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -294,8 +294,8 @@ conv_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       for (int w = blockIdx.x; w < a.work_items; w += gridDim.x, ++local) {
         const int mg = w % m_groups;
         const int live = min(a.msub, a.m_tiles - mg * a.msub);
-        const int buf = local & 1;
-        ptx::mbar_wait(bar_acc_empty + 8 * buf, ((local >> 1) & 1) ^ 1);  // epilogue has drained this buffer
+        const int buf = local % a.acc_bufs;
+        ptx::mbar_wait(bar_acc_empty + 8 * buf, ((local / a.acc_bufs) & 1) ^ 1);  // epilogue has drained this buffer
         ptx::tc_fence_after();
         const uint32_t acc = tmem_base + buf * acc_cols;
         int kb = 0;
@@ -332,7 +332,7 @@ conv_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       const int mg = w % m_groups;
       const int n0 = (w / m_groups) * a.n_tile;
       const int live = min(a.msub, a.m_tiles - mg * a.msub);
-      const int buf = local & 1;
+      const int buf = local % a.acc_bufs;
       if (n0 != cur_n0) {  // (re)load this channel tile's bias / slope; named barrier 1 = the 4 epilogue warps
         asm volatile("bar.sync 1, 128;" ::: "memory");
         for (int i = et; i < a.n_tile; i += 128) {
@@ -342,7 +342,7 @@ conv_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
         asm volatile("bar.sync 1, 128;" ::: "memory");
         cur_n0 = n0;
       }
-      ptx::mbar_wait(bar_acc_full + 8 * buf, (local >> 1) & 1);
+      ptx::mbar_wait(bar_acc_full + 8 * buf, (local / a.acc_bufs) & 1);
       ptx::tc_fence_after();
       for (int sub = 0; sub < live; ++sub) {
         const int t = mg * a.msub + sub;
@@ -486,7 +486,13 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   // with a 3-deep ring each: the second CTA's main loop hides the first one's epilogue and pipeline fill.
   const int cout16 = (d.cout + 15) / 16 * 16;
   int n_tile = d.force_n_tile;
-  if (n_tile <= 0) n_tile = cout16 <= 128 ? cout16 : 128;
+  if (n_tile <= 0) {
+    // An M=128 x N=128 tile is shared-memory-bandwidth bound (each K=16 MMA reads 8 KB in 64 cycles while TMA writes
+    // as much): measured ~900 TFLOP/s. N=256 halves the activation traffic per FLOP: measured 1243 TFLOP/s on
+    // 3x3 512->512 with a 2-deep ring and two CTAs per SM. Use it whenever the grid still fills the machine.
+    if (cout16 <= 128) n_tile = cout16;
+    else n_tile = (cout16 % 256 == 0 && m_tiles * (cout16 / 256) >= 148) ? 256 : 128;
+  }
   if (n_tile % 16 != 0 || n_tile > 256 || n_tile < 16) return fail(err, errlen, "conv: bad channel tile %lld", n_tile);
   const int n_tiles = (cout16 + n_tile - 1) / n_tile;
   a.n_tile = n_tile;
@@ -498,15 +504,25 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   a.tmem_cols = cols;
 
   // Variant: persistent CTAs pay off once every SM gets at least a couple of tiles.
+  // Measured on B200 (profiles/conv_test_v2_r1.log): 128-wide channel tiles run best as one tile per CTA with two
+  // CTAs per SM (v1); narrower tiles (64, 96) gain 20-65 % from the persistent variant with two pixel sub-tiles per
+  // weight stage, as long as the grid is large enough to give every persistent CTA several work items.
   int variant = d.variant;
-  if (variant <= 0) variant = 1;
+  if (variant <= 0) variant = (n_tile <= 96 && m_tiles * n_tiles >= 2 * 296) ? 2 : 1;
   int msub = 1;
+  int auto_stages = 0;
   if (variant == 2) {
-    msub = d.msub > 0 ? d.msub : ((m_tiles * n_tiles >= 4 * 148 && n_tile <= 128) ? 2 : 1);
-    if (msub < 1 || msub > 2 || 2 * msub * n_tile > 512) return fail(err, errlen, "conv: bad sub-tile count %lld", msub);
+    msub = d.msub > 0 ? d.msub : 2;
+    if (d.variant <= 0) auto_stages = 2;
+    int bufs = d.acc_bufs > 0 ? d.acc_bufs : (2 * msub * n_tile <= 256 ? 2 : 1);  // keep <= 256 columns: two CTAs per SM
+    if (msub < 1 || msub > 2 || bufs < 1 || bufs > 2 || bufs * msub * n_tile > 512)
+      return fail(err, errlen, "conv: bad sub-tile / accumulator buffer count %lld x %lld", msub, bufs);
     int cols2 = 32;
-    while (cols2 < 2 * msub * ((n_tile + 31) / 32 * 32)) cols2 <<= 1;
+    // the epilogue reads 32-column chunks: the last chunk of the last accumulator may overhang n_tile
+    while (cols2 < (bufs * msub - 1) * n_tile + (n_tile + 31) / 32 * 32) cols2 <<= 1;
+    if (cols2 > 512) return fail(err, errlen, "conv: accumulator does not fit TMEM (%lld columns)", cols2);
     a.tmem_cols = cols2;
+    a.acc_bufs = bufs;
   }
   a.msub = msub;
   a.m_tiles = static_cast<int>(m_tiles);
@@ -515,7 +531,7 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   out->variant = variant;
 
   const uint32_t per_stage = msub * kASlotBytes + a.b_stage_bytes;
-  int stages = d.force_stages;
+  int stages = d.force_stages > 0 ? d.force_stages : auto_stages;
   if (stages <= 0) {
     const uint32_t budget = variant == 2 ? 200u * 1024u : 110u * 1024u - kCtrlBytes - 1024u;  // v1: two CTAs per SM
     stages = static_cast<int>(budget / per_stage);
@@ -568,7 +584,12 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   }
 
   if (variant == 2) {
-    const int ctas = a.work_items < 148 ? a.work_items : 148;
+    int per_sm = static_cast<int>((226u * 1024u) / out->smem_bytes);  // persistent CTAs that fit on one SM
+    if (per_sm * a.tmem_cols > 512) per_sm = 512 / a.tmem_cols;
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm < 1) per_sm = 1;
+    const int slots = 148 * per_sm;
+    const int ctas = a.work_items < slots ? a.work_items : slots;
     out->grid = dim3(static_cast<unsigned>(ctas), 1, 1);
   } else {
     out->grid = dim3(static_cast<unsigned>(m_tiles), static_cast<unsigned>(n_tiles), 1);

@@ -51,6 +51,7 @@ struct ConvDesc {
   int force_bw, force_bh;
   int variant;  // 0 = automatic, 1 = one tile per CTA (v1), 2 = persistent CTAs with double-buffered TMEM (v2)
   int msub;     // v2: pixel sub-tiles per work item sharing one weight stage (0 = automatic, 1 or 2)
+  int acc_bufs; // v2: TMEM accumulator buffers (0 = automatic, 1 or 2)
 };
 
 // A fully resolved launch (tensor maps built once, reusable for every replay).
@@ -68,6 +69,7 @@ struct ConvArgs {
   uint32_t b_stage_bytes;
   // persistent variant
   int msub;        // pixel sub-tiles per work item
+  int acc_bufs;    // accumulator buffers in TMEM (2 = epilogue overlaps the next main loop inside the CTA)
   int m_tiles;     // pixel tiles in total (tiles_x * tiles_y * N)
   int n_tiles;     // channel tiles
   int work_items;  // ceil(m_tiles / msub) * n_tiles

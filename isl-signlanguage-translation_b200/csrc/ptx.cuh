@@ -47,14 +47,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 // Bounded wait: a protocol bug must surface as a trapped launch (an error the host sees), never
 // as a hung GPU. 2 s is three orders of magnitude above any legitimate wait in these kernels.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = globaltimer_ns();
+  // fast path: try_wait suspends the thread in hardware for a while, so a handful of attempts covers every
+  // legitimate wait; the (slow) global timer is only consulted after thousands of failed attempts
   uint32_t spins = 0;
+  uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > 2000000000ull) {
-      printf("islpose: mbarrier wait timed out (block %d,%d thread %d bar 0x%x parity %u)\n",
-             blockIdx.x, blockIdx.y, threadIdx.x, bar, parity);
-      __trap();
+    if ((++spins & 0xfff) == 0) {
+      const uint64_t now = globaltimer_ns();
+      if (t0 == 0) {
+        t0 = now;
+      } else if (now - t0 > 2000000000ull) {
+        printf("islpose: mbarrier wait timed out (block %d,%d thread %d bar 0x%x parity %u)\n", blockIdx.x, blockIdx.y,
+               threadIdx.x, bar, parity);
+        __trap();
+      }
     }
   }
 }
