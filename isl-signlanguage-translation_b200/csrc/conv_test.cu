@@ -61,7 +61,7 @@ struct Cfg {
   int N, H, W, in_c, in_cstride, coff, cout, k;
   bool f32_out, bf16_out;
   int force_n_tile, force_stages;
-  int variant, msub, acc_bufs;
+  int variant, msub, acc_bufs, bo_mode, no_loads;
 };
 
 static int run_cfg(const Cfg& c, bool timing) {
@@ -118,6 +118,8 @@ static int run_cfg(const Cfg& c, bool timing) {
   d.variant = c.variant;
   d.msub = c.msub;
   d.acc_bufs = c.acc_bufs;
+  d.halo_base_offset_mode = c.bo_mode;
+  d.debug_no_loads = c.no_loads;
 
   ConvLaunch L;
   char err[256];
@@ -173,7 +175,7 @@ static int run_cfg(const Cfg& c, bool timing) {
         if (raw[p * out_cstride + co] != 0x7f7f) ++bad_pad;
     }
   }
-  const bool ok = (!c.f32_out || err32 <= 2e-3 * (1.0 + max_ref)) && (!c.bf16_out || err16 <= 1e-2) && bad_pad == 0;
+  const bool ok = c.no_loads || (!c.f32_out || err32 <= 2e-3 * (1.0 + max_ref)) && (!c.bf16_out || err16 <= 1e-2) && bad_pad == 0;
   float ms = 0.f;
   if (timing && ok) {
     cudaEvent_t e0, e1;
@@ -265,6 +267,112 @@ static int run_v2_suite() {
   return fails ? 1 : 0;
 }
 
+static int run_v3_suite() {
+  // halo variant: both base-offset conventions on a small case first (one of them is wrong by construction),
+  // then correctness on awkward shapes and timings against v1
+  const Cfg cfgs[] = {
+      {"v3 3x3 64->64 16x8", 1, 16, 8, 64, 64, 0, 64, 3, true, true, 0, 0, 3, 0, 0, 0},
+      {"v3 7x7 128->128 23x41 b2", 2, 23, 41, 128, 128, 0, 128, 7, true, true, 0, 0, 3, 0, 0, 0},
+      {"v3 7x7 192->128 23x41 b2", 2, 23, 41, 192, 192, 0, 128, 7, true, true, 0, 0, 3, 0, 0, 0},
+      {"v3 3x3 slice 96/288->96", 2, 23, 41, 96, 288, 96, 96, 3, true, true, 0, 0, 3, 0, 0, 0},
+      {"v3 3x3 512->38 f32 46x62", 1, 46, 62, 512, 512, 0, 38, 3, true, true, 0, 0, 3, 0, 0, 0},
+      {"v1 7x7 128->128 92x164 b8", 8, 92, 164, 128, 128, 0, 128, 7, false, true, 0, 0, 1, 0, 0, 0},
+      {"v3 7x7 128->128 92x164 b8", 8, 92, 164, 128, 128, 0, 128, 7, false, true, 0, 0, 3, 0, 0, 0},
+      {"v3 7x7 128->128 92x164 b8 s2", 8, 92, 164, 128, 128, 0, 128, 7, false, true, 0, 2, 3, 0, 0, 0},
+      {"v3 7x7 128->128 92x164 b8 s6", 8, 92, 164, 128, 128, 0, 128, 7, false, true, 0, 6, 3, 0, 0, 0},
+      {"v1 7x7 192->128 60x80 b8", 8, 60, 80, 192, 192, 0, 128, 7, false, true, 0, 0, 1, 0, 0, 0},
+      {"v3 7x7 192->128 60x80 b8", 8, 60, 80, 192, 192, 0, 128, 7, false, true, 0, 0, 3, 0, 0, 0},
+      {"v1 3x3 128->128 368x496 b2", 2, 368, 496, 128, 128, 0, 128, 3, false, true, 0, 0, 1, 0, 0, 0},
+      {"v3 3x3 128->128 368x496 b2", 2, 368, 496, 128, 128, 0, 128, 3, false, true, 0, 0, 3, 0, 0, 0},
+      {"v1 3x3 512->512 92x164 b2 (nt256)", 2, 92, 164, 512, 512, 0, 512, 3, false, true, 0, 0, 1, 0, 0, 0},
+      {"v3 3x3 512->512 92x164 b2 nt128", 2, 92, 164, 512, 512, 0, 512, 3, false, true, 128, 0, 3, 0, 0, 0},
+      {"v3 3x3 512->512 92x164 b2 nt256", 2, 92, 164, 512, 512, 0, 512, 3, false, true, 256, 0, 3, 0, 0, 0},
+      {"v1 3x3 256->256 184x328 b2", 2, 184, 328, 256, 256, 0, 256, 3, false, true, 0, 0, 1, 0, 0, 0},
+      {"v3 3x3 256->256 184x328 b2 nt256", 2, 184, 328, 256, 256, 0, 256, 3, false, true, 256, 0, 3, 0, 0, 0},
+      {"auto 3x3 64->64 736x984 b2", 2, 736, 984, 64, 64, 0, 64, 3, false, true, 0, 0, 0, 0, 0, 0},
+      {"v3 3x3 64->64 736x984 b2", 2, 736, 984, 64, 64, 0, 64, 3, false, true, 0, 0, 3, 0, 0, 0},
+      {"v1 3x3 288->96 92x164 b8", 8, 92, 164, 288, 288, 0, 96, 3, false, true, 0, 0, 1, 0, 0, 0},
+      {"v3 3x3 288->96 92x164 b8", 8, 92, 164, 288, 288, 0, 96, 3, false, true, 0, 0, 3, 0, 0, 0},
+      {"v1 7x7 128->128 23x31 b8", 8, 23, 31, 128, 128, 0, 128, 7, false, true, 0, 0, 1, 0, 0, 0},
+      {"v3 7x7 128->128 23x31 b8", 8, 23, 31, 128, 128, 0, 128, 7, false, true, 0, 0, 3, 0, 0, 0},
+  };
+  int fails = 0;
+  for (const Cfg& c : cfgs) {
+    const int r = run_cfg(c, true);
+    if (r == 3) {
+      printf("context lost, stopping\n");
+      return 3;
+    }
+    fails += r;
+  }
+  printf("%s: %d failing configuration(s)\n", fails ? "FAILED" : "DONE", fails);
+  return 0;
+}
+
+static int run_v4_suite() {
+  // swapped operands (weights = M, pixels = N): correctness first, then timings against the best other variant
+  const Cfg cfgs[] = {
+      {"v4 1x1 64->128 16x8", 1, 8, 16, 64, 64, 0, 128, 1, true, true, 0, 0, 4, 0, 0, 0, 0},
+      {"v4 3x3 128->128 23x41 b2", 2, 23, 41, 128, 128, 0, 128, 3, true, true, 0, 0, 4, 0, 0, 0, 0},
+      {"v4 7x7 192->128 23x41 b2", 2, 23, 41, 192, 192, 0, 128, 7, true, true, 0, 0, 4, 0, 0, 0, 0},
+      {"v4 3x3 slice 96/288->96", 2, 23, 41, 96, 288, 96, 96, 3, true, true, 0, 0, 4, 0, 0, 0, 0},
+      {"v4 1x1 128->512 46x62", 1, 46, 62, 128, 128, 0, 512, 1, true, true, 0, 0, 4, 0, 0, 0, 0},
+      {"v4 1x1 512->38 head f32", 2, 23, 41, 512, 512, 0, 38, 1, true, true, 0, 0, 4, 0, 0, 0, 0},
+      {"v4 7x7 160->128 23x23 b3", 3, 23, 23, 160, 160, 0, 128, 7, true, true, 0, 0, 4, 0, 0, 0, 0},
+      {"v1 7x7 128->128 92x164 b8", 8, 92, 164, 128, 128, 0, 128, 7, false, true, 0, 0, 1, 0, 0, 0, 0},
+      {"v4 7x7 128->128 92x164 b8", 8, 92, 164, 128, 128, 0, 128, 7, false, true, 0, 0, 4, 0, 0, 0, 0},
+      {"v1 7x7 192->128 60x80 b8", 8, 60, 80, 192, 192, 0, 128, 7, false, true, 0, 0, 1, 0, 0, 0, 0},
+      {"v4 7x7 192->128 60x80 b8", 8, 60, 80, 192, 192, 0, 128, 7, false, true, 0, 0, 4, 0, 0, 0, 0},
+      {"v1 3x3 128->128 368x496 b2", 2, 368, 496, 128, 128, 0, 128, 3, false, true, 0, 0, 1, 0, 0, 0, 0},
+      {"v4 3x3 128->128 368x496 b2", 2, 368, 496, 128, 128, 0, 128, 3, false, true, 0, 0, 4, 0, 0, 0, 0},
+      {"v1 3x3 64->128 368x496 b2", 2, 368, 496, 64, 64, 0, 128, 3, false, true, 0, 0, 1, 0, 0, 0, 0},
+      {"v4 3x3 64->128 368x496 b2", 2, 368, 496, 64, 64, 0, 128, 3, false, true, 0, 0, 4, 0, 0, 0, 0},
+      {"v1 3x3 288->96 92x164 b8", 8, 92, 164, 288, 288, 0, 96, 3, false, true, 0, 0, 1, 0, 0, 0, 0},
+      {"v4 3x3 288->96 92x164 b8", 8, 92, 164, 288, 288, 0, 96, 3, false, true, 0, 0, 4, 0, 0, 0, 0},
+      {"v1 3x3 96->96 slice 92x164 b8", 8, 92, 164, 96, 288, 96, 96, 3, false, true, 0, 0, 1, 0, 0, 0, 0},
+      {"v4 3x3 96->96 slice 92x164 b8", 8, 92, 164, 96, 288, 96, 96, 3, false, true, 0, 0, 4, 0, 0, 0, 0},
+      {"v1 3x3 512->512 92x164 b2 nt256", 2, 92, 164, 512, 512, 0, 512, 3, false, true, 0, 0, 1, 0, 0, 0, 0},
+      {"v4 3x3 512->512 92x164 b2", 2, 92, 164, 512, 512, 0, 512, 3, false, true, 0, 0, 4, 0, 0, 0, 0},
+      {"v1 3x3 512->128 92x92 b8", 8, 92, 92, 512, 512, 0, 128, 3, false, true, 0, 0, 1, 0, 0, 0, 0},
+      {"v4 3x3 512->128 92x92 b8", 8, 92, 92, 512, 512, 0, 128, 3, false, true, 0, 0, 4, 0, 0, 0, 0},
+      {"v1 1x1 128->128 92x124 b8", 8, 92, 124, 128, 128, 0, 128, 1, false, true, 0, 0, 1, 0, 0, 0, 0},
+      {"v4 1x1 128->128 92x124 b8", 8, 92, 124, 128, 128, 0, 128, 1, false, true, 0, 0, 4, 0, 0, 0, 0},
+      {"v1 7x7 128->128 23x31 b8", 8, 23, 31, 128, 128, 0, 128, 7, false, true, 0, 0, 1, 0, 0, 0, 0},
+      {"v4 7x7 128->128 23x31 b8", 8, 23, 31, 128, 128, 0, 128, 7, false, true, 0, 0, 4, 0, 0, 0, 0},
+      {"v1 7x7 128->128 46x62 b8", 8, 46, 62, 128, 128, 0, 128, 7, false, true, 0, 0, 1, 0, 0, 0, 0},
+      {"v4 7x7 128->128 46x62 b8", 8, 46, 62, 128, 128, 0, 128, 7, false, true, 0, 0, 4, 0, 0, 0, 0},
+  };
+  int fails = 0;
+  for (const Cfg& c : cfgs) {
+    const int r = run_cfg(c, true);
+    if (r == 3) {
+      printf("context lost, stopping\n");
+      return 3;
+    }
+    fails += r;
+  }
+  printf("%s: %d failing configuration(s)\n", fails ? "FAILED" : "DONE", fails);
+  return 0;
+}
+
+static int run_limits_suite() {
+  // where is the ceiling? same layers with and without TMA traffic (no_loads: results are garbage by design)
+  const Cfg cfgs[] = {
+      {"7x7 128 nt128 s3 loads", 8, 92, 164, 128, 128, 0, 128, 7, false, true, 0, 3, 1, 0, 0, 0, 0},
+      {"7x7 128 nt128 s3 NO loads", 8, 92, 164, 128, 128, 0, 128, 7, false, true, 0, 3, 1, 0, 0, 0, 1},
+      {"7x7 128 nt128 s6 NO loads (1/SM)", 8, 92, 164, 128, 128, 0, 128, 7, false, true, 0, 6, 1, 0, 0, 0, 1},
+      {"7x7 128 nt64 s3 NO loads", 8, 92, 164, 128, 128, 0, 128, 7, false, true, 64, 3, 1, 0, 0, 0, 1},
+      {"3x3 512 nt256 s2 loads", 2, 92, 164, 512, 512, 0, 512, 3, false, true, 256, 2, 1, 0, 0, 0, 0},
+      {"3x3 512 nt256 s2 NO loads", 2, 92, 164, 512, 512, 0, 512, 3, false, true, 256, 2, 1, 0, 0, 0, 1},
+      {"3x3 512 nt128 s3 NO loads", 2, 92, 164, 512, 512, 0, 512, 3, false, true, 128, 3, 1, 0, 0, 0, 1},
+      {"3x3 512 nt256 s4 NO loads (1/SM)", 2, 92, 164, 512, 512, 0, 512, 3, false, true, 256, 4, 1, 0, 0, 0, 1},
+  };
+  for (const Cfg& c : cfgs) {
+    if (run_cfg(c, true) == 3) return 3;
+  }
+  return 0;
+}
+
 int main(int argc, char** argv) {
   const Cfg cfgs[] = {
       // name                       N   H    W  in_c cstr coff cout k  f32   bf16  ntile stages
@@ -303,6 +411,9 @@ int main(int argc, char** argv) {
   };
   const int n = sizeof(cfgs) / sizeof(cfgs[0]);
   if (argc > 1 && std::string(argv[1]) == "v2") return run_v2_suite();
+  if (argc > 1 && std::string(argv[1]) == "v3") return run_v3_suite();
+  if (argc > 1 && std::string(argv[1]) == "limits") return run_limits_suite();
+  if (argc > 1 && std::string(argv[1]) == "v4") return run_v4_suite();
   int fails = 0;
   for (int i = 0; i < n; ++i) {
     if (argc > 1 && atoi(argv[1]) != i) continue;

@@ -95,6 +95,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int s = it % a.stages;
           const uint32_t ph = (it / a.stages) & 1;
           ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          if (a.debug_no_loads && it >= a.stages) {  // measurement aid: the MMAs re-read what the ring already holds
+            ptx::mbar_arrive(bar_full + 8 * s);
+            continue;
+          }
           ptx::mbar_arrive_expect_tx(bar_full + 8 * s, tx_bytes);
           ptx::tma_load_4d(sA0 + s * kASlotBytes, &tmA, bar_full + 8 * s, cb * 64, x0 + kx - a.pad,
                            y0 + ky - a.pad, img);
@@ -409,6 +413,330 @@ conv_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ v3
+// Halo variant for k > 1: the CTA's 8 x 16 pixel tile needs, per 64-channel block, the (8+2p) x (16+2p) input
+// pixels around it. They are fetched ONCE as one TMA box of 16 x (16+2p) pixel rows (pitch 16 keeps every 8-row
+// group of the operand on the same swizzle phase) and all k*k taps read shifted windows of that box straight from
+// shared memory: the A operand of tap (ky, kx) starts at halo row ky*16 + kx, its 8-row groups (one image row of
+// the tile each) are 16 rows = 2048 B apart, and the swizzle is a function of the absolute shared-memory
+// address (TMA wrote it that way, the MMA reads it that way), so the descriptor's base offset stays 0. Only the weights stream from L2 per tap, which cuts the bytes delivered to the SM per FLOP by ~45 %
+// (7x7) / ~30 % (3x3) - the v1 kernel is bound by L2->SM delivery (profiles/r1_ncu_full_conv7x7_v1.txt).
+__global__ void __launch_bounds__(kThreads, 2)
+conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const ConvArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* const gbase = smem_raw + (base - raw);
+
+  const uint32_t halo_bytes = 128u * a.halo_w * a.halo_h;
+  const uint32_t halo_slot = (halo_bytes + 1023u) & ~1023u;
+  const uint32_t sH = base;                       // one halo buffer
+  const uint32_t sB0 = base + halo_slot;          // weight ring
+  const uint32_t ctrl = sB0 + a.stages * a.b_stage_bytes;
+  uint8_t* const gctrl = gbase + (ctrl - base);
+  const uint32_t bar_full = ctrl;         // weight stage filled
+  const uint32_t bar_empty = ctrl + 64;   // weight stage consumed
+  const uint32_t bar_accum = ctrl + 128;
+  const uint32_t tmem_slot = ctrl + 136;
+  const uint32_t bar_hfull = ctrl + 144;  // halo tile landed
+  const uint32_t bar_hempty = ctrl + 152; // all taps of this channel block have read the halo tile
+  volatile uint32_t* const tmem_slot_g = reinterpret_cast<volatile uint32_t*>(gctrl + 136);
+  float* const s_bias = reinterpret_cast<float*>(gctrl + 256);
+  float* const s_slope = s_bias + 256;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int t = blockIdx.x;
+  const int tx = t % a.tiles_x;
+  const int ty = (t / a.tiles_x) % a.tiles_y;
+  const int img = t / (a.tiles_x * a.tiles_y);
+  const int x0 = tx * a.bw;
+  const int y0 = ty * a.bh;
+  const int n0 = blockIdx.y * a.n_tile;
+  const int cblocks = (a.cin_k16 + 3) >> 2;
+  const int taps = a.ksize * a.ksize;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < a.stages; ++s) {
+      ptx::mbar_init(bar_full + 8 * s, 1);
+      ptx::mbar_init(bar_empty + 8 * s, 1);
+    }
+    ptx::mbar_init(bar_accum, 1);
+    ptx::mbar_init(bar_hfull, 1);
+    ptx::mbar_init(bar_hempty, 1);
+    ptx::mbar_fence_init();
+    ptx::prefetch_tensormap(&tmA);
+    ptx::prefetch_tensormap(&tmB);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, a.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  if (warp >= 2) {
+    for (int i = threadIdx.x - 64; i < a.n_tile; i += kThreads - 64) {
+      s_bias[i] = a.bias[n0 + i];
+      s_slope[i] = a.slope[n0 + i];
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_g;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int cb = 0; cb < cblocks; ++cb) {
+        ptx::mbar_wait(bar_hempty, (cb & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(bar_hfull, halo_bytes);
+        ptx::tma_load_4d(sH, &tmA, bar_hfull, cb * 64, x0 - a.pad, y0 - a.pad, img);
+        for (int tap = 0; tap < taps; ++tap, ++it) {
+          const int s = it % a.stages;
+          const uint32_t ph = (it / a.stages) & 1;
+          ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          ptx::mbar_arrive_expect_tx(bar_full + 8 * s, 128u * a.n_tile);
+          ptx::tma_load_3d(sB0 + s * a.b_stage_bytes, &tmB, bar_full + 8 * s, cb * 64, n0, tap);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = ptx::umma_idesc_bf16(128, a.n_tile);
+      const uint32_t sbo = 128u * a.halo_w;  // one image row of the tile further down = halo_w pixel rows
+      int it = 0;
+      for (int cb = 0; cb < cblocks; ++cb) {
+        ptx::mbar_wait(bar_hfull, cb & 1);
+        ptx::tc_fence_after();
+        const int ksteps = min(4, a.cin_k16 - cb * 4);
+        for (int tap = 0; tap < taps; ++tap, ++it) {
+          const int ky = tap / a.ksize;
+          const int kx = tap - ky * a.ksize;
+          const int s = it % a.stages;
+          const uint32_t ph = (it / a.stages) & 1;
+          ptx::mbar_wait(bar_full + 8 * s, ph);
+          ptx::tc_fence_after();
+          const uint32_t arow = sH + 128u * (ky * a.halo_w + kx);
+          // measured on B200: the swizzle XOR is taken from the absolute shared-memory address, so a window that
+          // starts on any 128-byte row needs base offset 0 (mode 1 = the start row's phase, kept for the bring-up test)
+          const uint32_t bo = a.halo_bo_mode == 1 ? ((arow >> 7) & 7u) : 0u;
+          const uint64_t da = ptx::umma_desc_sw128_strided(arow, sbo, bo);
+          const uint64_t db = ptx::umma_desc_sw128(sB0 + s * a.b_stage_bytes);
+          for (int k = 0; k < ksteps; ++k) {
+            ptx::umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(bar_empty + 8 * s);
+        }
+        ptx::umma_commit(bar_hempty);  // the halo tile may be overwritten once these MMAs have retired
+      }
+      ptx::umma_commit(bar_accum);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int py = row / a.bw;
+    const int px = row - py * a.bw;
+    const int x = x0 + px;
+    const int y = y0 + py;
+    const bool valid = (x < a.W) && (y < a.H);
+    const long long pix = (static_cast<long long>(img) * a.H + y) * a.W + x;
+    ptx::mbar_wait(bar_accum, 0);
+    ptx::tc_fence_after();
+    for (int c = 0; c < a.n_tile; c += 32) {
+      uint32_t r[32];
+      ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, r);
+      ptx::tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float acc = __uint_as_float(r[i]) + s_bias[c + i];
+        v[i] = acc > 0.f ? acc : acc * s_slope[c + i];
+      }
+      if (valid) {
+        if (a.out_bf16 != nullptr) {
+          __nv_bfloat16* dst = a.out_bf16 + pix * a.out_pix_stride + n0 + c;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (n0 + c + 8 * j < a.cout_store) {
+              uint4 pk;
+              __nv_bfloat162 h;
+              h = __floats2bfloat162_rn(v[8 * j + 0], v[8 * j + 1]);
+              pk.x = *reinterpret_cast<uint32_t*>(&h);
+              h = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+              pk.y = *reinterpret_cast<uint32_t*>(&h);
+              h = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
+              pk.z = *reinterpret_cast<uint32_t*>(&h);
+              h = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+              pk.w = *reinterpret_cast<uint32_t*>(&h);
+              *reinterpret_cast<uint4*>(dst + 8 * j) = pk;
+            }
+          }
+        }
+        if (a.out_f32 != nullptr) {
+          const long long plane = static_cast<long long>(a.H) * a.W;
+          float* dst = a.out_f32 + (static_cast<long long>(img) * a.out_f32_channels + n0 + c) * plane +
+                       static_cast<long long>(y) * a.W + x;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (n0 + c + i < a.cout) dst[i * plane] = v[i];
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tmem_dealloc(tmem_base, a.tmem_cols);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------ v4
+// Swapped operands for 65..128 output channels. Measured on B200 (profiles/conv_limits_r1.log): the MMA loop runs
+// at the same speed with and without TMA traffic, and throughput follows the instruction shape (N=64: 558, N=128:
+// 910, N=256: 1340 TFLOP/s) - every tcgen05.mma carries a fixed cost that only a larger instruction amortises. A
+// 128-channel layer cannot offer N=256 channels, but it can offer 256 pixels: D^T[channels, pixels] = W * X^T with
+// the weights as the M=128 operand (rows beyond Cout are zero-filled by TMA) and a 256-pixel activation box as N.
+// The accumulator is then [128 lanes = channels] x [256 columns = pixels]; epilogue lane = channel.
+__global__ void __launch_bounds__(kThreads, 2)
+conv_umma_swapped_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const ConvArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* const gbase = smem_raw + (base - raw);
+
+  constexpr uint32_t kWBytes = 128 * 128;   // 128 output channels x 64 input channels
+  constexpr uint32_t kXBytes = 256 * 128;   // up to 256 pixels x 64 input channels
+  const uint32_t sW0 = base;
+  const uint32_t sX0 = base + a.stages * kWBytes;
+  const uint32_t ctrl = sX0 + a.stages * kXBytes;
+  uint8_t* const gctrl = gbase + (ctrl - base);
+  const uint32_t bar_full = ctrl;
+  const uint32_t bar_empty = ctrl + 64;
+  const uint32_t bar_accum = ctrl + 128;
+  const uint32_t tmem_slot = ctrl + 136;
+  volatile uint32_t* const tmem_slot_g = reinterpret_cast<volatile uint32_t*>(gctrl + 136);
+  long long* const s_pix = reinterpret_cast<long long*>(gctrl + 256);  // 256 pixel offsets (-1 = outside)
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int t = blockIdx.x;
+  const int tx = t % a.tiles_x;
+  const int ty = (t / a.tiles_x) % a.tiles_y;
+  const int img = t / (a.tiles_x * a.tiles_y);
+  const int x0 = tx * a.bw;
+  const int y0 = ty * a.bh;
+  const int n0 = blockIdx.y * 128;
+  const int cblocks = (a.cin_k16 + 3) >> 2;
+  const int taps = a.ksize * a.ksize;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < a.stages; ++s) {
+      ptx::mbar_init(bar_full + 8 * s, 1);
+      ptx::mbar_init(bar_empty + 8 * s, 1);
+    }
+    ptx::mbar_init(bar_accum, 1);
+    ptx::mbar_fence_init();
+    ptx::prefetch_tensormap(&tmA);
+    ptx::prefetch_tensormap(&tmB);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, a.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  if (warp >= 2) {
+    for (int j = threadIdx.x - 64; j < 256; j += kThreads - 64) {
+      const int py = j / a.bw;
+      const int px = j - py * a.bw;
+      const int x = x0 + px, y = y0 + py;
+      const bool ok = j < a.bw * a.bh && x < a.W && y < a.H;
+      s_pix[j] = ok ? (static_cast<long long>(img) * a.H + y) * a.W + x : -1;
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_g;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t tx_bytes = kWBytes + 128u * a.bw * a.bh;
+      int it = 0;
+      for (int tap = 0; tap < taps; ++tap) {
+        const int ky = tap / a.ksize;
+        const int kx = tap - ky * a.ksize;
+        for (int cb = 0; cb < cblocks; ++cb, ++it) {
+          const int s = it % a.stages;
+          const uint32_t ph = (it / a.stages) & 1;
+          ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          ptx::mbar_arrive_expect_tx(bar_full + 8 * s, tx_bytes);
+          ptx::tma_load_3d(sW0 + s * kWBytes, &tmB, bar_full + 8 * s, cb * 64, n0, tap);
+          ptx::tma_load_4d(sX0 + s * kXBytes, &tmA, bar_full + 8 * s, cb * 64, x0 + kx - a.pad, y0 + ky - a.pad, img);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = ptx::umma_idesc_bf16(128, a.n_pix);
+      int it = 0;
+      for (int tap = 0; tap < taps; ++tap) {
+        for (int cb = 0; cb < cblocks; ++cb, ++it) {
+          const int s = it % a.stages;
+          const uint32_t ph = (it / a.stages) & 1;
+          ptx::mbar_wait(bar_full + 8 * s, ph);
+          ptx::tc_fence_after();
+          const uint64_t dw = ptx::umma_desc_sw128(sW0 + s * kWBytes);
+          const uint64_t dx = ptx::umma_desc_sw128(sX0 + s * kXBytes);
+          const int ksteps = min(4, a.cin_k16 - cb * 4);
+          for (int k = 0; k < ksteps; ++k) {
+            ptx::umma_bf16(tmem_base, dw + 2 * k, dx + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(bar_empty + 8 * s);
+        }
+      }
+      ptx::umma_commit(bar_accum);
+    }
+  } else {
+    // epilogue: this thread owns output channel n0 + 32*q + lane for all pixels of the tile
+    const int q = warp & 3;
+    const int ch = n0 + q * 32 + lane;
+    const float bias = a.bias[ch];
+    const float slope = a.slope[ch];
+    const bool st16 = a.out_bf16 != nullptr && ch < a.cout_store;
+    const bool st32 = a.out_f32 != nullptr && ch < a.cout;
+    const long long plane = static_cast<long long>(a.H) * a.W;
+    ptx::mbar_wait(bar_accum, 0);
+    ptx::tc_fence_after();
+    const int npix = a.bw * a.bh;
+    for (int c = 0; c < npix; c += 32) {
+      uint32_t r[32];
+      ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, r);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const long long pix = s_pix[c + i];  // same for the whole warp: no divergence
+        if (pix < 0) continue;
+        const float acc = __uint_as_float(r[i]) + bias;
+        const float v = acc > 0.f ? acc : acc * slope;
+        // 32 lanes = 32 neighbouring channels of one pixel: one 64-byte segment per warp store
+        if (st16) a.out_bf16[pix * a.out_pix_stride + ch] = __float2bfloat16_rn(v);
+        if (st32) {
+          const long long im = pix / plane;
+          a.out_f32[(im * a.out_f32_channels + ch) * plane + (pix - im * plane)] = v;
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tmem_dealloc(tmem_base, a.tmem_cols);
+  }
+}
+
 // ------------------------------------------------------------------ host side
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -460,22 +788,50 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   a.H = d.H;
   a.W = d.W;
 
-  // Pixel tile: the box (bw x bh) with bw*bh <= 128 that covers the image with the fewest tiles.
-  int bw = d.force_bw, bh = d.force_bh;
-  if (bw <= 0 || bh <= 0) {
-    long long best = -1;
-    for (int w = 1; w <= 128 && w <= d.W; ++w) {
-      int h = 128 / w;
-      if (h > d.H) h = d.H;
-      const long long tiles = static_cast<long long>((d.W + w - 1) / w) * ((d.H + h - 1) / h);
-      if (best < 0 || tiles < best || (tiles == best && w * h < bw * bh)) {
-        best = tiles;
-        bw = w;
-        bh = h;
+  // Cost model fitted to the measurements in profiles/ (cycles per CTA): a tcgen05.mma of M=128 x N x K=16 costs about
+  // 207 + N/2 when the CTA has its SM to itself and 192 + N when two CTAs share the SM; `epi` is the epilogue.
+  const int kblocks = d.ksize * d.ksize * ((d.in_c + 63) / 64);
+  auto estimate = [&](long long tiles, int n, double epi) {
+    const double per_mma = tiles <= 148 ? 207.0 + n / 2.0 : 192.0 + n;
+    return static_cast<double>((tiles + 295) / 296) * (kblocks * 4.0 * per_mma + epi);
+  };
+  auto best_box = [&](int cap, bool wave_model, int* obw, int* obh) {
+    double best = -1;
+    for (int w = 1; w <= cap && w <= d.W && w <= 256; ++w) {
+      const int hmax = cap / w < d.H ? cap / w : d.H;
+      for (int h = wave_model ? 1 : hmax; h <= hmax && h <= 256; ++h) {
+        const long long tiles = static_cast<long long>((d.W + w - 1) / w) * ((d.H + h - 1) / h) * d.N;
+        const double cost = wave_model ? estimate(tiles, (w * h + 15) / 16 * 16, 12000.0) + 1e-6 * tiles
+                                       : static_cast<double>(tiles) + 1e-3 * (w * h);
+        if (best < 0 || cost < best) {
+          best = cost;
+          *obw = w;
+          *obh = h;
+        }
       }
     }
+    return best;
+  };
+  // Variant 4 (swapped operands: weights = M, up to 256 pixels = N) for long reductions with 65..128 output
+  // channels, when the model predicts a win (measured: 7x7 128->128 at 92x164x8: 905 -> 1020 TFLOP/s,
+  // 7x7 192->128 at 60x80x8: 610 -> 792; slower on 3x3 / 1x1 layers and on small grids).
+  int want_variant = d.variant;
+  int bw = d.force_bw, bh = d.force_bh;
+  if (want_variant <= 0 && d.ksize == 7 && d.cout > 64 && d.cout <= 128 && d.force_n_tile <= 0 && bw <= 0) {
+    int w1 = 0, h1 = 0, w4 = 0, h4 = 0;
+    const double tiles1 = best_box(128, false, &w1, &h1);
+    const double t1 = estimate(static_cast<long long>(tiles1), 128, 3000.0);
+    const double t4 = best_box(256, true, &w4, &h4);
+    if (t4 < 0.95 * t1) want_variant = 4;
   }
-  if (bw * bh > 128 || bw > 256 || bh > 256) return fail(err, errlen, "conv: bad pixel tile %lldx%lld", bw, bh);
+  if (want_variant == 3) {
+    if (d.ksize == 1) return fail(err, errlen, "conv: the halo variant needs k > 1");
+    bw = 8;  // one 8-row operand group = 8 neighbouring pixels of one image row
+    bh = 16;
+  }
+  const int pix_cap = want_variant == 4 ? 256 : 128;  // v4: the pixels are the N operand (up to 256)
+  if (bw <= 0 || bh <= 0) best_box(pix_cap, want_variant == 4, &bw, &bh);
+  if (bw * bh > pix_cap || bw > 256 || bh > 256) return fail(err, errlen, "conv: bad pixel tile %lldx%lld", bw, bh);
   a.bw = bw;
   a.bh = bh;
   a.tiles_x = (d.W + bw - 1) / bw;
@@ -485,7 +841,7 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   // Channel tile (UMMA N): multiple of 16, at most 256. 128 keeps a stage at 32 KB so that two CTAs fit on one SM
   // with a 3-deep ring each: the second CTA's main loop hides the first one's epilogue and pipeline fill.
   const int cout16 = (d.cout + 15) / 16 * 16;
-  int n_tile = d.force_n_tile;
+  int n_tile = want_variant == 4 ? 128 : d.force_n_tile;
   if (n_tile <= 0) {
     // An M=128 x N=128 tile is shared-memory-bandwidth bound (each K=16 MMA reads 8 KB in 64 cycles while TMA writes
     // as much): measured ~900 TFLOP/s. N=256 halves the activation traffic per FLOP: measured 1243 TFLOP/s on
@@ -507,7 +863,7 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   // Measured on B200 (profiles/conv_test_v2_r1.log): 128-wide channel tiles run best as one tile per CTA with two
   // CTAs per SM (v1); narrower tiles (64, 96) gain 20-65 % from the persistent variant with two pixel sub-tiles per
   // weight stage, as long as the grid is large enough to give every persistent CTA several work items.
-  int variant = d.variant;
+  int variant = want_variant;
   if (variant <= 0) variant = (n_tile <= 96 && m_tiles * n_tiles >= 2 * 296) ? 2 : 1;
   int msub = 1;
   int auto_stages = 0;
@@ -530,10 +886,25 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   a.work_items = static_cast<int>((m_tiles + msub - 1) / msub) * n_tiles;
   out->variant = variant;
 
-  const uint32_t per_stage = msub * kASlotBytes + a.b_stage_bytes;
+  if (variant == 3) {
+    a.halo_w = 16;
+    a.halo_h = 16 + 2 * a.pad;
+    a.halo_bo_mode = d.halo_base_offset_mode;
+  }
+  a.debug_no_loads = d.debug_no_loads;
+  if (variant == 4) {
+    if (d.force_n_tile > 0 && d.force_n_tile != 128) return fail(err, errlen, "conv: the swapped variant uses 128-channel tiles");
+    a.n_tile = 128;
+    a.n_pix = (bw * bh + 15) / 16 * 16;
+    a.tmem_cols = 256;
+    a.b_stage_bytes = 128 * 128;
+  }
+  const uint32_t per_stage = variant == 4 ? (128u * 128u + 256u * 128u)
+                                          : (variant == 3 ? 0u : msub * kASlotBytes) + a.b_stage_bytes;
   int stages = d.force_stages > 0 ? d.force_stages : auto_stages;
   if (stages <= 0) {
-    const uint32_t budget = variant == 2 ? 200u * 1024u : 110u * 1024u - kCtrlBytes - 1024u;  // v1: two CTAs per SM
+    uint32_t budget = variant == 2 ? 200u * 1024u : 110u * 1024u - kCtrlBytes - 1024u;  // v1: two CTAs per SM
+    if (variant == 3) budget -= (128u * a.halo_w * a.halo_h + 1023u) & ~1023u;
     stages = static_cast<int>(budget / per_stage);
     if (stages < 2) stages = 2;
     const int iters = d.ksize * d.ksize * ((a.cin_k16 + 3) / 4);
@@ -543,6 +914,7 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   if (stages < 1) stages = 1;
   a.stages = stages;
   out->smem_bytes = stages * per_stage + kCtrlBytes + 1024;
+  if (variant == 3) out->smem_bytes += (128u * a.halo_w * a.halo_h + 1023u) & ~1023u;
   if (out->smem_bytes > 227u * 1024u) return fail(err, errlen, "conv: shared memory budget exceeded (%lld B)", out->smem_bytes);
 
   a.out_bf16 = d.out_bf16;
@@ -563,6 +935,10 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
                           static_cast<cuuint64_t>(d.in_cstride) * 2 * d.W,
                           static_cast<cuuint64_t>(d.in_cstride) * 2 * d.W * d.H};
     cuuint32_t box[4] = {64, static_cast<cuuint32_t>(bw), static_cast<cuuint32_t>(bh), 1};
+    if (variant == 3) {
+      box[1] = static_cast<cuuint32_t>(a.halo_w);
+      box[2] = static_cast<cuuint32_t>(a.halo_h);
+    }
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = encode(&out->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(d.in), gdim,
                         gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -575,7 +951,7 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
     cuuint64_t gdim[3] = {static_cast<cuuint64_t>(w_cin), static_cast<cuuint64_t>(d.cout),
                           static_cast<cuuint64_t>(d.ksize * d.ksize)};
     cuuint64_t gstr[2] = {static_cast<cuuint64_t>(w_cin) * 2, static_cast<cuuint64_t>(w_cin) * 2 * d.cout};
-    cuuint32_t box[3] = {64, static_cast<cuuint32_t>(n_tile), 1};
+    cuuint32_t box[3] = {64, static_cast<cuuint32_t>(variant == 4 ? 128 : n_tile), 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = encode(&out->tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(d.w), gdim, gstr,
                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -601,6 +977,10 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
     cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv_umma_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_umma_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_umma_swapped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail(err, errlen, "conv: cannot raise dynamic shared memory limit (%lld)", e);
     attr_set = true;
   }
@@ -610,6 +990,10 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
 int conv_run(const ConvLaunch& l, cudaStream_t stream) {
   if (l.variant == 2) {
     conv_umma_persistent_kernel<<<l.grid, kThreads, l.smem_bytes, stream>>>(l.tmA, l.tmB, l.args);
+  } else if (l.variant == 3) {
+    conv_umma_halo_kernel<<<l.grid, kThreads, l.smem_bytes, stream>>>(l.tmA, l.tmB, l.args);
+  } else if (l.variant == 4) {
+    conv_umma_swapped_kernel<<<l.grid, kThreads, l.smem_bytes, stream>>>(l.tmA, l.tmB, l.args);
   } else {
     conv_umma_kernel<<<l.grid, kThreads, l.smem_bytes, stream>>>(l.tmA, l.tmB, l.args);
   }

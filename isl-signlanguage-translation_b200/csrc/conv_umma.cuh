@@ -49,7 +49,11 @@ struct ConvDesc {
   int force_n_tile;
   int force_stages;
   int force_bw, force_bh;
-  int variant;  // 0 = automatic, 1 = one tile per CTA (v1), 2 = persistent CTAs with double-buffered TMEM (v2)
+  int variant;  // 0 = automatic, 1 = one tile per CTA (v1), 2 = persistent CTAs with double-buffered TMEM (v2),
+                // 3 = one 8x16 tile per CTA, activation halo tile resident in shared memory (v3),
+                // 4 = swapped operands: weights are the M=128 operand, up to 256 pixels are N (v4)
+  int debug_no_loads;  // measurement aid (v1): after the first ring fill the producer only signals, no TMA traffic
+  int halo_base_offset_mode;  // v3 bring-up switch: 0 = base offset 0 (correct on B200), 1 = start row's swizzle phase
   int msub;     // v2: pixel sub-tiles per work item sharing one weight stage (0 = automatic, 1 or 2)
   int acc_bufs; // v2: TMEM accumulator buffers (0 = automatic, 1 or 2)
 };
@@ -73,6 +77,11 @@ struct ConvArgs {
   int m_tiles;     // pixel tiles in total (tiles_x * tiles_y * N)
   int n_tiles;     // channel tiles
   int work_items;  // ceil(m_tiles / msub) * n_tiles
+  // halo variant
+  int halo_w, halo_h;     // halo box in pixels: 16 x (16 + 2 pad)
+  int halo_bo_mode;
+  int debug_no_loads;
+  int n_pix;       // v4: UMMA N = pixels per tile rounded up to 16
   __nv_bfloat16* out_bf16;
   long long out_pix_stride;
   float* out_f32;

@@ -150,6 +150,19 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;           // SWIZZLE_128B
   return d;
 }
+// Same layout for an operand whose 8-row groups are `sbo_bytes` apart (a multiple of 1024, so every group starts
+// at the same swizzle phase) and whose first row is not 1024-byte aligned: the start row's phase inside the
+// 8-row swizzle pattern goes into the base-offset field [49,52).
+__device__ __forceinline__ uint64_t umma_desc_sw128_strided(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t base_offset) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3fff);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(base_offset & 7) << 49;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
 // Instruction descriptor, kind::f16: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
 // A,B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
 __device__ __forceinline__ uint32_t umma_idesc_bf16(int m, int n) {
