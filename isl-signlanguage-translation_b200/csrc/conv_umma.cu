@@ -10,6 +10,7 @@
 #include "conv_umma.cuh"
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "ptx.cuh"
@@ -817,7 +818,8 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   // 7x7 192->128 at 60x80x8: 610 -> 792; slower on 3x3 / 1x1 layers and on small grids).
   int want_variant = d.variant;
   int bw = d.force_bw, bh = d.force_bh;
-  if (want_variant <= 0 && d.ksize == 7 && d.cout > 64 && d.cout <= 128 && d.force_n_tile <= 0 && bw <= 0) {
+  static const int env_no_v4 = getenv("ISLPOSE_NO_V4") != nullptr;  // debugging aid
+  if (want_variant <= 0 && !env_no_v4 && d.ksize == 7 && d.cout > 64 && d.cout <= 128 && d.force_n_tile <= 0 && bw <= 0) {
     int w1 = 0, h1 = 0, w4 = 0, h4 = 0;
     const double tiles1 = best_box(128, false, &w1, &h1);
     const double t1 = estimate(static_cast<long long>(tiles1), 128, 3000.0);

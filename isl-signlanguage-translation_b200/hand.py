@@ -41,6 +41,14 @@ class Hand(object):
         L = _lib.lib()
         geoms = [scale_geometry(c.shape[0], c.shape[1], self.scale_search, self.boxsize) for c in crops_dev]
         per_crop = [[] for _ in crops_dev]
+        # plan instances are created (and their buffers zero-filled) before the streams fork
+        group_sizes = {}
+        for g in geoms:
+            for si in range(len(self.scale_search)):
+                key = (si, g[si][3], g[si][4])
+                group_sizes[key] = group_sizes.get(key, 0) + 1
+        for (si, hp, wp), cnt in group_sizes.items():
+            self.model.instance(_pow2_at_least(cnt), hp, wp)
         main = torch.cuda.current_stream()
         timing = self.model.timing
         if timing is not None:

@@ -293,6 +293,9 @@ class _Instance:
                 _lib.check(L.islpose_plan_add_conv(handle, C.byref(d)), "islpose_plan_add_conv(%s)" % s["layer"])
         self.flops = L.islpose_plan_conv_flops(handle)
         self.launches = L.islpose_plan_num_launches(handle)
+        # the zero-fills above ran on the current stream, but the plan may be replayed on any stream: make the
+        # buffers (in particular their never-written zero pad channels) globally visible before first use
+        torch.cuda.current_stream().synchronize()
 
     def run(self):
         _lib.check(_lib.lib().islpose_plan_run(self.handle, _lib.stream_ptr()), "islpose_plan_run")

@@ -1,0 +1,152 @@
+"""GPU edge cases: ragged / tiny inputs, batch invariance, the .model contract and C-ABI error paths."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import isl_b200  # noqa: E402
+from isl_b200 import _lib, synth  # noqa: E402
+from isl_b200.body import scale_geometry  # noqa: E402
+from isl_b200.extract import KeypointExtractor  # noqa: E402
+from oracle import openpose_oracle as O  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def dev():
+    torch.cuda.set_device(0)
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def coco(dev):
+    return isl_b200.Body(O.make_flat_weights("coco", seed=1), "coco", scale_search=[0.5, 1.0])
+
+
+@pytest.fixture(scope="module")
+def hand(dev):
+    return isl_b200.Hand(O.make_flat_weights("hand", seed=2))
+
+
+@pytest.mark.parametrize("suite", ["v2", "v3", "v4"])
+def test_conv_variant_suites(suite):
+    exe = os.path.join(ROOT, "build", "conv_test")
+    if not os.path.isfile(exe):
+        pytest.skip("build/conv_test not built")
+    out = subprocess.run([exe, suite], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "FAIL" not in out.stdout, out.stdout[-3000:]
+
+
+def _oracle_body(body, frame, scales):
+    def net_fn(d):
+        p, h = body.model(torch.from_numpy(np.ascontiguousarray(d)).cuda())
+        return p[0].cpu().numpy(), h[0].cpu().numpy()
+
+    return O.body_call(net_fn, frame, "coco", tuple(scales), strict=False)
+
+
+@pytest.mark.parametrize("hw", [(40, 56), (33, 97), (121, 75)])
+def test_tiny_and_odd_frames(dev, coco, hw):
+    """Frames smaller than the Gaussian support (reflection wraps more than once) and odd aspect ratios."""
+    frame = synth.synth_frame(hw[0], hw[1], 31)
+    cand, sub = coco(frame)
+    ocand, osub = _oracle_body(coco, frame, [0.5, 1.0])
+    assert cand.shape == ocand.shape and np.array_equal(cand, ocand)
+    assert sub.shape == osub.shape and np.array_equal(sub, osub)
+
+
+def test_batch_invariance_and_order(dev, coco):
+    frames = [synth.synth_frame(96, 128, s) for s in (1, 2, 3, 4, 5)]
+    together = coco.batch(frames)
+    for f, (c, s) in zip(frames, together):
+        c1, s1 = coco(f)
+        assert c.shape == c1.shape and np.array_equal(c, c1) and np.array_equal(s, s1)
+    # sharding two ways and merging gives the same list
+    ex = KeypointExtractor(coco, None)
+    from isl_b200.extract import merge_shards
+    merged = merge_shards([ex.run_sharded(frames, r, 2, batch_size=2) for r in range(2)], len(frames))
+    for (c, s, _), (c0, s0) in zip(merged, together):
+        assert np.array_equal(c, c0) and np.array_equal(s, s0)
+
+
+def test_non_square_hand_crop(dev, hand):
+    """Hand.__call__ accepts any image (hand.py:24); a non-square crop makes the four network inputs non-square and
+    padded."""
+    crop = synth.synth_frame(90, 131, 9)
+
+    def hand_fn(d):
+        return hand.model(torch.from_numpy(np.ascontiguousarray(d)).cuda())[0].cpu().numpy()
+
+    assert np.array_equal(hand(crop), O.hand_call(hand_fn, crop))
+
+
+def test_model_contract(dev, coco, hand):
+    """What ISLSignPos / TorchModuleWrapper need from body_estimation.model (ISL_Model_parameter.py:44-47,84-85)."""
+    m = coco.model
+    assert m.eval() is m and m.to("cuda") is m and m.cuda() is m
+    params = list(m.parameters())
+    assert len(params) == 2 * 92 and all(isinstance(p, torch.Tensor) for p in params)
+    sd = m.state_dict()
+    assert isl_b200.util.transfer(m, sd).keys() == sd.keys()
+    x = torch.zeros((1, 3, 64, 88), device="cuda")
+    with torch.no_grad():
+        paf, heat = m(x)
+    assert paf.shape == (1, 38, 8, 11) and heat.shape == (1, 19, 8, 11) and paf.dtype == torch.float32 and paf.is_cuda
+    assert hand.model(torch.zeros((2, 3, 48, 48), device="cuda")).shape == (2, 22, 6, 6)
+    with pytest.raises(ValueError):
+        m(torch.zeros((1, 3, 60, 88), device="cuda"))  # not a multiple of 8
+    assert coco.njoint == 19 and coco.npaf == 38 and coco.model_type == "coco"
+
+
+def test_unknown_model_type_falls_back_to_coco(dev, capsys):
+    b = isl_b200.Body(O.make_flat_weights("coco", seed=1), "nonsense")   # body.py:25-29
+    assert "not right model_type" in capsys.readouterr().out
+    assert b.njoint == 19 and b.model_type == "nonsense"
+
+
+def test_abi_error_paths_on_device(dev):
+    L = _lib.lib()
+    handle = C.c_void_p()
+    assert L.islpose_plan_create(C.byref(handle)) == 0
+    buf = torch.zeros(4096, dtype=torch.bfloat16, device="cuda")
+    d = _lib.ConvDesc()
+    d.in_ = buf.data_ptr() + 2   # misaligned
+    d.in_c, d.in_cstride, d.n, d.h, d.w = 64, 64, 1, 4, 4
+    d.weights, d.cout, d.ksize = buf.data_ptr(), 64, 3
+    d.bias = d.slope = buf.data_ptr()
+    d.out_bf16, d.out_cstride = buf.data_ptr(), 64
+    assert L.islpose_plan_add_conv(handle, C.byref(d)) != 0 and b"aligned" in L.islpose_last_error()
+    d.in_ = buf.data_ptr()
+    d.ksize = 5
+    assert L.islpose_plan_add_conv(handle, C.byref(d)) != 0 and b"kernel size" in L.islpose_last_error()
+    assert L.islpose_plan_add_maxpool2x2(handle, buf.data_ptr(), buf.data_ptr(), 1, 3, 4, 64) != 0
+    assert L.islpose_body_peaks(buf.data_ptr(), 1, 8, 8, (C.c_double * 25)(), 0.1, 4096, buf.data_ptr(), buf.data_ptr(),
+                                buf.data_ptr(), buf.data_ptr(), None) != 0
+    assert L.islpose_plan_destroy(handle) == 0
+
+
+def test_keypoint_extractor_with_real_hand_boxes(dev):
+    """body -> util.handDetect -> hand on a frame whose injected maps contain people: the boxes handDetect finds are
+    cropped and every hand result is offset by its box origin (demo.py:21-43)."""
+    mt, H, W = "coco", 240, 320
+    body = isl_b200.Body(O.make_flat_weights(mt, seed=0), mt, scale_search=[0.5])
+    hand = isl_b200.Hand(O.make_flat_weights("hand", seed=0, init="torch"))
+    sk = synth.synth_skeletons(mt, 3, 1)
+    maps = []
+    for (m, rh, rw, hp, wp) in scale_geometry(H, W, body.scale_search, body.boxsize):
+        paf, heat = synth.render_maps(mt, sk, hp // 8, wp // 8)
+        maps.append((torch.from_numpy(paf)[None].cuda(), torch.from_numpy(heat)[None].cuda(), (rh, rw, hp, wp)))
+    (cand, sub), = body.postprocess(maps, 1, H, W, body._workspace(1, H, W))
+    frame = synth.synth_frame(H, W, 1)
+    boxes = isl_b200.util.handDetect(cand, sub, frame)
+    assert len(boxes) == 6
+    peaks = hand.batch([frame[y:y + w, x:x + w, :] for x, y, w, _ in boxes])
+    assert len(peaks) == 6 and all(p.shape == (21, 2) for p in peaks)
+    for (x, y, w, _), p in zip(boxes, peaks):
+        assert (p[:, 0] < w).all() and (p[:, 1] < w).all() and (p >= 0).all()
