@@ -603,7 +603,7 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 // The accumulator is then [128 lanes = channels] x [256 columns = pixels]; epilogue lane = channel.
 __global__ void __launch_bounds__(kThreads, 2)
 conv_umma_swapped_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const ConvArgs a) {
+                         const __grid_constant__ CUtensorMap tmC, const ConvArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -703,30 +703,69 @@ conv_umma_swapped_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   } else {
     // epilogue: this thread owns output channel n0 + 32*q + lane for all pixels of the tile
     const int q = warp & 3;
-    const int ch = n0 + q * 32 + lane;
+    const int chl = q * 32 + lane;  // channel inside the 128-channel tile
+    const int ch = n0 + chl;
     const float bias = a.bias[ch];
     const float slope = a.slope[ch];
-    const bool st16 = a.out_bf16 != nullptr && ch < a.cout_store;
     const bool st32 = a.out_f32 != nullptr && ch < a.cout;
     const long long plane = static_cast<long long>(a.H) * a.W;
     ptx::mbar_wait(bar_accum, 0);
     ptx::tc_fence_after();
     const int npix = a.bw * a.bh;
-    for (int c = 0; c < npix; c += 32) {
-      uint32_t r[32];
-      ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, r);
-      ptx::tmem_ld_wait();
+    if (a.tma_store) {
+      // The bf16 tile goes out as [pixel][channel] rows through the (now idle) activation ring: two swizzled blocks
+      // of 64 channels, exactly the layout a TMA store with SWIZZLE_128B expects, then one bulk store per block.
+      // Pixels outside the frame and channels beyond the slice are clipped by the tensor map.
+      const uint32_t blk = sX0 + (chl >> 6) * kXBytes;       // channels 0..63 -> stage 0, 64..127 -> stage 1
+      const uint32_t chunk = (chl & 63) >> 3;                 // 16-byte chunk of the 128-byte pixel row
+      const uint32_t inner = (chl & 7) * 2;
+      for (int c = 0; c < npix; c += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, r);
+        ptx::tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const long long pix = s_pix[c + i];  // same for the whole warp: no divergence
-        if (pix < 0) continue;
-        const float acc = __uint_as_float(r[i]) + bias;
-        const float v = acc > 0.f ? acc : acc * slope;
-        // 32 lanes = 32 neighbouring channels of one pixel: one 64-byte segment per warp store
-        if (st16) a.out_bf16[pix * a.out_pix_stride + ch] = __float2bfloat16_rn(v);
-        if (st32) {
-          const long long im = pix / plane;
-          a.out_f32[(im * a.out_f32_channels + ch) * plane + (pix - im * plane)] = v;
+        for (int i = 0; i < 32; ++i) {
+          const float acc = __uint_as_float(r[i]) + bias;
+          const float v = acc > 0.f ? acc : acc * slope;
+          const uint32_t row = c + i;
+          const uint32_t addr = blk + row * 128u + ((chunk ^ (row & 7u)) << 4) + inner;
+          const __nv_bfloat16 h = __float2bfloat16_rn(v);
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(*reinterpret_cast<const uint16_t*>(&h)) : "memory");
+          if (st32) {
+            const long long pix = s_pix[row];
+            if (pix >= 0) {
+              const long long im = pix / plane;
+              a.out_f32[(im * a.out_f32_channels + ch) * plane + (pix - im * plane)] = v;
+            }
+          }
+        }
+      }
+      ptx::fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
+      if (threadIdx.x == 64) {
+        ptx::tma_store_4d(&tmC, sX0, n0, x0, y0, img);
+        if (n0 + 64 < a.cout_store) ptx::tma_store_4d(&tmC, sX0 + kXBytes, n0 + 64, x0, y0, img);
+        ptx::tma_store_commit();
+        ptx::tma_store_wait_all();
+      }
+    } else {
+      const bool st16 = a.out_bf16 != nullptr && ch < a.cout_store;
+      for (int c = 0; c < npix; c += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const long long pix = s_pix[c + i];  // same for the whole warp: no divergence
+          if (pix < 0) continue;
+          const float acc = __uint_as_float(r[i]) + bias;
+          const float v = acc > 0.f ? acc : acc * slope;
+          // 32 lanes = 32 neighbouring channels of one pixel: one 64-byte segment per warp store
+          if (st16) a.out_bf16[pix * a.out_pix_stride + ch] = __float2bfloat16_rn(v);
+          if (st32) {
+            const long long im = pix / plane;
+            a.out_f32[(im * a.out_f32_channels + ch) * plane + (pix - im * plane)] = v;
+          }
         }
       }
     }
@@ -802,7 +841,7 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
       const int hmax = cap / w < d.H ? cap / w : d.H;
       for (int h = wave_model ? 1 : hmax; h <= hmax && h <= 256; ++h) {
         const long long tiles = static_cast<long long>((d.W + w - 1) / w) * ((d.H + h - 1) / h) * d.N;
-        const double cost = wave_model ? estimate(tiles, (w * h + 15) / 16 * 16, 12000.0) + 1e-6 * tiles
+        const double cost = wave_model ? estimate(tiles, (w * h + 15) / 16 * 16, 6000.0) + 1e-6 * tiles
                                        : static_cast<double>(tiles) + 1e-3 * (w * h);
         if (best < 0 || cost < best) {
           best = cost;
@@ -813,18 +852,19 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
     }
     return best;
   };
-  // Variant 4 (swapped operands: weights = M, up to 256 pixels = N) for long reductions with 65..128 output
-  // channels, when the model predicts a win (measured: 7x7 128->128 at 92x164x8: 905 -> 1020 TFLOP/s,
-  // 7x7 192->128 at 60x80x8: 610 -> 792; slower on 3x3 / 1x1 layers and on small grids).
+  // Variant 4 (swapped operands: weights = M, up to 256 pixels = N) for 3x3 / 7x7 layers with 65..128 output
+  // channels, when the model predicts a win (measured, profiles/conv_test_v4_swapped_r1.log: 7x7 128->128 at
+  // 92x164x8: 909 -> 1307 TFLOP/s, 7x7 192->128 at 60x80x8: 610 -> 1034, 3x3 512->128 at 92x92x8: 936 -> 1186;
+  // equal on small grids, slower on 1x1 layers).
   int want_variant = d.variant;
   int bw = d.force_bw, bh = d.force_bh;
   static const int env_no_v4 = getenv("ISLPOSE_NO_V4") != nullptr;  // debugging aid
-  if (want_variant <= 0 && !env_no_v4 && d.ksize == 7 && d.cout > 64 && d.cout <= 128 && d.force_n_tile <= 0 && bw <= 0) {
+  if (want_variant <= 0 && !env_no_v4 && d.ksize >= 3 && d.cout > 64 && d.cout <= 128 && d.force_n_tile <= 0 && bw <= 0) {
     int w1 = 0, h1 = 0, w4 = 0, h4 = 0;
     const double tiles1 = best_box(128, false, &w1, &h1);
     const double t1 = estimate(static_cast<long long>(tiles1), 128, 3000.0);
     const double t4 = best_box(256, true, &w4, &h4);
-    if (t4 < 0.95 * t1) want_variant = 4;
+    if (t4 < 0.9 * t1) want_variant = 4;
   }
   if (want_variant == 3) {
     if (d.ksize == 1) return fail(err, errlen, "conv: the halo variant needs k > 1");
@@ -961,6 +1001,20 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
     if (r != CUDA_SUCCESS) return fail(err, errlen, "conv: weight tensor map rejected (CUresult %lld)", r);
   }
 
+  if (variant == 4 && d.out_bf16 != nullptr && stages >= 2) {
+    cuuint64_t gdim[4] = {static_cast<cuuint64_t>(a.cout_store), static_cast<cuuint64_t>(d.W),
+                          static_cast<cuuint64_t>(d.H), static_cast<cuuint64_t>(d.N)};
+    cuuint64_t gstr[3] = {static_cast<cuuint64_t>(d.out_cstride) * 2, static_cast<cuuint64_t>(d.out_cstride) * 2 * d.W,
+                          static_cast<cuuint64_t>(d.out_cstride) * 2 * d.W * d.H};
+    cuuint32_t box[4] = {64, static_cast<cuuint32_t>(bw), static_cast<cuuint32_t>(bh), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&out->tmC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d.out_bf16, gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(err, errlen, "conv: output tensor map rejected (CUresult %lld)", r);
+    a.tma_store = d.variant == 4 && d.msub == 99 ? 0 : 1;  // msub = 99 with an explicit v4 request: scalar-store epilogue
+  }
+
   if (variant == 2) {
     int per_sm = static_cast<int>((226u * 1024u) / out->smem_bytes);  // persistent CTAs that fit on one SM
     if (per_sm * a.tmem_cols > 512) per_sm = 512 / a.tmem_cols;
@@ -995,7 +1049,7 @@ int conv_run(const ConvLaunch& l, cudaStream_t stream) {
   } else if (l.variant == 3) {
     conv_umma_halo_kernel<<<l.grid, kThreads, l.smem_bytes, stream>>>(l.tmA, l.tmB, l.args);
   } else if (l.variant == 4) {
-    conv_umma_swapped_kernel<<<l.grid, kThreads, l.smem_bytes, stream>>>(l.tmA, l.tmB, l.args);
+    conv_umma_swapped_kernel<<<l.grid, kThreads, l.smem_bytes, stream>>>(l.tmA, l.tmB, l.tmC, l.args);
   } else {
     conv_umma_kernel<<<l.grid, kThreads, l.smem_bytes, stream>>>(l.tmA, l.tmB, l.args);
   }

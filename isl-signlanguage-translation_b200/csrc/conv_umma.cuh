@@ -82,6 +82,7 @@ struct ConvArgs {
   int halo_bo_mode;
   int debug_no_loads;
   int n_pix;       // v4: UMMA N = pixels per tile rounded up to 16
+  int tma_store;   // v4: the bf16 tile leaves through shared memory + TMA store
   __nv_bfloat16* out_bf16;
   long long out_pix_stride;
   float* out_f32;
@@ -93,6 +94,7 @@ struct ConvArgs {
 struct ConvLaunch {
   alignas(64) CUtensorMap tmA;
   alignas(64) CUtensorMap tmB;
+  alignas(64) CUtensorMap tmC;  // v4: bf16 output slice, written with TMA stores
   ConvArgs args;
   dim3 grid;
   uint32_t smem_bytes;
