@@ -81,9 +81,14 @@ typedef struct islpose_scale {
 
 /* Map post-processing (src/body.py:69-81, src/hand.py:51-56): x8 cubic, crop, cubic to (W,H), /S, accumulate in
  * float64. Writes channels [0, parts) of the result as planes: out float64 [n][parts][H][W].
- * double_running_sum != 0 reproduces `heatmap_avg += heatmap_avg + heatmap / S` (body.py:80). */
+ * double_running_sum != 0 reproduces `heatmap_avg += heatmap_avg + heatmap / S` (body.py:80).
+ * workspace (optional, may be NULL): float32 scratch of islpose_maps_workspace_floats() elements; with it the
+ * up-sampled maps are materialised once per scale (same results, ~8x less arithmetic), without it every output
+ * pixel evaluates both resizes from a 5x5 window of the stride-8 map. */
+int64_t islpose_maps_workspace_floats(const islpose_scale* scales, int32_t n_scales, int32_t n, int32_t parts);
 int islpose_maps_accumulate(const islpose_scale* scales, int32_t n_scales, int32_t channels, int32_t n, int32_t H,
-                            int32_t W, int32_t parts, int32_t double_running_sum, double* out, void* stream);
+                            int32_t W, int32_t parts, int32_t double_running_sum, double* out, float* workspace,
+                            int64_t workspace_floats, void* stream);
 
 /* Peak detection (src/body.py:86-107): scipy gaussian_filter(sigma=3) in float64 with reflect borders, 4-neighbour
  * NMS against zero-filled shifts, threshold; peaks of every (frame, part) plane sorted in row-major order.

@@ -45,8 +45,9 @@ SYMBOLS = {
     "islpose_plan_conv_flops": (C.c_double, [C.c_void_p]),
     "islpose_resize_pad_normalize": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_int32,
                                                C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "islpose_maps_workspace_floats": (C.c_int64, [C.POINTER(Scale), C.c_int32, C.c_int32, C.c_int32]),
     "islpose_maps_accumulate": (C.c_int, [C.POINTER(Scale), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
-                                          C.c_int32, C.c_void_p, C.c_void_p]),
+                                          C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "islpose_body_peaks": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.c_double, C.c_int32,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "islpose_body_group": (C.c_int, [C.POINTER(Scale), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double,

@@ -147,8 +147,11 @@ class Body(object):
         parts = self.njoint - 1
         heat_scales = self._scales_struct(maps, 1)
         paf_scales = self._scales_struct(maps, 0)
-        _lib.check(L.islpose_maps_accumulate(heat_scales, len(maps), self.njoint, n, H, W, parts, 1, _lib.ptr(ws["heat"]), st),
-                   "islpose_maps_accumulate")
+        need = L.islpose_maps_workspace_floats(heat_scales, len(maps), n, parts)
+        if ws.get("mid") is None or ws["mid"].numel() < need:
+            ws["mid"] = torch.empty((need,), dtype=torch.float32, device=self.device)
+        _lib.check(L.islpose_maps_accumulate(heat_scales, len(maps), self.njoint, n, H, W, parts, 1, _lib.ptr(ws["heat"]),
+                                             _lib.ptr(ws["mid"]), ws["mid"].numel(), st), "islpose_maps_accumulate")
         _lib.check(L.islpose_body_peaks(_lib.ptr(ws["heat"]), n * parts, H, W, self._gauss, self.thre1, PEAK_CAP,
                                         _lib.ptr(ws["counts"]), _lib.ptr(ws["keys"]), _lib.ptr(ws["scores"]),
                                         _lib.ptr(ws["overflow"]), st), "islpose_body_peaks")

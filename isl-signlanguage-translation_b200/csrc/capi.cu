@@ -215,13 +215,22 @@ int islpose_resize_pad_normalize(const uint8_t* frames, int32_t n, int32_t H, in
   return 0;
 }
 
+int64_t islpose_maps_workspace_floats(const islpose_scale* scales, int32_t n_scales, int32_t n, int32_t parts) {
+  int64_t total = 0;
+  if (scales == nullptr) return 0;
+  for (int s = 0; s < n_scales; ++s) total += static_cast<int64_t>(n) * parts * scales[s].hc * scales[s].wc;
+  return total;
+}
+
 int islpose_maps_accumulate(const islpose_scale* scales, int32_t n_scales, int32_t channels, int32_t n, int32_t H,
-                            int32_t W, int32_t parts, int32_t double_running_sum, double* out, void* stream) {
+                            int32_t W, int32_t parts, int32_t double_running_sum, double* out, float* workspace,
+                            int64_t workspace_floats, void* stream) {
   if (scales == nullptr || out == nullptr) return set_err("maps_accumulate: null pointer");
   if (parts <= 0 || parts > channels || n <= 0 || H <= 0 || W <= 0) return set_err("maps_accumulate: bad sizes");
   ScaleSet ss;
   if (fill_scales(scales, n_scales, channels, H, W, &ss) != 0) return 1;
-  if (launch_heat_accumulate(ss, n, H, W, parts, double_running_sum, out, static_cast<cudaStream_t>(stream)) != 0)
+  if (launch_heat_accumulate(ss, n, H, W, parts, double_running_sum, out, workspace, workspace_floats,
+                             static_cast<cudaStream_t>(stream)) != 0)
     return check_cuda("maps_accumulate") ? 1 : set_err("maps_accumulate: launch failed");
   return 0;
 }

@@ -23,7 +23,9 @@ int launch_resize_pad_norm(const uint8_t* frames, int N, int H, int W, double sc
                            float* out_nchw, uint8_t* out_u8, cudaStream_t st);
 int launch_im2col3x3(const float* in, int N, int h, int w, void* out, cudaStream_t st);
 int launch_maxpool2x2(const void* in, int N, int H, int W, int C, void* out, cudaStream_t st);
-int launch_heat_accumulate(const ScaleSet& ss, int N, int H, int W, int parts, int q1, double* out, cudaStream_t st);
+long long heat_accumulate_workspace_floats(const ScaleSet& ss, int N, int parts);
+int launch_heat_accumulate(const ScaleSet& ss, int N, int H, int W, int parts, int q1, double* out, float* workspace,
+                           long long workspace_floats, cudaStream_t st);
 int launch_gauss_nms(const double* heat, int planes_total, int H, int W, const GaussWeights& gw, double thre, int cap,
                      int* counts, uint32_t* keys, double* scores, int* overflow, cudaStream_t st);
 int launch_gauss_smooth(const double* heat, int planes_total, int H, int W, const GaussWeights& gw, double* smoothed,

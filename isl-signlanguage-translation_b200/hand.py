@@ -105,7 +105,12 @@ class Hand(object):
         labels = torch.empty((21, h, w), dtype=torch.int32, device=dev)
         mass = torch.empty((21, h, w), dtype=torch.float64, device=dev)
         out = torch.zeros((21, 2), dtype=torch.int32, device=dev)
-        _lib.check(L.islpose_maps_accumulate(arr, len(maps), 22, 1, h, w, 21, 0, _lib.ptr(heat), st), "islpose_maps_accumulate")
+        # small crops: one pass (fewer launches); large crops: materialise the up-sampled maps first (less arithmetic)
+        mid = None
+        if h * w >= 256 * 256:
+            mid = torch.empty((L.islpose_maps_workspace_floats(arr, len(maps), 1, 21),), dtype=torch.float32, device=dev)
+        _lib.check(L.islpose_maps_accumulate(arr, len(maps), 22, 1, h, w, 21, 0, _lib.ptr(heat), _lib.ptr(mid),
+                                             mid.numel() if mid is not None else 0, st), "islpose_maps_accumulate")
         _lib.check(L.islpose_hand_peaks(_lib.ptr(heat), 21, h, w, self._gauss, self.thre, _lib.ptr(smoothed),
                                         _lib.ptr(labels), _lib.ptr(mass), _lib.ptr(out), st), "islpose_hand_peaks")
         return out

@@ -150,3 +150,26 @@ def test_keypoint_extractor_with_real_hand_boxes(dev):
     assert len(peaks) == 6 and all(p.shape == (21, 2) for p in peaks)
     for (x, y, w, _), p in zip(boxes, peaks):
         assert (p[:, 0] < w).all() and (p[:, 1] < w).all() and (p >= 0).all()
+
+
+def test_maps_accumulate_single_pass_equals_two_pass(dev):
+    """islpose_maps_accumulate gives bit-identical planes with and without the float32 workspace."""
+    L = _lib.lib()
+    H, W, n, C, parts = 97, 131, 2, 19, 18
+    scales = scale_geometry(H, W, [0.5, 1.0, 1.5], 368)
+    arr = (_lib.Scale * len(scales))()
+    keep = []
+    rng = np.random.RandomState(0)
+    for i, (m, rh, rw, hp, wp) in enumerate(scales):
+        t = torch.from_numpy(rng.randn(n, C, hp // 8, wp // 8).astype(np.float32)).to(dev)
+        keep.append(t)
+        arr[i].lowres = t.data_ptr()
+        arr[i].gh, arr[i].gw, arr[i].hc, arr[i].wc = hp // 8, wp // 8, rh, rw
+    a = torch.empty((n, parts, H, W), dtype=torch.float64, device=dev)
+    b = torch.empty_like(a)
+    need = L.islpose_maps_workspace_floats(arr, len(scales), n, parts)
+    wsp = torch.empty((need,), dtype=torch.float32, device=dev)
+    _lib.check(L.islpose_maps_accumulate(arr, len(scales), C, n, H, W, parts, 1, _lib.ptr(a), None, 0, _lib.stream_ptr()), "single")
+    _lib.check(L.islpose_maps_accumulate(arr, len(scales), C, n, H, W, parts, 1, _lib.ptr(b), _lib.ptr(wsp), need,
+                                         _lib.stream_ptr()), "two-pass")
+    assert torch.equal(a, b)
