@@ -33,7 +33,7 @@ SCALES = [0.5, 1.0, 1.5, 2.0]
 WEIGHT_INIT = "torch"   # nn.Conv2d's default init distribution; "he" = noisy-map stress
 WORKLOADS = {
     # name: (model_type, H, W, hand boxes [x, y, w, is_left], default batch per rank)
-    "C2": ("coco", 480, 640, [[400, 250, 109, True], [22, 246, 90, False]], 8),
+    "C2": ("coco", 480, 640, [[400, 250, 109, True], [22, 246, 90, False]], 16),
     "C3": ("body25", 720, 1280, [[800, 300, 128, True], [300, 300, 128, False]], 8),
 }
 
@@ -239,7 +239,18 @@ def main():
         d2h = sum(c.nbytes + sb.nbytes + sum(p.nbytes for p in hp) for c, sb, hp in res)
     barrier()
     e2e_ms = sum(a.elapsed_time(b) for a, b in e2e_events)
-    h2d = B * H * W * 3 + sum(b[2] * b[2] * 3 for b in boxes) * B
+    h2d = B * H * W * 3   # hand crops are cut from the device copy of the frame
+
+    # ---- single-frame latency through the same public API (BASELINE.json's C2 is literally one frame) -------
+    one = [host_frames[0][0]]
+    for _ in range(2):
+        ex.batch(one, hand_boxes[:1])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        ex.batch(one, hand_boxes[:1])
+    torch.cuda.synchronize()
+    single_ms = (time.perf_counter() - t0) / 3 * 1e3
 
     times = torch.tensor([dev_ms, e2e_ms, conv_ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -257,11 +268,12 @@ def main():
             "config": {"workload": workload_name(args.workload, B), "weights": "seeded random init, %s (no trained weights ship with the reference)" % (
                            "nn.Conv2d default distribution" if WEIGHT_INIT == "torch" else "He-uniform (noisy maps: thousands of peaks)"),
                        "l2": "flushed with a 256 MiB write before every timed step",
-                       "timing": "CUDA events on the launching stream per step, summed; max over ranks"},
+                       "timing": "CUDA events on the launching stream per step, summed; max over ranks",
+                       "single_frame_latency_ms": round(single_ms, 2)},
             "clocks": sampler.summary(),
             "e2e": {"value": frames_total / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(gpu_launches),
-            "roofline": {"bound": "tensor", "kernel": "conv_umma_kernel (all network replays of the timed steps; im2col and max-pool launches are inside the same events)",
+            "roofline": {"bound": "tensor", "kernel": "conv_umma_* (tcgen05 implicit-GEMM variants; all network replays of the timed steps, fork-to-join per network phase; the im2col, max-pool and resize launches are inside the same events)",
                          "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
                          "peak_source": "%s bf16_tflops_sustained (burst %.1f)" % (src, burst), "traffic": None,
                          "conv_share_of_step": conv_ms / (dev_ms if world == 1 else max(dev_ms, 1e-9))},

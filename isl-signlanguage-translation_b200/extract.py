@@ -46,8 +46,11 @@ class KeypointExtractor(object):
 
     def batch(self, frames, hand_boxes=None):
         """frames: same-size uint8 [H,W,3] arrays. hand_boxes: optional per-frame list of [x, y, w, is_left] that
-        replaces util.handDetect (benchmark configs fix the boxes because random-init weights find no persons)."""
-        bodies = self.body.batch(frames)
+        replaces util.handDetect (benchmark configs fix the boxes because random-init weights find no persons).
+        The frames are uploaded once; hand crops are cut from the device copy."""
+        if hasattr(self.body, "upload"):
+            return self.batch_device(self.body.upload(frames), hand_boxes)
+        bodies = self.body.batch(frames)   # stand-in estimators without a device path (tests)
         if self.hand is None:
             return [(c, s, []) for c, s in bodies]
         crops, owner = [], []
@@ -57,10 +60,14 @@ class KeypointExtractor(object):
                 crops.append(np.asarray(frame)[y:y + w, x:x + w, :])
                 owner.append((fi, x, y))
         peaks = self.hand.batch(crops) if crops else []
-        per_frame = [[] for _ in frames]
+        return self._assemble(bodies, owner, peaks)
+
+    @staticmethod
+    def _assemble(bodies, owner, peaks):
+        per_frame = [[] for _ in bodies]
         for (fi, x, y), p in zip(owner, peaks):
             p = p.copy()
-            p[:, 0] = np.where(p[:, 0] == 0, p[:, 0], p[:, 0] + x)
+            p[:, 0] = np.where(p[:, 0] == 0, p[:, 0], p[:, 0] + x)   # demo.py:36-37: 0 means "not found"
             p[:, 1] = np.where(p[:, 1] == 0, p[:, 1], p[:, 1] + y)
             per_frame[fi].append(p)
         return [(c, s, per_frame[i]) for i, (c, s) in enumerate(bodies)]
@@ -78,13 +85,7 @@ class KeypointExtractor(object):
                 crops.append(frames_dev[fi, y:y + w, x:x + w, :].contiguous())
                 owner.append((fi, x, y))
         peaks = self.hand.batch_device(crops) if crops else []
-        per_frame = [[] for _ in range(frames_dev.shape[0])]
-        for (fi, x, y), p in zip(owner, peaks):
-            p = p.copy()
-            p[:, 0] = np.where(p[:, 0] == 0, p[:, 0], p[:, 0] + x)
-            p[:, 1] = np.where(p[:, 1] == 0, p[:, 1], p[:, 1] + y)
-            per_frame[fi].append(p)
-        return [(c, s, per_frame[i]) for i, (c, s) in enumerate(bodies)]
+        return self._assemble(bodies, owner, peaks)
 
     def run_sharded(self, frames, rank, world_size, batch_size=8, hand_boxes=None):
         """Processes this rank's shard of `frames` in batches; returns results in shard order."""
