@@ -12,8 +12,11 @@ Hand boxes are fixed per workload because random-init weights never produce a pe
 value   frames/s with the frames already resident in HBM (device-timed, max over ranks)
 e2e     frames/s through the public host API (numpy frames in, numpy results out; H2D from pinned memory and the
         D2H of candidate / subset / hand peaks inside the timed region)
-roofline     the tcgen05 conv kernel: algorithmic FLOPs of all network replays in the timed steps / their CUDA-event time
-cpu_baseline the oracle (restated reference, calling cv2 / scipy / torch-CPU where the reference does) on the host cores
+roofline      the tcgen05 conv kernels: algorithmic FLOPs of a step's network replays / the CUDA-event time of those
+              replays run on their own (a step overlaps them with the post-processing, so they cannot be timed inside it)
+post_roofline the body map post-processing (x8 cubic, resize to frame size, scale accumulation, gaussian, NMS) of one
+              chunk run on its own: SURVEY.md 8d bytes / CUDA-event time against the measured HBM copy bandwidth
+cpu_baseline  the oracle (restated reference, calling cv2 / scipy / torch-CPU where the reference does) on the host cores
 """
 import argparse
 import json
@@ -48,8 +51,13 @@ def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(path):
         p = json.load(open(path))
-        return p.get("bf16_tflops_sustained", 1379.5), p.get("bf16_tflops", 1636.0), "measured"
-    return 1400.0, 1590.0, "fallback"
+        return p.get("bf16_tflops_sustained", 1379.5), p.get("bf16_tflops", 1636.0), p.get("hbm_gbs", 6542.7), "measured"
+    return 1400.0, 1590.0, 6500.0, "fallback"
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant conv kernel from the committed
+# `ncu --set full` capture (profiles/): filled in by hand from the capture, None until one exists for this round
+CONV_DRAM_TRAFFIC = None
 
 
 class ClockSampler(threading.Thread):
@@ -150,6 +158,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="frames per step per rank (0 = workload default)")
+    ap.add_argument("--chunk", type=int, default=4, help="frames per pipeline stage inside a step (0 = no pipelining)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--weights", default="torch", choices=["torch", "he"], help="random-init distribution (he = noisy-map stress)")
@@ -164,7 +173,7 @@ def main():
     import torch.distributed as dist
 
     import isl_b200
-    from isl_b200 import synth
+    from isl_b200 import _lib, synth
     from isl_b200.extract import KeypointExtractor
     from oracle import openpose_oracle as O  # weights generator only on this path; the oracle runs in cpu_baseline
 
@@ -179,7 +188,7 @@ def main():
     B = args.batch or default_batch
     body = isl_b200.Body(O.make_flat_weights(mt, seed=0, init=WEIGHT_INIT), mt, scale_search=SCALES)
     hand = isl_b200.Hand(O.make_flat_weights("hand", seed=0, init=WEIGHT_INIT))
-    ex = KeypointExtractor(body, hand)
+    ex = KeypointExtractor(body, hand, chunk=args.chunk or None)
     hand_boxes = [boxes] * B
 
     def frames_for(step):
@@ -193,17 +202,19 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- leg 1: device-resident inputs (value) + conv roofline -----------------------------------------------
+    L = _lib.lib()
+
+    # ---- leg 1: device-resident inputs (value) ---------------------------------------------------------------
     total_steps = args.warmup + args.steps
     dev_frames = [torch.from_numpy(np.stack(frames_for(s))).cuda() for s in range(min(total_steps, 4))]
     for s in range(args.warmup):
         flush.zero_()
         ex.batch_device(dev_frames[s % len(dev_frames)], hand_boxes)
-    body.model.timing, hand.model.timing = [], []
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
     step_events = []
+    launches0 = L.islpose_launch_count()
     for s in range(args.steps):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -212,15 +223,9 @@ def main():
         e1.record()
         step_events.append((e0, e1))
     barrier()
+    gpu_launches = L.islpose_launch_count() - launches0
     sampler.stop_flag = True
     dev_ms = sum(a.elapsed_time(b) for a, b in step_events)
-    conv_ms = sum(a.elapsed_time(b) for a, b, _, _ in body.model.timing + hand.model.timing)
-    conv_flops = sum(f for _, _, f, _ in body.model.timing + hand.model.timing)
-    net_launches = sum(l for _, _, _, l in body.model.timing + hand.model.timing)
-    body.model.timing, hand.model.timing = None, None
-    n_hand_crops = B * len(boxes)
-    other_launches = args.steps * (len(SCALES) * 1 + 1 + 2 + 2 + n_hand_crops * (len(SCALES) + 1 + 2))
-    gpu_launches = net_launches + other_launches
 
     # ---- leg 2: host API end to end (e2e) ------------------------------------------------------------------
     host_frames = [frames_for(1000 + s) for s in range(min(args.steps, 4))]
@@ -241,6 +246,86 @@ def main():
     e2e_ms = sum(a.elapsed_time(b) for a, b in e2e_events)
     h2d = B * H * W * 3   # hand crops are cut from the device copy of the frame
 
+    # ---- leg 3: the convolution plans of one step on their own (roofline of the tcgen05 kernels) -------------
+    # exactly the network replays a step performs (same chunks, lanes and streams; resize, im2col and max-pool
+    # launches included), without the post-processing, so the events time tensor-bound work only
+    chunk = ex.chunk or B
+    lanes = ex._lane_streams(torch)
+    main = torch.cuda.current_stream()
+
+    def networks_only(frames_dev):
+        flops = 0
+        ready = torch.cuda.Event()
+        ready.record(main)
+        for ci, a in enumerate(range(0, B, chunk)):
+            sub = frames_dev[a:a + chunk]
+            with torch.cuda.stream(lanes[ci % 2]):
+                lanes[ci % 2].wait_event(ready)
+                body.model.timing = []
+                body.network_outputs(sub, H, W, lane=ci % 2)
+                flops += sum(t[2] for t in body.model.timing)
+            with torch.cuda.stream(lanes[2 + ci % 2]):
+                lanes[2 + ci % 2].wait_event(ready)
+                crops = [frames_dev[a + i, y:y + w, x:x + w, :].contiguous() for i in range(sub.shape[0]) for (x, y, w, _) in boxes]
+                hand.model.timing = []
+                hand.network_outputs(crops, lane=ci % 2)
+                flops += sum(t[2] for t in hand.model.timing)
+        for st in lanes:
+            main.wait_stream(st)
+        body.model.timing = hand.model.timing = None
+        return flops
+
+    networks_only(dev_frames[0])
+    barrier()
+    conv_events, conv_flops = [], 0
+    for s in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        conv_flops += networks_only(dev_frames[s % len(dev_frames)])
+        e1.record()
+        conv_events.append((e0, e1))
+    barrier()
+    conv_ms = sum(a.elapsed_time(b) for a, b in conv_events)
+
+    # ---- leg 4: the body map post-processing on its own (HBM roofline of subsystem 2) -------------------------
+    # maps accumulation + gaussian/NMS/peak lists for one chunk, from the network outputs left by leg 3
+    nb = min(chunk, B)
+    ws = body._workspace(nb, H, W, 0)
+    maps = body.network_outputs(dev_frames[0][:nb], H, W, lane=0)
+    parts = body.njoint - 1
+    heat_scales = body._scales_struct(maps, 1)
+    need = L.islpose_maps_workspace_floats(heat_scales, len(maps), nb, parts)
+    if ws.get("mid") is None or ws["mid"].numel() < need:
+        ws["mid"] = torch.empty((need,), dtype=torch.float32, device="cuda")
+
+    def post_maps():
+        _lib.check(L.islpose_maps_accumulate(heat_scales, len(maps), body.njoint, nb, H, W, parts, 1, _lib.ptr(ws["heat"]),
+                                             _lib.ptr(ws["mid"]), ws["mid"].numel(), _lib.stream_ptr()), "maps_accumulate")
+        _lib.check(L.islpose_body_peaks(_lib.ptr(ws["heat"]), nb * parts, H, W, body._gauss, body.thre1, 1024,
+                                        _lib.ptr(ws["counts"]), _lib.ptr(ws["keys"]), _lib.ptr(ws["scores"]),
+                                        _lib.ptr(ws["overflow"]), _lib.stream_ptr()), "body_peaks")
+
+    post_maps()
+    barrier()
+    post_events = []
+    for s in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        post_maps()
+        e1.record()
+        post_events.append((e0, e1))
+    barrier()
+    post_ms = sum(a.elapsed_time(b) for a, b in post_events) / args.steps
+    ws["overflow"].zero_()
+    # SURVEY.md section 8d convention for the bytes of the reference dataflow, heat maps only (the PAF maps are never
+    # materialised here; their share of B_post is reported separately as what the lazy sampler avoids)
+    S = len(SCALES)
+    grid_bytes = sum(4 * (m[2][2] // 8) * (m[2][3] // 8) for m in maps)
+    post_bytes_heat = nb * (4 * H * W * ((2 * S - 1) * body.njoint + 2 * parts) + grid_bytes * body.njoint)
+    post_bytes_all = nb * (4 * H * W * ((2 * S - 1) * (body.njoint + body.npaf) + 2 * parts) + grid_bytes * (body.njoint + body.npaf))
+
     # ---- single-frame latency through the same public API (BASELINE.json's C2 is literally one frame) -------
     one = [host_frames[0][0]]
     for _ in range(2):
@@ -252,13 +337,13 @@ def main():
     torch.cuda.synchronize()
     single_ms = (time.perf_counter() - t0) / 3 * 1e3
 
-    times = torch.tensor([dev_ms, e2e_ms, conv_ms], dtype=torch.float64, device="cuda")
+    times = torch.tensor([dev_ms, e2e_ms, conv_ms, post_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, conv_ms_max = [float(x) for x in times.cpu()]
+    dev_ms, e2e_ms, conv_ms, post_ms = [float(x) for x in times.cpu()]
 
     if rank == 0:
-        sustained, burst, src = peaks()
+        sustained, burst, hbm_peak, src = peaks()
         achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
         frames_total = world * B * args.steps
         line = {
@@ -269,14 +354,24 @@ def main():
                            "nn.Conv2d default distribution" if WEIGHT_INIT == "torch" else "He-uniform (noisy maps: thousands of peaks)"),
                        "l2": "flushed with a 256 MiB write before every timed step",
                        "timing": "CUDA events on the launching stream per step, summed; max over ranks",
+                       "pipeline": "%s-frame chunks on two lanes inside a step (post-processing of one chunk under the "
+                                   "convolutions of the next)" % (args.chunk or B),
                        "single_frame_latency_ms": round(single_ms, 2)},
             "clocks": sampler.summary(),
             "e2e": {"value": frames_total / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(gpu_launches),
-            "roofline": {"bound": "tensor", "kernel": "conv_umma_* (tcgen05 implicit-GEMM variants; all network replays of the timed steps, fork-to-join per network phase; the im2col, max-pool and resize launches are inside the same events)",
+            "roofline": {"bound": "tensor", "kernel": "conv_umma_* (tcgen05 implicit-GEMM variants): the network replays of "
+                                                      "a step run on their own, same chunks / lanes / streams as the step; the "
+                                                      "resize, im2col and max-pool launches are inside the same events",
                          "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
-                         "peak_source": "%s bf16_tflops_sustained (burst %.1f)" % (src, burst), "traffic": None,
-                         "conv_share_of_step": conv_ms / (dev_ms if world == 1 else max(dev_ms, 1e-9))},
+                         "peak_source": "%s bf16_tflops_sustained (burst %.1f)" % (src, burst),
+                         "traffic": CONV_DRAM_TRAFFIC, "conv_share_of_step": conv_ms / max(dev_ms, 1e-9)},
+            "post_roofline": {"bound": "hbm", "kernel": "upsample8 + resize_accumulate + gauss_window + sort_peaks "
+                                                        "(body maps of one %d-frame chunk, run on their own)" % nb,
+                              "achieved": post_bytes_heat / (post_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                              "frac": post_bytes_heat / (post_ms * 1e-3) / 1e9 / hbm_peak,
+                              "ms_per_frame": post_ms / nb, "algorithmic_bytes_per_frame": post_bytes_heat // nb,
+                              "reference_dataflow_bytes_per_frame_incl_paf": post_bytes_all // nb},
         }
         if world == 1 and not args.no_cpu_baseline:
             t, _ = cpu_reference_frame(args.workload, 0)

@@ -24,6 +24,9 @@ extern "C" {
 
 int islpose_abi_version(void);
 const char* islpose_last_error(void);
+/* Number of kernels this library has launched since it was loaded (all threads); bench.py reports the difference
+ * over its timed region as gpu_launches. */
+int64_t islpose_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Network plans: a recorded list of kernel launches (one per layer) over caller-owned device buffers,

@@ -5,6 +5,10 @@ There is no CPU fallback: if the library is missing or a call fails, an exceptio
 import ctypes as C
 import os
 
+# Scales, lanes and hand crops run on a few dozen streams; with the default of 8 hardware queues unrelated streams
+# would share a queue and serialise. Only effective if set before the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libislpose.so")
 
@@ -35,6 +39,7 @@ class GroupBuffers(C.Structure):
 SYMBOLS = {
     "islpose_abi_version": (C.c_int, []),
     "islpose_last_error": (C.c_char_p, []),
+    "islpose_launch_count": (C.c_int64, []),
     "islpose_plan_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "islpose_plan_destroy": (C.c_int, [C.c_void_p]),
     "islpose_plan_add_conv": (C.c_int, [C.c_void_p, C.POINTER(ConvDesc)]),

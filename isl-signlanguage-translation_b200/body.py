@@ -56,15 +56,16 @@ class Body(object):
         self.device = self.model.device
         self._gauss = (C.c_double * 25)(*gaussian_weights().tolist())
         self._work = {}
-        self._streams = []
+        self._staging = {}   # (n, H, W) -> (pinned host frames, device frames)
+        self._streams = {}   # lane -> side streams, one per scale
         self.last_overflow = 0
 
     # ------------------------------------------------------------------------------------------------
     def __call__(self, oriImg):
         return self.batch([oriImg])[0]
 
-    def _workspace(self, n, H, W):
-        key = (n, H, W)
+    def _workspace(self, n, H, W, lane=0):
+        key = (n, H, W, lane)
         ws = self._work.get(key)
         if ws is None:
             dev = self.device
@@ -73,7 +74,6 @@ class Body(object):
             i32 = dict(dtype=torch.int32, device=dev)
             f64 = dict(dtype=torch.float64, device=dev)
             ws = dict(
-                frames=torch.empty((n, H, W, 3), dtype=torch.uint8, device=dev),
                 heat=torch.empty((n, parts, H, W), **f64),
                 counts=torch.zeros((n * parts,), **i32),
                 keys=torch.zeros((n * parts, PEAK_CAP), dtype=torch.int32, device=dev),
@@ -90,22 +90,23 @@ class Body(object):
                 subset=torch.zeros((n, MAX_PERSON, self.njoint + 1), **f64),
                 n_person=torch.zeros((n,), **i32),
                 overflow=torch.zeros((1,), **i32),
-                pinned=torch.empty((n, H, W, 3), dtype=torch.uint8).pin_memory(),
             )
             self._work[key] = ws
         return ws
 
-    def network_outputs(self, frames_dev, H, W):
+    def network_outputs(self, frames_dev, H, W, lane=0):
         """Runs every scale; returns [(paf, heat, geometry)] with the plans' float32 NCHW output tensors.
         The scales are independent (body.py:51 loops over them sequentially), so each runs on its own stream: the
-        small-scale networks are latency-bound (a few dozen CTAs per layer) and hide under the large ones."""
+        small-scale networks are latency-bound (a few dozen CTAs per layer) and hide under the large ones.
+        `lane` selects an independent set of plan buffers and streams, so that two batches can be in flight."""
         L = _lib.lib()
         n = frames_dev.shape[0]
         geoms = scale_geometry(H, W, self.scale_search, self.boxsize)
-        insts = [self.model.instance(n, hp, wp) for (_, _, _, hp, wp) in geoms]
+        insts = [self.model.instance(n, hp, wp, lane) for (_, _, _, hp, wp) in geoms]
         main = torch.cuda.current_stream()
-        while len(self._streams) < len(geoms):
-            self._streams.append(torch.cuda.Stream(device=self.device))
+        streams = self._streams.setdefault(lane, [])
+        while len(streams) < len(geoms):
+            streams.append(torch.cuda.Stream(device=self.device))
         timing = self.model.timing
         if timing is not None:
             t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -114,7 +115,7 @@ class Body(object):
         fork.record(main)
         outs = []
         for i, ((m, rh, rw, hp, wp), inst) in enumerate(zip(geoms, insts)):
-            side = self._streams[i] if len(geoms) > 1 else main
+            side = streams[i] if len(geoms) > 1 else main
             with torch.cuda.stream(side):
                 side.wait_event(fork)
                 _lib.check(L.islpose_resize_pad_normalize(_lib.ptr(frames_dev), n, H, W, m, rh, rw, hp, wp,
@@ -140,56 +141,87 @@ class Body(object):
             arr[i].gh, arr[i].gw, arr[i].hc, arr[i].wc = hp // 8, wp // 8, rh, rw
         return arr
 
-    def postprocess(self, maps, n, H, W, ws):
-        """Peaks, PAF scoring and grouping from the per-scale network outputs -> list of (candidate, subset)."""
+    def _group(self, maps, n, H, W, ws):
+        L = _lib.lib()
+        parts = self.njoint - 1
+        paf_scales = self._scales_struct(maps, 0)
+        gb = _lib.GroupBuffers()
+        gb.cap, gb.pair_cap, gb.max_cand, gb.max_person = PEAK_CAP, ws["pair_cap"], parts * PEAK_CAP, ws["max_person"]
+        for f in ("counts", "keys", "scores", "pair_score", "conn_count", "conn_ij", "conn_score", "owner", "candidate",
+                  "n_cand", "subset", "n_person", "overflow"):
+            setattr(gb, f, ws[f].data_ptr())
+        _lib.check(L.islpose_body_group(paf_scales, len(maps), 1 if self._kind == 'body25' else 0, n, H, W, self.thre2,
+                                        self.mid_num, C.byref(gb), _lib.stream_ptr()), "islpose_body_group")
+        # the three small result tables travel together, asynchronously, into pinned memory
+        ws["tail_dev"][:n].copy_(ws["n_cand"])
+        ws["tail_dev"][n:2 * n].copy_(ws["n_person"])
+        ws["tail_dev"][2 * n:2 * n + 1].copy_(ws["overflow"])
+        ws["tail_host"].copy_(ws["tail_dev"], non_blocking=True)
+
+    def post_enqueue(self, maps, n, H, W, ws):
+        """Launches peaks, PAF scoring and grouping for the per-scale network outputs on the current stream (no
+        host synchronisation); post_finish() collects the results."""
         L = _lib.lib()
         st = _lib.stream_ptr()
         parts = self.njoint - 1
         heat_scales = self._scales_struct(maps, 1)
-        paf_scales = self._scales_struct(maps, 0)
         need = L.islpose_maps_workspace_floats(heat_scales, len(maps), n, parts)
         if ws.get("mid") is None or ws["mid"].numel() < need:
             ws["mid"] = torch.empty((need,), dtype=torch.float32, device=self.device)
+        if ws.get("tail_dev") is None:
+            ws["tail_dev"] = torch.zeros((2 * n + 1,), dtype=torch.int32, device=self.device)
+            ws["tail_host"] = torch.zeros((2 * n + 1,), dtype=torch.int32).pin_memory()
         _lib.check(L.islpose_maps_accumulate(heat_scales, len(maps), self.njoint, n, H, W, parts, 1, _lib.ptr(ws["heat"]),
                                              _lib.ptr(ws["mid"]), ws["mid"].numel(), st), "islpose_maps_accumulate")
         _lib.check(L.islpose_body_peaks(_lib.ptr(ws["heat"]), n * parts, H, W, self._gauss, self.thre1, PEAK_CAP,
                                         _lib.ptr(ws["counts"]), _lib.ptr(ws["keys"]), _lib.ptr(ws["scores"]),
                                         _lib.ptr(ws["overflow"]), st), "islpose_body_peaks")
-        while True:
-            gb = _lib.GroupBuffers()
-            gb.cap, gb.pair_cap, gb.max_cand, gb.max_person = PEAK_CAP, ws["pair_cap"], parts * PEAK_CAP, ws["max_person"]
-            for f in ("counts", "keys", "scores", "pair_score", "conn_count", "conn_ij", "conn_score", "owner", "candidate",
-                      "n_cand", "subset", "n_person", "overflow"):
-                setattr(gb, f, ws[f].data_ptr())
-            _lib.check(L.islpose_body_group(paf_scales, len(maps), 1 if self._kind == 'body25' else 0, n, H, W, self.thre2,
-                                            self.mid_num, C.byref(gb), st), "islpose_body_group")
-            n_cand = ws["n_cand"].cpu().numpy()
-            n_person = ws["n_person"].cpu().numpy()
-            self.last_overflow = int(ws["overflow"].cpu().item())
-            if self.last_overflow == 0:
-                break
-            ws["overflow"].zero_()
-            if self.last_overflow == 3 and ws["pair_cap"] < PEAK_CAP * PEAK_CAP:
-                # a limb has more candidate pairs than the scratch matrix holds: enlarge it and redo the grouping
-                ws["pair_cap"] = min(ws["pair_cap"] * 4, PEAK_CAP * PEAK_CAP)
-                ws["pair_score"] = torch.empty((ws["conn_count"].numel(), ws["pair_cap"]), dtype=torch.float64,
+        self._group(maps, n, H, W, ws)
+        done = torch.cuda.Event()
+        done.record()
+        return dict(maps=maps, n=n, H=H, W=W, ws=ws, done=done, stream=torch.cuda.current_stream())
+
+    def post_finish(self, ticket):
+        """Waits for a post_enqueue() ticket and returns the list of (candidate, subset)."""
+        maps, n, H, W, ws = ticket["maps"], ticket["n"], ticket["H"], ticket["W"], ticket["ws"]
+        with torch.cuda.stream(ticket["stream"]):
+            while True:
+                ticket["done"].synchronize()
+                tail = ws["tail_host"].numpy()
+                n_cand, n_person = tail[:n].copy(), tail[n:2 * n].copy()
+                self.last_overflow = int(tail[2 * n])
+                if self.last_overflow == 0:
+                    break
+                ws["overflow"].zero_()
+                if self.last_overflow == 3 and ws["pair_cap"] < PEAK_CAP * PEAK_CAP:
+                    # a limb has more candidate pairs than the scratch matrix holds: enlarge it and redo the grouping
+                    ws["pair_cap"] = min(ws["pair_cap"] * 4, PEAK_CAP * PEAK_CAP)
+                    ws["pair_score"] = torch.empty((ws["conn_count"].numel(), ws["pair_cap"]), dtype=torch.float64,
+                                                   device=self.device)
+                elif self.last_overflow == 4 and ws["max_person"] < 65536:
+                    ws["max_person"] *= 4
+                    ws["subset"] = torch.zeros((n, ws["max_person"], self.njoint + 1), dtype=torch.float64,
                                                device=self.device)
-                continue
-            if self.last_overflow == 4 and ws["max_person"] < 65536:
-                ws["max_person"] *= 4
-                ws["subset"] = torch.zeros((n, ws["max_person"], self.njoint + 1), dtype=torch.float64, device=self.device)
-                continue
-            raise _lib.IslposeError("body grouping exceeded a fixed capacity (code %d: 1 = more than %d peaks in one part, "
-                                    "2 = candidate table, 4 = more than 65536 person rows)" % (self.last_overflow, PEAK_CAP))
-        max_c, max_p = int(n_cand.max()) if n else 0, int(n_person.max()) if n else 0
-        cand = ws["candidate"][:, :max(max_c, 1)].cpu().numpy()
-        sub = ws["subset"][:, :max(max_p, 1)].cpu().numpy()
+                else:
+                    raise _lib.IslposeError("body grouping exceeded a fixed capacity (code %d: 1 = more than %d peaks in "
+                                            "one part, 2 = candidate table, 4 = more than 65536 person rows)" % (
+                                                self.last_overflow, PEAK_CAP))
+                self._group(maps, n, H, W, ws)
+                ticket["done"] = torch.cuda.Event()
+                ticket["done"].record()
+            max_c, max_p = int(n_cand.max()) if n else 0, int(n_person.max()) if n else 0
+            cand = ws["candidate"][:, :max(max_c, 1)].cpu().numpy()
+            sub = ws["subset"][:, :max(max_p, 1)].cpu().numpy()
         results = []
         for i in range(n):
             c = cand[i, :n_cand[i]].copy() if n_cand[i] else np.array([])   # body.py:183 gives shape (0,) when empty
             s = sub[i, :n_person[i]].copy() if n_person[i] else -1 * np.ones((0, self.njoint + 1))
             results.append((c, s))
         return results
+
+    def postprocess(self, maps, n, H, W, ws):
+        """Peaks, PAF scoring and grouping from the per-scale network outputs -> list of (candidate, subset)."""
+        return self.post_finish(self.post_enqueue(maps, n, H, W, ws))
 
     def upload(self, frames):
         """Host frames -> this call's device staging buffer [n,H,W,3] (through pinned memory)."""
@@ -198,20 +230,35 @@ class Body(object):
         for f in frames:
             if f.shape != (H, W, 3) or f.dtype != np.uint8:
                 raise ValueError("Body.batch needs uint8 [H,W,3] frames of one size, got %s %s" % (f.shape, f.dtype))
-        ws = self._workspace(len(frames), H, W)
-        host = ws["pinned"].numpy()
+        key = (len(frames), H, W)
+        stage = self._staging.get(key)
+        if stage is None:
+            stage = (torch.empty((len(frames), H, W, 3), dtype=torch.uint8).pin_memory(),
+                     torch.empty((len(frames), H, W, 3), dtype=torch.uint8, device=self.device))
+            self._staging[key] = stage
+        host = stage[0].numpy()
         for i, f in enumerate(frames):
             host[i] = f   # also resolves negative-stride views such as frame[:, :, ::-1]
-        ws["frames"].copy_(ws["pinned"], non_blocking=True)
-        return ws["frames"]
+        stage[1].copy_(stage[0], non_blocking=True)
+        return stage[1]
+
+    def enqueue(self, frames_dev, lane=0):
+        """Launches networks and post-processing for frames_dev (uint8 cuda tensor [n,H,W,3]) on the current stream
+        and the lane's side streams without waiting for anything; finish(ticket) returns the results. Two lanes
+        let the (memory / latency bound) post-processing of one batch run under the convolutions of the next."""
+        n, H, W, _ = frames_dev.shape
+        with torch.cuda.device(self.device):
+            ws = self._workspace(n, H, W, lane)
+            maps = self.network_outputs(frames_dev, H, W, lane)
+            return self.post_enqueue(maps, n, H, W, ws)
+
+    def finish(self, ticket):
+        with torch.cuda.device(self.device):
+            return self.post_finish(ticket)
 
     def batch_device(self, frames_dev):
         """frames_dev: uint8 cuda tensor [n,H,W,3] (contiguous) -> list of (candidate, subset)."""
-        n, H, W, _ = frames_dev.shape
-        with torch.cuda.device(self.device):
-            ws = self._workspace(n, H, W)
-            maps = self.network_outputs(frames_dev, H, W)
-            return self.postprocess(maps, n, H, W, ws)
+        return self.finish(self.enqueue(frames_dev))
 
     def batch(self, frames):
         """frames: list of uint8 [H,W,3] BGR arrays of one size -> list of (candidate, subset)."""

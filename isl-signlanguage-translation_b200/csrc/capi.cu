@@ -3,6 +3,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
 #include <vector>
 
 #include "../../include/islpose.h"
@@ -14,6 +15,7 @@ using namespace islpose;
 namespace {
 
 thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};  // kernels launched by this library since load (islpose_launch_count)
 
 int set_err(const char* fmt, ...) {
   va_list ap;
@@ -103,6 +105,7 @@ struct islpose_plan {
 extern "C" {
 
 int islpose_abi_version(void) { return ISLPOSE_ABI_VERSION; }
+int64_t islpose_launch_count(void) { return g_launches.load(); }
 const char* islpose_last_error(void) { return g_err; }
 
 int islpose_plan_create(islpose_plan** out) {
@@ -194,6 +197,7 @@ int islpose_plan_run(const islpose_plan* plan, void* stream) {
     } else {
       rc = launch_im2col3x3(static_cast<const float*>(op.in), op.n, op.h, op.w, op.out, st);
     }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     if (rc != 0) {
       check_cuda("plan_run");
       return set_err("plan_run: launch %d of %d failed: %s", static_cast<int>(i), static_cast<int>(plan->ops.size()), g_err);
@@ -212,6 +216,7 @@ int islpose_resize_pad_normalize(const uint8_t* frames, int32_t n, int32_t H, in
     return set_err("resize_pad_normalize: bad geometry (%dx%d -> %dx%d padded %dx%d)", H, W, rh, rw, hp, wp);
   if (launch_resize_pad_norm(frames, n, H, W, scale, rh, rw, hp, wp, out_nchw, out_u8, static_cast<cudaStream_t>(stream)) != 0)
     return check_cuda("resize_pad_normalize") ? 1 : set_err("resize_pad_normalize: launch failed");
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }
 
@@ -232,6 +237,8 @@ int islpose_maps_accumulate(const islpose_scale* scales, int32_t n_scales, int32
   if (launch_heat_accumulate(ss, n, H, W, parts, double_running_sum, out, workspace, workspace_floats,
                              static_cast<cudaStream_t>(stream)) != 0)
     return check_cuda("maps_accumulate") ? 1 : set_err("maps_accumulate: launch failed");
+  const bool two_pass = workspace != nullptr && workspace_floats >= heat_accumulate_workspace_floats(ss, n, parts);
+  g_launches.fetch_add(two_pass ? n_scales + 1 : 1, std::memory_order_relaxed);
   return 0;
 }
 
@@ -244,6 +251,7 @@ int islpose_body_peaks(const double* heat, int32_t planes, int32_t H, int32_t W,
   memcpy(gw.w, h_gauss, sizeof(gw.w));
   if (launch_gauss_nms(heat, planes, H, W, gw, thre1, cap, counts, keys, scores, overflow, static_cast<cudaStream_t>(stream)) != 0)
     return check_cuda("body_peaks") ? 1 : set_err("body_peaks: launch failed");
+  g_launches.fetch_add(2, std::memory_order_relaxed);
   return 0;
 }
 
@@ -277,6 +285,7 @@ int islpose_body_group(const islpose_scale* paf_scales, int32_t n_scales, int32_
   if (launch_paf_score(ss, lt, n, H, W, thre2, mid_num, gb, st) != 0)
     return check_cuda("body_group/paf_score") ? 1 : set_err("body_group: peak capacity out of range (cap %d)", gb.cap);
   if (launch_group(lt, n, W, gb, st) != 0) return check_cuda("body_group/group") ? 1 : set_err("body_group: launch failed");
+  g_launches.fetch_add(3, std::memory_order_relaxed);
   return 0;
 }
 
@@ -291,6 +300,7 @@ int islpose_hand_peaks(const double* heat, int32_t planes, int32_t H, int32_t W,
     return check_cuda("hand_peaks/gauss") ? 1 : set_err("hand_peaks: launch failed");
   if (launch_hand_peaks(heat, smoothed, planes, H, W, thre, labels, mass, out_xy, st) != 0)
     return check_cuda("hand_peaks") ? 1 : set_err("hand_peaks: launch failed");
+  g_launches.fetch_add(2, std::memory_order_relaxed);
   return 0;
 }
 

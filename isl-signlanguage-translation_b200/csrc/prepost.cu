@@ -9,6 +9,7 @@
 #include "prepost.cuh"
 
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "cubic.cuh"
 
@@ -337,6 +338,97 @@ gauss_kernel(const double* __restrict__ heat, int planes, int H, int W, const Ga
   }
 }
 
+// Sliding-window variant of the same filter (bit-identical: the very same __dmul_rn/__dadd_rn sequence per output).
+// gauss_kernel above reads 25 shared-memory doubles per output and per axis, which makes it shared-memory-bandwidth
+// bound; here a thread produces kR1 (axis 0) / kR2 (axis 1) consecutive outputs from one register window of
+// kR + 24 inputs, i.e. 2.5 / 3.2 loads per output, which leaves the FP64 pipe as the limiter.
+//   pass 1 (axis 0): lanes = adjacent columns, inputs straight from global memory (coalesced, reflect per index),
+//                    results into s_v[32][90]
+//   pass 2 (axis 1): lanes = rows (odd pitch: conflict-free), window from s_v, results into s_s[32][66]
+//   pass 3: NMS / store of the 30 x 64 interior
+constexpr int kG2W = 64;                 // output tile width
+constexpr int kG2H = 30;                 // output tile height
+constexpr int kG2SW = kG2W + 2;          // smoothed tile (1-pixel ring)
+constexpr int kG2SH = kG2H + 2;          // 32
+constexpr int kG2IW = kG2SW + 2 * kGR;   // 90 columns enter pass 1
+constexpr int kR1 = 16;                  // axis-0 outputs per thread (2 chunks cover 32 rows)
+constexpr int kR2 = 11;                  // axis-1 outputs per thread (6 chunks cover 66 columns)
+constexpr int kG2Threads = 192;
+static_assert(kG2SH % kR1 == 0 && kG2SW % kR2 == 0, "tile / chunk mismatch");
+static_assert((kG2SH / kR1) * kG2IW <= kG2Threads && (kG2SW / kR2) * kG2SH <= kG2Threads, "one work item per thread");
+
+template <bool kNms>
+__global__ void __launch_bounds__(kG2Threads)
+gauss_window_kernel(const double* __restrict__ heat, int H, int W, const GaussWeights gw, double thre, int cap,
+                    int* __restrict__ counts, uint32_t* __restrict__ keys, double* __restrict__ scores,
+                    double* __restrict__ smoothed) {
+  __shared__ double s_v[kG2SH][kG2IW + 1];   // pitch 91 doubles (odd)
+  __shared__ double s_s[kG2SH][kG2SW + 1];   // pitch 67 doubles (odd)
+  const int plane_id = blockIdx.z;
+  const double* src = heat + static_cast<long long>(plane_id) * H * W;
+  const int x0 = blockIdx.x * kG2W, y0 = blockIdx.y * kG2H;
+  {
+    const int item = threadIdx.x;
+    if (item < (kG2SH / kR1) * kG2IW) {
+      const int chunk = item / kG2IW, c = item - chunk * kG2IW;
+      const double* col = src + reflect_index(x0 - 1 - kGR + c, W);
+      double win[kR1 + 2 * kGR];
+      const int ybase = y0 - 1 - kGR + chunk * kR1;
+#pragma unroll
+      for (int k = 0; k < kR1 + 2 * kGR; ++k) win[k] = __ldg(col + static_cast<long long>(reflect_index(ybase + k, H)) * W);
+#pragma unroll
+      for (int o = 0; o < kR1; ++o) {
+        double tmp = __dmul_rn(win[o + kGR], gw.w[kGR]);
+#pragma unroll
+        for (int jj = -kGR; jj < 0; ++jj)
+          tmp = __dadd_rn(tmp, __dmul_rn(__dadd_rn(win[o + kGR + jj], win[o + kGR - jj]), gw.w[kGR + jj]));
+        s_v[chunk * kR1 + o][c] = tmp;
+      }
+    }
+  }
+  __syncthreads();
+  {
+    const int item = threadIdx.x;
+    if (item < (kG2SW / kR2) * kG2SH) {
+      const int chunk = item / kG2SH, r = item - chunk * kG2SH;
+      const int c0 = chunk * kR2;
+      double win[kR2 + 2 * kGR];
+#pragma unroll
+      for (int k = 0; k < kR2 + 2 * kGR; ++k) win[k] = s_v[r][c0 + k];
+      const int ys = y0 - 1 + r;
+      const bool row_in = ys >= 0 && ys < H;
+#pragma unroll
+      for (int o = 0; o < kR2; ++o) {
+        double tmp = __dmul_rn(win[o + kGR], gw.w[kGR]);
+#pragma unroll
+        for (int jj = -kGR; jj < 0; ++jj)
+          tmp = __dadd_rn(tmp, __dmul_rn(__dadd_rn(win[o + kGR + jj], win[o + kGR - jj]), gw.w[kGR + jj]));
+        const int xs = x0 - 1 + c0 + o;
+        // outside the frame the NMS neighbours are zero (body.py:90-97)
+        s_s[r][c0 + o] = (row_in && xs >= 0 && xs < W) ? tmp : 0.0;
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kG2H * kG2W; i += kG2Threads) {
+    const int r = i / kG2W, c = i - r * kG2W;
+    const int y = y0 + r, x = x0 + c;
+    if (y >= H || x >= W) continue;
+    const double v = s_s[r + 1][c + 1];
+    if (kNms) {
+      if (v >= s_s[r][c + 1] && v >= s_s[r + 2][c + 1] && v >= s_s[r + 1][c] && v >= s_s[r + 1][c + 2] && v > thre) {
+        const int slot = atomicAdd(counts + plane_id, 1);
+        if (slot < cap) {
+          keys[static_cast<long long>(plane_id) * cap + slot] = static_cast<uint32_t>(y) * W + x;
+          scores[static_cast<long long>(plane_id) * cap + slot] = src[static_cast<long long>(y) * W + x];
+        }
+      }
+    } else {
+      smoothed[static_cast<long long>(plane_id) * H * W + static_cast<long long>(y) * W + x] = v;
+    }
+  }
+}
+
 // One CTA per (frame, part): bitonic sort of the appended peaks by y*W+x = np.nonzero order.
 constexpr int kSortCap = 1024;
 __global__ void __launch_bounds__(512)
@@ -390,6 +482,15 @@ sort_peaks_kernel(int cap, int* __restrict__ counts, uint32_t* __restrict__ keys
 
 // ------------------------------------------------------------------------------------------------ launchers
 #define ISL_LAUNCH_OK() (cudaGetLastError() == cudaSuccess ? 0 : 1)
+
+// ISLPOSE_GAUSS=1 selects the first-generation tile kernel (kept for A/B measurements; results are identical)
+static int gauss_variant() {
+  static const int v = [] {
+    const char* e = getenv("ISLPOSE_GAUSS");
+    return (e != nullptr && e[0] == '1') ? 1 : 2;
+  }();
+  return v;
+}
 
 int launch_resize_pad_norm(const uint8_t* frames, int N, int H, int W, double scale, int rh, int rw, int hp, int wp,
                            float* out_nchw, uint8_t* out_u8, cudaStream_t st) {
@@ -448,16 +549,26 @@ int launch_gauss_nms(const double* heat, int planes_total, int H, int W, const G
                      int* counts, uint32_t* keys, double* scores, int* overflow, cudaStream_t st) {
   if (cap > kSortCap) return 1;
   if (cudaMemsetAsync(counts, 0, sizeof(int) * planes_total, st) != cudaSuccess) return 1;
-  const dim3 grid((W + kGT - 1) / kGT, (H + kGT - 1) / kGT, planes_total);
-  gauss_kernel<true><<<grid, 256, 0, st>>>(heat, 0, H, W, gw, thre, cap, counts, keys, scores, nullptr);
+  if (gauss_variant() == 1) {
+    const dim3 grid((W + kGT - 1) / kGT, (H + kGT - 1) / kGT, planes_total);
+    gauss_kernel<true><<<grid, 256, 0, st>>>(heat, 0, H, W, gw, thre, cap, counts, keys, scores, nullptr);
+  } else {
+    const dim3 grid((W + kG2W - 1) / kG2W, (H + kG2H - 1) / kG2H, planes_total);
+    gauss_window_kernel<true><<<grid, kG2Threads, 0, st>>>(heat, H, W, gw, thre, cap, counts, keys, scores, nullptr);
+  }
   sort_peaks_kernel<<<planes_total, 512, 0, st>>>(cap, counts, keys, scores, overflow);
   return ISL_LAUNCH_OK();
 }
 
 int launch_gauss_smooth(const double* heat, int planes_total, int H, int W, const GaussWeights& gw, double* smoothed,
                         cudaStream_t st) {
-  const dim3 grid((W + kGT - 1) / kGT, (H + kGT - 1) / kGT, planes_total);
-  gauss_kernel<false><<<grid, 256, 0, st>>>(heat, 0, H, W, gw, 0.0, 0, nullptr, nullptr, nullptr, smoothed);
+  if (gauss_variant() == 1) {
+    const dim3 grid((W + kGT - 1) / kGT, (H + kGT - 1) / kGT, planes_total);
+    gauss_kernel<false><<<grid, 256, 0, st>>>(heat, 0, H, W, gw, 0.0, 0, nullptr, nullptr, nullptr, smoothed);
+  } else {
+    const dim3 grid((W + kG2W - 1) / kG2W, (H + kG2H - 1) / kG2H, planes_total);
+    gauss_window_kernel<false><<<grid, kG2Threads, 0, st>>>(heat, H, W, gw, 0.0, 0, nullptr, nullptr, nullptr, smoothed);
+  }
   return ISL_LAUNCH_OK();
 }
 

@@ -37,9 +37,11 @@ def merge_shards(shards, n_items):
 class KeypointExtractor(object):
     """(candidate, subset, all_hand_peaks) per frame, like ISLSignPos.call (ISL_Model_parameter.py:51-60)."""
 
-    def __init__(self, body, hand=None):
+    def __init__(self, body, hand=None, chunk=4):
         self.body = body
         self.hand = hand
+        self.chunk = chunk      # frames per pipeline stage of batch_device(); None = no pipelining
+        self._lanes = None
 
     def __call__(self, frame):
         return self.batch([frame])[0]
@@ -72,9 +74,76 @@ class KeypointExtractor(object):
             per_frame[fi].append(p)
         return [(c, s, per_frame[i]) for i, (c, s) in enumerate(bodies)]
 
-    def batch_device(self, frames_dev, hand_boxes):
-        """Same as batch() for frames already resident on the device (uint8 cuda tensor [n,H,W,3]); the hand boxes
-        must be given because util.handDetect needs the host copy of candidate/subset either way."""
+    def batch_device(self, frames_dev, hand_boxes, chunk=None):
+        """Same as batch() for frames already resident on the device (uint8 cuda tensor [n,H,W,3]). hand_boxes=None
+        runs util.handDetect on every frame's (candidate, subset) as the reference loop does.
+
+        The batch is processed as a software pipeline over chunks of `chunk` frames on two lanes (independent
+        buffers and streams): while the host waits for the body results of chunk i (it needs them for
+        util.handDetect), the body networks of chunk i+1 are already queued, and the hand networks of chunk i
+        are queued before the host waits for chunk i+1. The memory- and latency-bound stages (map accumulation,
+        peaks, grouping, hand key points, the D2H copies) therefore run under the tensor-bound convolutions of
+        the neighbouring chunks. The per-frame dependency body -> handDetect -> hand is unchanged."""
+        import torch
+
+        n = int(frames_dev.shape[0])
+        chunk = int(chunk or self.chunk or n)
+        if not hasattr(self.body, "enqueue") or n <= chunk:
+            return self._batch_device_serial(frames_dev, hand_boxes)
+        bounds = [(a, min(a + chunk, n)) for a in range(0, n, chunk)]
+        lanes = self._lane_streams(torch)
+        main = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(main)
+
+        def start_body(ci):
+            a, b = bounds[ci]
+            st = lanes[ci % 2]
+            with torch.cuda.stream(st):
+                st.wait_event(ready)
+                return self.body.enqueue(frames_dev[a:b], lane=ci % 2)
+
+        results = [None] * n
+        hand_tickets = []
+        nxt = start_body(0)
+        for ci, (a, b) in enumerate(bounds):
+            cur = nxt
+            nxt = start_body(ci + 1) if ci + 1 < len(bounds) else None
+            bodies = self.body.finish(cur)
+            for k, r in enumerate(bodies):
+                results[a + k] = r
+            if self.hand is None:
+                continue
+            crops, owner = [], []
+            st = lanes[2 + ci % 2]
+            with torch.cuda.stream(st):
+                st.wait_event(ready)
+                for fi in range(a, b):
+                    cand, sub = results[fi]
+                    boxes = hand_boxes[fi] if hand_boxes is not None else util.handDetect(cand, sub, frames_dev[fi])
+                    for (x, y, w, is_left) in boxes:
+                        crops.append(frames_dev[fi, y:y + w, x:x + w, :].contiguous())
+                        owner.append((fi, x, y))
+                hand_tickets.append((owner, self.hand.enqueue(crops, lane=ci % 2) if crops else None))
+        if self.hand is None:
+            return [(c, s, []) for c, s in results]
+        owners, peaks = [], []
+        for owner, t in hand_tickets:
+            owners.extend(owner)
+            peaks.extend(self.hand.finish(t))
+        for st in lanes:
+            main.wait_stream(st)
+        return self._assemble(results, owners, peaks)
+
+    def _lane_streams(self, torch):
+        if self._lanes is None:
+            # body lanes run the post-processing on their own (high-priority) stream: its short kernels are on the
+            # critical path of the host loop and must not queue behind thousands of convolution CTAs
+            self._lanes = [torch.cuda.Stream(device=self.body.device, priority=-1) for _ in range(2)] + \
+                          [torch.cuda.Stream(device=self.body.device) for _ in range(2)]
+        return self._lanes
+
+    def _batch_device_serial(self, frames_dev, hand_boxes):
         bodies = self.body.batch_device(frames_dev)
         if self.hand is None:
             return [(c, s, []) for c, s in bodies]

@@ -29,12 +29,12 @@ class Hand(object):
         self.scale_search = [0.5, 1.0, 1.5, 2.0]   # hand.py:25
         self.boxsize, self.stride, self.padValue, self.thre = 368, 8, 128, 0.05
         self._gauss = (C.c_double * 25)(*gaussian_weights().tolist())
-        self._streams = []
+        self._streams = {}   # lane -> side streams
 
     def __call__(self, oriImg):
         return self.batch([oriImg])[0]
 
-    def network_outputs(self, crops_dev):
+    def network_outputs(self, crops_dev, lane=0):
         """crops_dev: list of uint8 cuda tensors [h,w,3]. Crops whose network inputs have the same shape (all square
         crops do: 184, 368, 552, 736) share a batched plan per scale. Returns per crop a list of
         (heat tensor, plane offset in elements, geometry)."""
@@ -48,7 +48,8 @@ class Hand(object):
                 key = (si, g[si][3], g[si][4])
                 group_sizes[key] = group_sizes.get(key, 0) + 1
         for (si, hp, wp), cnt in group_sizes.items():
-            self.model.instance(_pow2_at_least(cnt), hp, wp)
+            self.model.instance(_pow2_at_least(cnt), hp, wp, lane)
+        streams = self._streams.setdefault(lane, [])
         main = torch.cuda.current_stream()
         timing = self.model.timing
         if timing is not None:
@@ -57,18 +58,18 @@ class Hand(object):
         fork = torch.cuda.Event()
         fork.record(main)
         flops = launches = 0
-        lane = 0
+        used = 0
         for si in range(len(self.scale_search)):
             groups = {}
             for ci, g in enumerate(geoms):
                 groups.setdefault((g[si][3], g[si][4]), []).append(ci)
             for (hp, wp), members in groups.items():
                 # every (scale, input shape) group is an independent network replay: one stream each
-                while len(self._streams) <= lane:
-                    self._streams.append(torch.cuda.Stream(device=self.device))
-                side = self._streams[lane]
-                lane += 1
-                inst = self.model.instance(_pow2_at_least(len(members)), hp, wp)
+                while len(streams) <= used:
+                    streams.append(torch.cuda.Stream(device=self.device))
+                side = streams[used]
+                used += 1
+                inst = self.model.instance(_pow2_at_least(len(members)), hp, wp, lane)
                 with torch.cuda.stream(side):
                     side.wait_event(fork)
                     for slot, ci in enumerate(members):
@@ -125,29 +126,46 @@ class Hand(object):
         with torch.cuda.device(self.device):
             return self.batch_device([torch.from_numpy(c).to(self.device, non_blocking=True) for c in crops])
 
-    def batch_device(self, dev_crops):
-        """dev_crops: list of contiguous uint8 cuda tensors [h,w,3] -> list of int64 arrays [21,2]."""
+    def enqueue(self, dev_crops, lane=0):
+        """Launches the four network scales and the key-point selection of every crop (list of contiguous uint8
+        cuda tensors [h,w,3]) without waiting; finish(ticket) returns the list of int64 [21,2] arrays."""
         if not dev_crops:
-            return []
+            return None
         with torch.cuda.device(self.device):
-            per_crop = self.network_outputs(dev_crops)
+            per_crop = self.network_outputs(dev_crops, lane)
             # a crop's post-processing launches only 21 CTAs per kernel: spread the crops over a few streams
             main = torch.cuda.current_stream()
             fork = torch.cuda.Event()
             fork.record(main)
             lanes = min(len(dev_crops), 8)
-            while len(self._streams) < lanes:
-                self._streams.append(torch.cuda.Stream(device=self.device))
+            streams = self._streams.setdefault(lane, [])
+            while len(streams) < lanes:
+                streams.append(torch.cuda.Stream(device=self.device))
             outs = []
             for i in range(len(dev_crops)):
-                side = self._streams[i % lanes] if lanes > 1 else main
+                side = streams[i % lanes] if lanes > 1 else main
                 with torch.cuda.stream(side):
                     side.wait_event(fork)
                     outs.append(self.postprocess(per_crop[i], dev_crops[i].shape[0], dev_crops[i].shape[1]))
             if lanes > 1:
                 for j in range(lanes):
                     done = torch.cuda.Event()
-                    done.record(self._streams[j])
+                    done.record(streams[j])
                     main.wait_event(done)
-            stacked = torch.stack(outs).cpu().numpy()
-        return [stacked[i].astype(np.int64) for i in range(len(dev_crops))]
+            stacked = torch.stack(outs)
+            host = torch.empty(stacked.shape, dtype=stacked.dtype).pin_memory()
+            host.copy_(stacked, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(main)
+        return dict(host=host, done=done, n=len(dev_crops), keep=(outs, stacked, dev_crops))
+
+    def finish(self, ticket):
+        if ticket is None:
+            return []
+        ticket["done"].synchronize()
+        stacked = ticket["host"].numpy()
+        return [stacked[i].astype(np.int64) for i in range(ticket["n"])]
+
+    def batch_device(self, dev_crops):
+        """dev_crops: list of contiguous uint8 cuda tensors [h,w,3] -> list of int64 arrays [21,2]."""
+        return self.finish(self.enqueue(dev_crops))

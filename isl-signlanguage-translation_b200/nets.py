@@ -376,10 +376,12 @@ class PoseNet:
     def to(self, *args, **kwargs):
         return self
 
-    def instance(self, n, h, w):
+    def instance(self, n, h, w, lane=0):
+        """The plan (and its activation buffers) for one input shape. `lane` selects an independent copy, so that
+        two batches of the same shape can be in flight at once."""
         if h % 8 or w % 8:
             raise ValueError("network input must be a multiple of 8 in both dimensions, got %dx%d" % (h, w))
-        key = (n, h, w)
+        key = (n, h, w, lane)
         inst = self._instances.get(key)
         if inst is None:
             with torch.cuda.device(self.device):
