@@ -117,6 +117,7 @@ static int run_cfg(const Cfg& c, bool timing) {
   d.force_stages = c.force_stages;
   d.variant = c.variant;
   d.msub = c.msub;
+  if (c.variant == 5) d.force_bh = c.msub;  // v5: the msub column carries the tile height
   d.acc_bufs = c.acc_bufs;
   d.halo_base_offset_mode = c.bo_mode;
   d.debug_no_loads = c.no_loads;
@@ -355,6 +356,64 @@ static int run_v4_suite() {
   return 0;
 }
 
+static int run_v5_suite() {
+  // swapped operands + resident halo, persistent: correctness on awkward shapes first, then timings against v1 / v4
+  const Cfg cfgs[] = {
+      {"v5 3x3 64->128 16x8", 1, 8, 16, 64, 64, 0, 128, 3, false, true, 0, 0, 5, 0, 0, 0, 0},
+      {"v5 3x3 128->128 23x41 b2", 2, 23, 41, 128, 128, 0, 128, 3, false, true, 0, 0, 5, 0, 0, 0, 0},
+      {"v5 7x7 192->128 23x41 b2", 2, 23, 41, 192, 192, 0, 128, 7, false, true, 0, 0, 5, 0, 0, 0, 0},
+      {"v5 3x3 slice 96/288->96", 2, 23, 41, 96, 288, 96, 96, 3, false, true, 0, 0, 5, 0, 0, 0, 0},
+      {"v5 7x7 160->128 23x23 b3", 3, 23, 23, 160, 160, 0, 128, 7, false, true, 0, 0, 5, 0, 0, 0, 0},
+      {"v5 3x3 256->256 46x82 b2", 2, 46, 82, 256, 256, 0, 256, 3, false, true, 0, 0, 5, 0, 0, 0, 0},
+      {"v5 7x7 128->38 33x17 b1", 1, 33, 17, 128, 128, 0, 38, 7, false, true, 0, 0, 5, 0, 0, 0, 0},
+      {"v4 7x7 128->128 92x164 b8", 8, 92, 164, 128, 128, 0, 128, 7, false, true, 0, 0, 4, 0, 0, 0, 0},
+      {"v5 7x7 128->128 92x164 b8", 8, 92, 164, 128, 128, 0, 128, 7, false, true, 0, 0, 5, 0, 0, 0, 0},
+      {"v5 7x7 128 92x164 b8 th32", 8, 92, 164, 128, 128, 0, 128, 7, false, true, 0, 0, 5, 32, 0, 0, 0},
+      {"v5 7x7 128 92x164 b8 th32 norot", 8, 92, 164, 128, 128, 0, 128, 7, false, true, 0, 0, 5, 32, 1, 0, 0},
+      {"v5 7x7 128 92x164 b8 th24 norot", 8, 92, 164, 128, 128, 0, 128, 7, false, true, 0, 0, 5, 24, 1, 0, 0},
+      {"v5 7x7 128 92x164 b8 th24 s3", 8, 92, 164, 128, 128, 0, 128, 7, false, true, 0, 3, 5, 24, 0, 0, 0},
+      {"v5 7x7 128 92x164 b8 th16", 8, 92, 164, 128, 128, 0, 128, 7, false, true, 0, 0, 5, 16, 0, 0, 0},
+      {"v5 7x7 128 92x164 b8 th16 s4", 8, 92, 164, 128, 128, 0, 128, 7, false, true, 0, 4, 5, 16, 0, 0, 0},
+      {"v4 7x7 192->128 60x80 b8", 8, 60, 80, 192, 192, 0, 128, 7, false, true, 0, 0, 4, 0, 0, 0, 0},
+      {"v5 7x7 192->128 60x80 b8", 8, 60, 80, 192, 192, 0, 128, 7, false, true, 0, 0, 5, 0, 0, 0, 0},
+      {"v1 3x3 128->128 368x496 b2", 2, 368, 496, 128, 128, 0, 128, 3, false, true, 0, 0, 1, 0, 0, 0, 0},
+      {"v5 3x3 128->128 368x496 b2", 2, 368, 496, 128, 128, 0, 128, 3, false, true, 0, 0, 5, 0, 0, 0, 0},
+      {"v1 3x3 64->128 368x496 b2", 2, 368, 496, 64, 64, 0, 128, 3, false, true, 0, 0, 1, 0, 0, 0, 0},
+      {"v5 3x3 64->128 368x496 b2", 2, 368, 496, 64, 64, 0, 128, 3, false, true, 0, 0, 5, 0, 0, 0, 0},
+      {"v1 3x3 288->96 92x164 b8", 8, 92, 164, 288, 288, 0, 96, 3, false, true, 0, 0, 1, 0, 0, 0, 0},
+      {"v5 3x3 288->96 92x164 b8", 8, 92, 164, 288, 288, 0, 96, 3, false, true, 0, 0, 5, 0, 0, 0, 0},
+      {"v1 3x3 96->96 slice 92x164 b8", 8, 92, 164, 96, 288, 96, 96, 3, false, true, 0, 0, 1, 0, 0, 0, 0},
+      {"v5 3x3 96->96 slice 92x164 b8", 8, 92, 164, 96, 288, 96, 96, 3, false, true, 0, 0, 5, 0, 0, 0, 0},
+      {"v1 3x3 128->128 92x164 b8", 8, 92, 164, 128, 128, 0, 128, 3, false, true, 0, 0, 1, 0, 0, 0, 0},
+      {"v5 3x3 128->128 92x164 b8", 8, 92, 164, 128, 128, 0, 128, 3, false, true, 0, 0, 5, 0, 0, 0, 0},
+      {"v1 3x3 512->512 92x164 b2 nt256", 2, 92, 164, 512, 512, 0, 512, 3, false, true, 0, 0, 1, 0, 0, 0, 0},
+      {"v5 3x3 512->512 92x164 b2", 2, 92, 164, 512, 512, 0, 512, 3, false, true, 0, 0, 5, 0, 0, 0, 0},
+      {"v1 3x3 256->256 184x328 b2", 2, 184, 328, 256, 256, 0, 256, 3, false, true, 0, 0, 1, 0, 0, 0, 0},
+      {"v5 3x3 256->256 184x328 b2", 2, 184, 328, 256, 256, 0, 256, 3, false, true, 0, 0, 5, 0, 0, 0, 0},
+      {"v4 3x3 512->128 92x92 b8", 8, 92, 92, 512, 512, 0, 128, 3, false, true, 0, 0, 4, 0, 0, 0, 0},
+      {"v5 3x3 512->128 92x92 b8", 8, 92, 92, 512, 512, 0, 128, 3, false, true, 0, 0, 5, 0, 0, 0, 0},
+      {"v1 7x7 128->128 23x31 b8", 8, 23, 31, 128, 128, 0, 128, 7, false, true, 0, 0, 1, 0, 0, 0, 0},
+      {"v5 7x7 128->128 23x31 b8", 8, 23, 31, 128, 128, 0, 128, 7, false, true, 0, 0, 5, 0, 0, 0, 0},
+      {"v1 7x7 128->128 46x62 b8", 8, 46, 62, 128, 128, 0, 128, 7, false, true, 0, 0, 1, 0, 0, 0, 0},
+      {"v5 7x7 128->128 46x62 b8", 8, 46, 62, 128, 128, 0, 128, 7, false, true, 0, 0, 5, 0, 0, 0, 0},
+      {"v1 7x7 128->128 69x92 b8", 8, 69, 92, 128, 128, 0, 128, 7, false, true, 0, 0, 1, 0, 0, 0, 0},
+      {"v5 7x7 128->128 69x92 b8", 8, 69, 92, 128, 128, 0, 128, 7, false, true, 0, 0, 5, 0, 0, 0, 0},
+      {"v5 7x7 128->128 23x31 b2", 2, 23, 31, 128, 128, 0, 128, 7, false, true, 0, 0, 5, 0, 0, 0, 0},
+      {"v1 7x7 128->128 23x31 b2", 2, 23, 31, 128, 128, 0, 128, 7, false, true, 0, 0, 1, 0, 0, 0, 0},
+  };
+  int fails = 0;
+  for (const Cfg& c : cfgs) {
+    const int r = run_cfg(c, true);
+    if (r == 3) {
+      printf("context lost, stopping\n");
+      return 3;
+    }
+    fails += r;
+  }
+  printf("%s: %d failing configuration(s)\n", fails ? "FAILED" : "DONE", fails);
+  return fails ? 1 : 0;
+}
+
 static int run_limits_suite() {
   // where is the ceiling? same layers with and without TMA traffic (no_loads: results are garbage by design)
   const Cfg cfgs[] = {
@@ -414,6 +473,7 @@ int main(int argc, char** argv) {
   if (argc > 1 && std::string(argv[1]) == "v3") return run_v3_suite();
   if (argc > 1 && std::string(argv[1]) == "limits") return run_limits_suite();
   if (argc > 1 && std::string(argv[1]) == "v4") return run_v4_suite();
+  if (argc > 1 && std::string(argv[1]) == "v5") return run_v5_suite();
   int fails = 0;
   for (int i = 0; i < n; ++i) {
     if (argc > 1 && atoi(argv[1]) != i) continue;

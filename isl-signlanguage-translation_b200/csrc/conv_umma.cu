@@ -24,6 +24,26 @@ constexpr uint32_t kASlotBytes = 128 * 128;  // 128 pixel rows x 64 bf16
 constexpr int kMaxStages = 8;
 constexpr uint32_t kCtrlBytes = 256 + 2 * 256 * 4;  // barriers + bias + slope
 
+// The four K=16 MMAs of one 64-channel block, fully unrolled with constant descriptor offsets (+32 bytes along K
+// inside the 128-byte swizzle row = +2 in the >>4 address field). The issue loops run on ONE lane: every instruction
+// in them is on the critical path of the tensor pipe (build/mma_rate: a lean loop issues a K-block in ~70 cycles per
+// MMA; runtime divisions and per-MMA predicate set-up had pushed that to ~270). No division, no variable trip
+// count, no per-MMA predicate in the common case.
+__device__ __forceinline__ void issue_kblock4(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, bool accumulate_first) {
+  ptx::umma_bf16(d, da, db, idesc, accumulate_first ? 1u : 0u);
+  ptx::umma_bf16_acc(d, da + 2, db + 2, idesc);
+  ptx::umma_bf16_acc(d, da + 4, db + 4, idesc);
+  ptx::umma_bf16_acc(d, da + 6, db + 6, idesc);
+}
+__device__ __forceinline__ void issue_kblock(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, bool accumulate_first,
+                                             int ksteps) {
+  if (ksteps == 4) {
+    issue_kblock4(d, da, db, idesc, accumulate_first);
+  } else {  // the slice ends inside this block (only the 32-channel first layer)
+    for (int k = 0; k < ksteps; ++k) ptx::umma_bf16(d, da + 2 * k, db + 2 * k, idesc, (accumulate_first || k != 0) ? 1u : 0u);
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const ConvArgs a) {
@@ -85,50 +105,75 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot_g;
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------ TMA producer (whole warp, one elected lane issues)
+    {
       const uint32_t tx_bytes = 128u * a.bw * a.bh + 128u * a.n_tile;
-      int it = 0;
-      for (int tap = 0; tap < taps; ++tap) {
-        const int ky = tap / a.ksize;
-        const int kx = tap - ky * a.ksize;
-        for (int cb = 0; cb < cblocks; ++cb, ++it) {
-          const int s = it % a.stages;
-          const uint32_t ph = (it / a.stages) & 1;
-          ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1);
+      const int total = taps * cblocks;
+      const int xb = x0 - a.pad, yb = y0 - a.pad;
+      ptx::RingPos r(bar_full, bar_empty, a.stages);
+      uint32_t sa = sA0, sb = sB0;
+      int kx = 0, ky = 0, cb = 0, tap = 0;
+      for (int it = 0; it < total; ++it) {
+        ptx::mbar_wait(r.empty, r.ph ^ 1);
+        if (ptx::elect_one()) {
           if (a.debug_no_loads && it >= a.stages) {  // measurement aid: the MMAs re-read what the ring already holds
-            ptx::mbar_arrive(bar_full + 8 * s);
-            continue;
+            ptx::mbar_arrive(r.full);
+          } else {
+            ptx::mbar_arrive_expect_tx(r.full, tx_bytes);
+            ptx::tma_load_4d(sa, &tmA, r.full, cb * 64, xb + kx, yb + ky, img);
+            ptx::tma_load_3d(sb, &tmB, r.full, cb * 64, n0, tap);
           }
-          ptx::mbar_arrive_expect_tx(bar_full + 8 * s, tx_bytes);
-          ptx::tma_load_4d(sA0 + s * kASlotBytes, &tmA, bar_full + 8 * s, cb * 64, x0 + kx - a.pad,
-                           y0 + ky - a.pad, img);
-          ptx::tma_load_3d(sB0 + s * a.b_stage_bytes, &tmB, bar_full + 8 * s, cb * 64, n0, tap);
+        }
+        __syncwarp();
+        if (++cb == cblocks) {
+          cb = 0;
+          ++tap;
+          if (++kx == a.ksize) {
+            kx = 0;
+            ++ky;
+          }
+        }
+        sa += kASlotBytes;
+        sb += a.b_stage_bytes;
+        if (r.advance()) {
+          sa = sA0;
+          sb = sB0;
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------ MMA issuer (whole warp, one elected lane issues)
+    {
       const uint32_t idesc = ptx::umma_idesc_bf16(128, a.n_tile);
-      int it = 0;
-      for (int tap = 0; tap < taps; ++tap) {
-        for (int cb = 0; cb < cblocks; ++cb, ++it) {
-          const int s = it % a.stages;
-          const uint32_t ph = (it / a.stages) & 1;
-          ptx::mbar_wait(bar_full + 8 * s, ph);
-          ptx::tc_fence_after();
-          const uint64_t da = ptx::umma_desc_sw128(sA0 + s * kASlotBytes);
-          const uint64_t db = ptx::umma_desc_sw128(sB0 + s * a.b_stage_bytes);
-          const int ksteps = min(4, a.cin_k16 - cb * 4);
-          for (int k = 0; k < ksteps; ++k) {
-            // +32 bytes (16 bf16) along K inside the 128-byte swizzle row = +2 in the >>4 address field
-            ptx::umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
-          }
-          ptx::umma_commit(bar_empty + 8 * s);  // slot reusable once these MMAs have read it
+      const int total = taps * cblocks;
+      const int tail_ksteps = a.cin_k16 - (cblocks - 1) * 4;  // K=16 steps of the last channel block: 1..4
+      const uint64_t da0 = ptx::umma_desc_sw128(sA0), db0 = ptx::umma_desc_sw128(sB0);
+      const uint32_t a_step = kASlotBytes >> 4, b_step = a.b_stage_bytes >> 4;
+      uint64_t da = da0, db = db0;
+      ptx::RingPos r(bar_full, bar_empty, a.stages);
+      int cb = 0;
+      for (int it = 0; it < total; ++it) {
+        ptx::mbar_wait(r.full, r.ph);
+        ptx::tc_fence_after();
+        int ksteps = 4;
+        if (tail_ksteps != 4 && ++cb == cblocks) {
+          cb = 0;
+          ksteps = tail_ksteps;
+        }
+        if (ptx::elect_one()) {
+          issue_kblock(tmem_base, da, db, idesc, it != 0, ksteps);
+          ptx::umma_commit(r.empty);  // slot reusable once these MMAs have read it
+        }
+        __syncwarp();
+        da += a_step;
+        db += b_step;
+        if (r.advance()) {
+          da = da0;
+          db = db0;
         }
       }
-      ptx::umma_commit(bar_accum);
+      if (ptx::elect_one()) ptx::umma_commit(bar_accum);
+      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------ epilogue
@@ -254,9 +299,10 @@ conv_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   const uint32_t acc_cols = a.msub * a.n_tile;  // columns of one accumulator buffer
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int it = 0;
+    // ------------------------------------------------------------ TMA producer (whole warp, one elected lane issues)
+    {
+      ptx::RingPos r(bar_full, bar_empty, a.stages);
+      uint32_t sa = sA0, sb = sB0;
       for (int w = blockIdx.x; w < a.work_items; w += gridDim.x) {
         const int mg = w % m_groups;
         const int n0 = (w / m_groups) * a.n_tile;
@@ -266,62 +312,83 @@ conv_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
           const int t = mg * a.msub + sub;
           if (t < a.m_tiles) {
             img[sub] = t / tiles_per_img;
-            const int r = t - img[sub] * tiles_per_img;
-            y0[sub] = (r / a.tiles_x) * a.bh;
-            x0[sub] = (r % a.tiles_x) * a.bw;
+            const int rr = t - img[sub] * tiles_per_img;
+            y0[sub] = (rr / a.tiles_x) * a.bh - a.pad;
+            x0[sub] = (rr % a.tiles_x) * a.bw - a.pad;
             ++live;
           }
         }
         const uint32_t tx_bytes = 128u * a.bw * a.bh * live + 128u * a.n_tile;
-        for (int tap = 0; tap < taps; ++tap) {
-          const int ky = tap / a.ksize;
-          const int kx = tap - ky * a.ksize;
-          for (int cb = 0; cb < cblocks; ++cb, ++it) {
-            const int s = it % a.stages;
-            const uint32_t ph = (it / a.stages) & 1;
-            ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1);
-            ptx::mbar_arrive_expect_tx(bar_full + 8 * s, tx_bytes);
-            for (int sub = 0; sub < live; ++sub) {
-              ptx::tma_load_4d(sA0 + s * a_stage_bytes + sub * kASlotBytes, &tmA, bar_full + 8 * s, cb * 64,
-                               x0[sub] + kx - a.pad, y0[sub] + ky - a.pad, img[sub]);
+        int tap = 0;
+        for (int ky = 0; ky < a.ksize; ++ky) {
+          for (int kx = 0; kx < a.ksize; ++kx, ++tap) {
+            for (int cb = 0; cb < cblocks; ++cb) {
+              ptx::mbar_wait(r.empty, r.ph ^ 1);
+              if (ptx::elect_one()) {
+                ptx::mbar_arrive_expect_tx(r.full, tx_bytes);
+                ptx::tma_load_4d(sa, &tmA, r.full, cb * 64, x0[0] + kx, y0[0] + ky, img[0]);
+                if (live > 1) ptx::tma_load_4d(sa + kASlotBytes, &tmA, r.full, cb * 64, x0[1] + kx, y0[1] + ky, img[1]);
+                ptx::tma_load_3d(sb, &tmB, r.full, cb * 64, n0, tap);
+              }
+              __syncwarp();
+              sa += a_stage_bytes;
+              sb += a.b_stage_bytes;
+              if (r.advance()) {
+                sa = sA0;
+                sb = sB0;
+              }
             }
-            ptx::tma_load_3d(sB0 + s * a.b_stage_bytes, &tmB, bar_full + 8 * s, cb * 64, n0, tap);
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------ MMA issuer (whole warp, one elected lane issues)
+    {
       const uint32_t idesc = ptx::umma_idesc_bf16(128, a.n_tile);
-      int it = 0;
-      int local = 0;
-      for (int w = blockIdx.x; w < a.work_items; w += gridDim.x, ++local) {
+      const int total = taps * cblocks;
+      const int tail_ksteps = a.cin_k16 - (cblocks - 1) * 4;
+      const uint64_t da0 = ptx::umma_desc_sw128(sA0), db0 = ptx::umma_desc_sw128(sB0);
+      const uint32_t a_step = a_stage_bytes >> 4, b_step = a.b_stage_bytes >> 4, sub_step = kASlotBytes >> 4;
+      uint64_t da = da0, db = db0;
+      ptx::RingPos r(bar_full, bar_empty, a.stages);
+      uint32_t buf = 0, buf_ph = 0;  // accumulator buffer of this work item and the phase of its current use
+      for (int w = blockIdx.x; w < a.work_items; w += gridDim.x) {
         const int mg = w % m_groups;
         const int live = min(a.msub, a.m_tiles - mg * a.msub);
-        const int buf = local % a.acc_bufs;
-        ptx::mbar_wait(bar_acc_empty + 8 * buf, ((local / a.acc_bufs) & 1) ^ 1);  // epilogue has drained this buffer
+        ptx::mbar_wait(bar_acc_empty + 8 * buf, buf_ph ^ 1);  // epilogue has drained this buffer
         ptx::tc_fence_after();
         const uint32_t acc = tmem_base + buf * acc_cols;
-        int kb = 0;
-        for (int tap = 0; tap < taps; ++tap) {
-          for (int cb = 0; cb < cblocks; ++cb, ++it, ++kb) {
-            const int s = it % a.stages;
-            const uint32_t ph = (it / a.stages) & 1;
-            ptx::mbar_wait(bar_full + 8 * s, ph);
-            ptx::tc_fence_after();
-            const uint64_t db = ptx::umma_desc_sw128(sB0 + s * a.b_stage_bytes);
-            const int ksteps = min(4, a.cin_k16 - cb * 4);
-            for (int sub = 0; sub < live; ++sub) {
-              const uint64_t da = ptx::umma_desc_sw128(sA0 + s * a_stage_bytes + sub * kASlotBytes);
-              for (int k = 0; k < ksteps; ++k) {
-                ptx::umma_bf16(acc + sub * a.n_tile, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-              }
+        int cb = 0;
+        for (int kb = 0; kb < total; ++kb) {
+          ptx::mbar_wait(r.full, r.ph);
+          ptx::tc_fence_after();
+          int ksteps = 4;
+          if (tail_ksteps != 4) {
+            if (++cb == cblocks) {
+              cb = 0;
+              ksteps = tail_ksteps;
             }
-            ptx::umma_commit(bar_empty + 8 * s);
+          }
+          if (ptx::elect_one()) {
+            issue_kblock(acc, da, db, idesc, kb != 0, ksteps);
+            if (live > 1) issue_kblock(acc + a.n_tile, da + sub_step, db, idesc, kb != 0, ksteps);
+            ptx::umma_commit(r.empty);
+          }
+          __syncwarp();
+          da += a_step;
+          db += b_step;
+          if (r.advance()) {
+            da = da0;
+            db = db0;
           }
         }
-        ptx::umma_commit(bar_acc_full + 8 * buf);
+        if (ptx::elect_one()) ptx::umma_commit(bar_acc_full + 8 * buf);
+        __syncwarp();
+        if (++buf == static_cast<uint32_t>(a.acc_bufs)) {
+          buf = 0;
+          buf_ph ^= 1;
+        }
       }
     }
   } else {
@@ -488,17 +555,18 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
   if (warp == 0) {
     if (lane == 0) {
-      int it = 0;
+      ptx::RingPos r(bar_full, bar_empty, a.stages);
+      uint32_t sb = sB0;
       for (int cb = 0; cb < cblocks; ++cb) {
         ptx::mbar_wait(bar_hempty, (cb & 1) ^ 1);
         ptx::mbar_arrive_expect_tx(bar_hfull, halo_bytes);
         ptx::tma_load_4d(sH, &tmA, bar_hfull, cb * 64, x0 - a.pad, y0 - a.pad, img);
-        for (int tap = 0; tap < taps; ++tap, ++it) {
-          const int s = it % a.stages;
-          const uint32_t ph = (it / a.stages) & 1;
-          ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1);
-          ptx::mbar_arrive_expect_tx(bar_full + 8 * s, 128u * a.n_tile);
-          ptx::tma_load_3d(sB0 + s * a.b_stage_bytes, &tmB, bar_full + 8 * s, cb * 64, n0, tap);
+        for (int tap = 0; tap < taps; ++tap) {
+          ptx::mbar_wait(r.empty, r.ph ^ 1);
+          ptx::mbar_arrive_expect_tx(r.full, 128u * a.n_tile);
+          ptx::tma_load_3d(sb, &tmB, r.full, cb * 64, n0, tap);
+          sb += a.b_stage_bytes;
+          if (r.advance()) sb = sB0;
         }
       }
     }
@@ -506,28 +574,28 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (lane == 0) {
       const uint32_t idesc = ptx::umma_idesc_bf16(128, a.n_tile);
       const uint32_t sbo = 128u * a.halo_w;  // one image row of the tile further down = halo_w pixel rows
-      int it = 0;
+      const uint64_t db0 = ptx::umma_desc_sw128(sB0);
+      const uint32_t b_step = a.b_stage_bytes >> 4;
+      uint64_t db = db0;
+      ptx::RingPos r(bar_full, bar_empty, a.stages);
       for (int cb = 0; cb < cblocks; ++cb) {
         ptx::mbar_wait(bar_hfull, cb & 1);
         ptx::tc_fence_after();
         const int ksteps = min(4, a.cin_k16 - cb * 4);
-        for (int tap = 0; tap < taps; ++tap, ++it) {
-          const int ky = tap / a.ksize;
-          const int kx = tap - ky * a.ksize;
-          const int s = it % a.stages;
-          const uint32_t ph = (it / a.stages) & 1;
-          ptx::mbar_wait(bar_full + 8 * s, ph);
-          ptx::tc_fence_after();
-          const uint32_t arow = sH + 128u * (ky * a.halo_w + kx);
-          // measured on B200: the swizzle XOR is taken from the absolute shared-memory address, so a window that
-          // starts on any 128-byte row needs base offset 0 (mode 1 = the start row's phase, kept for the bring-up test)
-          const uint32_t bo = a.halo_bo_mode == 1 ? ((arow >> 7) & 7u) : 0u;
-          const uint64_t da = ptx::umma_desc_sw128_strided(arow, sbo, bo);
-          const uint64_t db = ptx::umma_desc_sw128(sB0 + s * a.b_stage_bytes);
-          for (int k = 0; k < ksteps; ++k) {
-            ptx::umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+        for (int ky = 0; ky < a.ksize; ++ky) {
+          for (int kx = 0; kx < a.ksize; ++kx) {
+            ptx::mbar_wait(r.full, r.ph);
+            ptx::tc_fence_after();
+            const uint32_t arow = sH + 128u * (ky * a.halo_w + kx);
+            // measured on B200: the swizzle XOR is taken from the absolute shared-memory address, so a window that
+            // starts on any 128-byte row needs base offset 0 (mode 1 = the start row's phase, kept for the bring-up test)
+            const uint32_t bo = a.halo_bo_mode == 1 ? ((arow >> 7) & 7u) : 0u;
+            const uint64_t da = ptx::umma_desc_sw128_strided(arow, sbo, bo);
+            issue_kblock(tmem_base, da, db, idesc, (cb | ky | kx) != 0, ksteps);
+            ptx::umma_commit(r.empty);
+            db += b_step;
+            if (r.advance()) db = db0;
           }
-          ptx::umma_commit(bar_empty + 8 * s);
         }
         ptx::umma_commit(bar_hempty);  // the halo tile may be overwritten once these MMAs have retired
       }
@@ -663,42 +731,68 @@ conv_umma_swapped_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const uint32_t tmem_base = *tmem_slot_g;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       const uint32_t tx_bytes = kWBytes + 128u * a.bw * a.bh;
-      int it = 0;
-      for (int tap = 0; tap < taps; ++tap) {
-        const int ky = tap / a.ksize;
-        const int kx = tap - ky * a.ksize;
-        for (int cb = 0; cb < cblocks; ++cb, ++it) {
-          const int s = it % a.stages;
-          const uint32_t ph = (it / a.stages) & 1;
-          ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1);
-          ptx::mbar_arrive_expect_tx(bar_full + 8 * s, tx_bytes);
-          ptx::tma_load_3d(sW0 + s * kWBytes, &tmB, bar_full + 8 * s, cb * 64, n0, tap);
-          ptx::tma_load_4d(sX0 + s * kXBytes, &tmA, bar_full + 8 * s, cb * 64, x0 + kx - a.pad, y0 + ky - a.pad, img);
+      const int total = taps * cblocks;
+      const int xb = x0 - a.pad, yb = y0 - a.pad;
+      ptx::RingPos r(bar_full, bar_empty, a.stages);
+      uint32_t sw = sW0, sx = sX0;
+      int kx = 0, ky = 0, cb = 0, tap = 0;
+      for (int it = 0; it < total; ++it) {
+        ptx::mbar_wait(r.empty, r.ph ^ 1);
+        if (ptx::elect_one()) {
+          ptx::mbar_arrive_expect_tx(r.full, tx_bytes);
+          ptx::tma_load_3d(sw, &tmB, r.full, cb * 64, n0, tap);
+          ptx::tma_load_4d(sx, &tmA, r.full, cb * 64, xb + kx, yb + ky, img);
+        }
+        __syncwarp();
+        if (++cb == cblocks) {
+          cb = 0;
+          ++tap;
+          if (++kx == a.ksize) {
+            kx = 0;
+            ++ky;
+          }
+        }
+        sw += kWBytes;
+        sx += kXBytes;
+        if (r.advance()) {
+          sw = sW0;
+          sx = sX0;
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       const uint32_t idesc = ptx::umma_idesc_bf16(128, a.n_pix);
-      int it = 0;
-      for (int tap = 0; tap < taps; ++tap) {
-        for (int cb = 0; cb < cblocks; ++cb, ++it) {
-          const int s = it % a.stages;
-          const uint32_t ph = (it / a.stages) & 1;
-          ptx::mbar_wait(bar_full + 8 * s, ph);
-          ptx::tc_fence_after();
-          const uint64_t dw = ptx::umma_desc_sw128(sW0 + s * kWBytes);
-          const uint64_t dx = ptx::umma_desc_sw128(sX0 + s * kXBytes);
-          const int ksteps = min(4, a.cin_k16 - cb * 4);
-          for (int k = 0; k < ksteps; ++k) {
-            ptx::umma_bf16(tmem_base, dw + 2 * k, dx + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
-          }
-          ptx::umma_commit(bar_empty + 8 * s);
+      const int total = taps * cblocks;
+      const int tail_ksteps = a.cin_k16 - (cblocks - 1) * 4;
+      const uint64_t dw0 = ptx::umma_desc_sw128(sW0), dx0 = ptx::umma_desc_sw128(sX0);
+      uint64_t dw = dw0, dx = dx0;
+      ptx::RingPos r(bar_full, bar_empty, a.stages);
+      int cb = 0;
+      for (int it = 0; it < total; ++it) {
+        ptx::mbar_wait(r.full, r.ph);
+        ptx::tc_fence_after();
+        int ksteps = 4;
+        if (tail_ksteps != 4 && ++cb == cblocks) {
+          cb = 0;
+          ksteps = tail_ksteps;
+        }
+        if (ptx::elect_one()) {
+          issue_kblock(tmem_base, dw, dx, idesc, it != 0, ksteps);
+          ptx::umma_commit(r.empty);
+        }
+        __syncwarp();
+        dw += kWBytes >> 4;
+        dx += kXBytes >> 4;
+        if (r.advance()) {
+          dw = dw0;
+          dx = dx0;
         }
       }
-      ptx::umma_commit(bar_accum);
+      if (ptx::elect_one()) ptx::umma_commit(bar_accum);
+      __syncwarp();
     }
   } else {
     // epilogue: this thread owns output channel n0 + 32*q + lane for all pixels of the tile
@@ -777,6 +871,239 @@ conv_umma_swapped_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   }
 }
 
+// ------------------------------------------------------------------------------------------------ v5
+// Swapped operands + resident activation halo, persistent. With lean issue loops the v1 / v4 kernels are bound by
+// L2 -> SM operand delivery (~60 B/clk/SM: 32 KB per 128x128x64 K-block, 48 KB per 128x256x64), not by the tensor
+// pipe (build/mma_rate, profiles/). For k > 1 almost all of those bytes are the same activations fetched again
+// for every tap. Here a work item is 128 output channels x (8 x th) pixels, th <= 32:
+//   * per 64-channel block the (8+2p) x (th+2p) input window is fetched ONCE as a TMA box of 16 x (th+2p) pixel
+//     rows (pitch 16 rows = 2048 B keeps every 8-row operand group on one swizzle phase); it is the B operand
+//     (N = 8*th pixels): tap (ky,kx) reads the window that starts at halo row ky*16+kx, its 8-row groups (one image
+//     row of the tile each) 2048 B apart. The UMMA swizzle is a function of the absolute shared-memory address
+//     (established with v3), so a window may start on any 128-byte row with base offset 0;
+//   * only the 16 KB weight tile of each (tap, channel block) streams through a ring: 16 KB per 128 x 256 x 64
+//     K-block = 32 B/clk/SM at the tensor pipe's full rate;
+//   * halo buffers and TMEM accumulators are double buffered and the CTA is persistent (one per SM), so the halo
+//     fetch of the next channel block, the epilogue of the previous work item and the weight stream all overlap
+//     the MMAs. Epilogue lane = output channel; 32 lanes store 32 neighbouring channels of one pixel.
+__global__ void __launch_bounds__(kThreads, 1)
+conv_umma_halo_swapped_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                              const ConvArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* const gbase = smem_raw + (base - raw);
+
+  constexpr uint32_t kWBytes = 128 * 128;
+  const uint32_t halo_bytes = 2048u * a.halo_h;  // 16 pixel rows x 128 B per image row of the window
+  const uint32_t sH0 = base;
+  const uint32_t sW0 = base + 2 * halo_bytes;
+  const uint32_t ctrl = sW0 + a.stages * kWBytes;
+  uint8_t* const gctrl = gbase + (ctrl - base);
+  const uint32_t bar_wfull = ctrl;            // kMaxStages x 8 B
+  const uint32_t bar_wempty = ctrl + 64;      // kMaxStages x 8 B
+  const uint32_t bar_hfull = ctrl + 128;      // 2 x 8 B: halo buffer landed
+  const uint32_t bar_hempty = ctrl + 144;     // 2 x 8 B: every tap of the channel block has read it
+  const uint32_t bar_acc_full = ctrl + 160;   // 2 x 8 B
+  const uint32_t bar_acc_empty = ctrl + 176;  // 2 x 8 B
+  const uint32_t tmem_slot = ctrl + 192;
+  volatile uint32_t* const tmem_slot_g = reinterpret_cast<volatile uint32_t*>(gctrl + 192);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int cblocks = (a.cin_k16 + 3) >> 2;
+  const int tiles_per_img = a.tiles_x * a.tiles_y;
+  // Every CTA walks the same k*k weight tiles per channel block. Starting each CTA at a different tap keeps the
+  // 148 CTAs from requesting the same 16 KB tile from the same L2 slices at the same moment (fp32 accumulation
+  // order differs per CTA, deterministically).
+  const int rot = a.tap_rot ? static_cast<int>(blockIdx.x % (a.ksize * a.ksize)) : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < a.stages; ++s) {
+      ptx::mbar_init(bar_wfull + 8 * s, 1);
+      ptx::mbar_init(bar_wempty + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(bar_hfull + 8 * b, 1);
+      ptx::mbar_init(bar_hempty + 8 * b, 1);
+      ptx::mbar_init(bar_acc_full + 8 * b, 1);
+      ptx::mbar_init(bar_acc_empty + 8 * b, 4);  // one arrival per epilogue warp
+    }
+    ptx::mbar_fence_init();
+    ptx::prefetch_tensormap(&tmX);
+    ptx::prefetch_tensormap(&tmW);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_g;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (whole warp, one elected lane issues)
+    {
+      ptx::RingPos r(bar_wfull, bar_wempty, a.stages);
+      uint32_t sw = sW0;
+      uint32_t hb = 0, hph = 0;
+      const int taps = a.ksize * a.ksize;
+      for (int w = blockIdx.x; w < a.work_items; w += gridDim.x) {
+        const int ct = w % a.n_tiles;
+        const int pt = w / a.n_tiles;
+        const int img = pt / tiles_per_img;
+        const int rr = pt - img * tiles_per_img;
+        const int ty = rr / a.tiles_x;
+        const int xh = (rr - ty * a.tiles_x) * 8 - a.pad;
+        const int yh = ty * a.bh - a.pad;
+        const int c0 = ct * 128;
+        for (int cb = 0; cb < cblocks; ++cb) {
+          ptx::mbar_wait(bar_hempty + 8 * hb, hph ^ 1);
+          if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(bar_hfull + 8 * hb, halo_bytes);
+            ptx::tma_load_4d(sH0 + hb * halo_bytes, &tmX, bar_hfull + 8 * hb, cb * 64, xh, yh, img);
+          }
+          __syncwarp();
+          int tap = rot;
+          for (int t = 0; t < taps; ++t) {
+            ptx::mbar_wait(r.empty, r.ph ^ 1);
+            if (ptx::elect_one()) {
+              ptx::mbar_arrive_expect_tx(r.full, kWBytes);
+              ptx::tma_load_3d(sw, &tmW, r.full, cb * 64, c0, tap);
+            }
+            __syncwarp();
+            if (++tap == taps) tap = 0;
+            sw += kWBytes;
+            if (r.advance()) sw = sW0;
+          }
+          hb ^= 1;
+          if (hb == 0) hph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (whole warp, one elected lane issues)
+    {
+      const uint32_t idesc = ptx::umma_idesc_bf16(128, a.n_pix);
+      const uint64_t dw0 = ptx::umma_desc_sw128(sW0);
+      uint64_t dw = dw0;
+      const uint64_t dh0 = ptx::umma_desc_sw128_strided(sH0, 2048u, 0u);
+      const uint64_t dh1 = ptx::umma_desc_sw128_strided(sH0 + halo_bytes, 2048u, 0u);
+      ptx::RingPos r(bar_wfull, bar_wempty, a.stages);
+      uint32_t hb = 0, hph = 0;
+      uint32_t buf = 0, buf_ph = 0;
+      const uint32_t row_skip = static_cast<uint32_t>(16 - a.ksize) * 8u;  // descriptor units (16 B) to the next window row
+      const int taps = a.ksize * a.ksize;
+      const int rot_ky = rot / a.ksize, rot_kx = rot - rot_ky * a.ksize;
+      const uint32_t rot_off = static_cast<uint32_t>(rot_ky * 16 + rot_kx) * 8u;
+      for (int w = blockIdx.x; w < a.work_items; w += gridDim.x) {
+        ptx::mbar_wait(bar_acc_empty + 8 * buf, buf_ph ^ 1);  // the epilogue has drained this accumulator
+        ptx::tc_fence_after();
+        const uint32_t acc = tmem_base + buf * 256u;
+        uint32_t accumulate = 0;
+        for (int cb = 0; cb < cblocks; ++cb) {
+          ptx::mbar_wait(bar_hfull + 8 * hb, hph);
+          ptx::tc_fence_after();
+          const int ksteps = min(4, a.cin_k16 - cb * 4);
+          const uint64_t dx0 = hb ? dh1 : dh0;
+          uint64_t dx = dx0 + rot_off;
+          int kx = rot_kx, tap = rot;
+          for (int t = 0; t < taps; ++t) {
+            ptx::mbar_wait(r.full, r.ph);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+              if (ksteps == 4) {
+                ptx::umma_bf16(acc, dw, dx, idesc, accumulate);
+                ptx::umma_bf16_acc(acc, dw + 2, dx + 2, idesc);
+                ptx::umma_bf16_acc(acc, dw + 4, dx + 4, idesc);
+                ptx::umma_bf16_acc(acc, dw + 6, dx + 6, idesc);
+              } else {
+                for (int k = 0; k < ksteps; ++k) ptx::umma_bf16(acc, dw + 2 * k, dx + 2 * k, idesc, accumulate | k);
+              }
+              ptx::umma_commit(r.empty);
+            }
+            __syncwarp();
+            accumulate = 1;
+            dx += 8;  // next tap to the right: one 128-byte halo row further
+            if (++kx == a.ksize) {
+              kx = 0;
+              dx += row_skip;
+            }
+            if (++tap == taps) {  // rotated tap order wraps to the first tap
+              tap = 0;
+              dx = dx0;
+            }
+            dw += kWBytes >> 4;
+            if (r.advance()) dw = dw0;
+          }
+          if (ptx::elect_one()) ptx::umma_commit(bar_hempty + 8 * hb);  // refill allowed once these MMAs have retired
+          __syncwarp();
+          hb ^= 1;
+          if (hb == 0) hph ^= 1;
+        }
+        if (ptx::elect_one()) ptx::umma_commit(bar_acc_full + 8 * buf);
+        __syncwarp();
+        buf ^= 1;
+        if (buf == 0) buf_ph ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5): lane = output channel
+    const int q = warp & 3;
+    const int chl = q * 32 + lane;
+    uint32_t buf = 0, buf_ph = 0;
+    for (int w = blockIdx.x; w < a.work_items; w += gridDim.x) {
+      const int ct = w % a.n_tiles;
+      const int pt = w / a.n_tiles;
+      const int img = pt / tiles_per_img;
+      const int rr = pt - img * tiles_per_img;
+      const int ty = rr / a.tiles_x;
+      const int x0 = (rr - ty * a.tiles_x) * 8;
+      const int y0 = ty * a.bh;
+      const int ch = ct * 128 + chl;
+      const float bias = a.bias[ch];
+      const float slope = a.slope[ch];
+      const bool ch_ok = ch < a.cout_store;
+      __nv_bfloat16* const out = a.out_bf16 + ch;
+      ptx::mbar_wait(bar_acc_full + 8 * buf, buf_ph);
+      ptx::tc_fence_after();
+      const uint32_t acc = tmem_base + buf * 256u + (static_cast<uint32_t>(q * 32) << 16);
+      for (int c = 0; c < a.n_pix; c += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(acc + c, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {  // 4 image rows of 8 pixels per 32-column chunk
+          const int y = y0 + (c >> 3) + g;
+          if (c + 8 * g < a.n_pix && y < a.H && ch_ok) {
+            __nv_bfloat16* const row = out + (static_cast<long long>(img) * a.H + y) * a.W * a.out_pix_stride;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int x = x0 + i;
+              if (x < a.W) {
+                const float v0 = __uint_as_float(r[8 * g + i]) + bias;
+                row[static_cast<long long>(x) * a.out_pix_stride] = __float2bfloat16_rn(v0 > 0.f ? v0 : v0 * slope);
+              }
+            }
+          }
+        }
+      }
+      // this warp has finished reading the accumulator: hand it back to the MMA issuer
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar_acc_empty + 8 * buf);
+      buf ^= 1;
+      if (buf == 0) buf_ph ^= 1;
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ------------------------------------------------------------------ host side
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -827,6 +1154,103 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   a.cin_k16 = (d.in_c + 15) / 16;
   a.H = d.H;
   a.W = d.W;
+
+  // Automatic choice (measured, profiles/conv_test_v5_r1.log): every 3x3 / 7x7 layer with at least 64 input channels and
+  // more than 64 output channels runs fastest on v5 (7x7 128->128: 1419 TFLOP/s against 1277 for v4 and 1085 for v1 on a
+  // 92x164x8 grid, 1245 against 938 on 69x92x8; 3x3 256->256: 1358 against 1047). 1x1 layers, the float32 network heads,
+  // the 64-channel full-resolution layers and the 32-channel first layer stay on v1 / v2.
+  static const int env_no_v5 = getenv("ISLPOSE_NO_V5") != nullptr;  // A/B measurement aid
+  const bool auto_v5 = d.variant <= 0 && !env_no_v5 && d.ksize >= 3 && d.in_c >= 64 && d.cout > 64 && d.out_bf16 != nullptr &&
+                       d.out_f32 == nullptr && d.force_n_tile <= 0 && d.force_bw <= 0;
+  if (d.variant == 5 || auto_v5) {
+    // swapped operands + resident halo, persistent (see the kernel): 8 x th pixel tiles, th even, <= 32
+    if (d.ksize < 3) return fail(err, errlen, "conv: the halo variants need k > 1");
+    if (d.out_bf16 == nullptr || d.out_f32 != nullptr) return fail(err, errlen, "conv: v5 writes bf16 slices only");
+    const int kb5 = d.ksize * d.ksize * ((d.in_c + 63) / 64);
+    const int n_ct = (d.cout + 127) / 128;
+    int th = d.force_bh;
+    if (th <= 0) {
+      double best = -1;
+      for (int h = 2; h <= 32; h += 2) {
+        const long long tiles = static_cast<long long>((d.W + 7) / 8) * ((d.H + h - 1) / h) * d.N * n_ct;
+        // fitted to profiles/conv_test_v5_r1.log: 121 / 138 / 166 cycles per MMA at N = 128 / 192 / 256 (tensor pipe
+        // N/2 plus shared-memory contention with the weight stream), never below ~100 (issue rate of one warp)
+        const double fit = 76.0 + 2.8 * h;
+        const double per_mma = fit > 100.0 ? fit : 100.0;
+        const double cost = static_cast<double>((tiles + 147) / 148) * (kb5 * 4.0 * per_mma + 6000.0);
+        if (best < 0 || cost < best) {
+          best = cost;
+          th = h;
+        }
+      }
+    }
+    if (th < 2 || th > 32 || th % 2 != 0) return fail(err, errlen, "conv: v5 tile height must be even and <= 32, got %lld", th);
+    a.bw = 8;
+    a.bh = th;
+    a.tiles_x = (d.W + 7) / 8;
+    a.tiles_y = (d.H + th - 1) / th;
+    a.n_pix = 8 * th;
+    a.n_tile = 128;
+    a.n_tiles = n_ct;
+    a.m_tiles = a.tiles_x * a.tiles_y * d.N;
+    a.work_items = a.m_tiles * n_ct;
+    a.halo_w = 16;
+    a.halo_h = th + 2 * a.pad;
+    a.cout = d.cout;
+    a.cout_store = (d.cout + 7) / 8 * 8;
+    a.tmem_cols = 512;
+    a.b_stage_bytes = 128 * 128;
+    const uint32_t fixed = 2u * 2048u * a.halo_h + 1024u + 512u;
+    int stages = (d.force_stages > 0 && d.variant == 5) ? d.force_stages : static_cast<int>((227u * 1024u - fixed) / (128u * 128u));
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 2) return fail(err, errlen, "conv: v5 does not fit shared memory (halo %lld rows)", a.halo_h);
+    a.stages = stages;
+    a.tap_rot = 0;  // measured: no effect (the weight tiles are not an L2 hot spot); kept as a kernel option
+    out->smem_bytes = fixed + stages * 128u * 128u;
+    out->variant = 5;
+    a.out_bf16 = d.out_bf16;
+    a.out_pix_stride = d.out_cstride;
+    a.bias = d.bias;
+    a.slope = d.slope;
+    {
+      int c_dim = d.in_c;
+      const int c64 = (d.in_c + 63) / 64 * 64;
+      if (d.in_c_readable >= c64) c_dim = c64;
+      cuuint64_t gdim[4] = {static_cast<cuuint64_t>(c_dim), static_cast<cuuint64_t>(d.W), static_cast<cuuint64_t>(d.H),
+                            static_cast<cuuint64_t>(d.N)};
+      cuuint64_t gstr[3] = {static_cast<cuuint64_t>(d.in_cstride) * 2, static_cast<cuuint64_t>(d.in_cstride) * 2 * d.W,
+                            static_cast<cuuint64_t>(d.in_cstride) * 2 * d.W * d.H};
+      cuuint32_t box[4] = {64, 16, static_cast<cuuint32_t>(a.halo_h), 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      CUresult r = encode(&out->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(d.in), gdim, gstr,
+                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(err, errlen, "conv: activation tensor map rejected (CUresult %lld)", r);
+    }
+    {
+      const int w_cin = d.w_cin > 0 ? d.w_cin : d.in_c;
+      if (w_cin < d.in_c || w_cin % 8 != 0) return fail(err, errlen, "conv: bad weight Cin stride %lld", w_cin);
+      cuuint64_t gdim[3] = {static_cast<cuuint64_t>(w_cin), static_cast<cuuint64_t>(d.cout),
+                            static_cast<cuuint64_t>(d.ksize * d.ksize)};
+      cuuint64_t gstr[2] = {static_cast<cuuint64_t>(w_cin) * 2, static_cast<cuuint64_t>(w_cin) * 2 * d.cout};
+      cuuint32_t box[3] = {64, 128, 1};
+      cuuint32_t estr[3] = {1, 1, 1};
+      CUresult r = encode(&out->tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(d.w), gdim, gstr,
+                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(err, errlen, "conv: weight tensor map rejected (CUresult %lld)", r);
+    }
+    out->grid = dim3(static_cast<unsigned>(a.work_items < 148 ? a.work_items : 148), 1, 1);
+    out->flops = 2.0 * d.in_c * d.cout * d.ksize * d.ksize * static_cast<double>(d.H) * d.W * d.N;
+    static bool attr5 = false;
+    if (!attr5) {
+      if (cudaFuncSetAttribute(conv_umma_halo_swapped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
+          cudaSuccess)
+        return fail(err, errlen, "conv: cannot raise dynamic shared memory limit");
+      attr5 = true;
+    }
+    return 0;
+  }
 
   // Cost model fitted to the measurements in profiles/ (cycles per CTA): a tcgen05.mma of M=128 x N x K=16 costs about
   // 207 + N/2 when the CTA has its SM to itself and 192 + N when two CTAs share the SM; `epi` is the epilogue.
@@ -1050,6 +1474,8 @@ int conv_run(const ConvLaunch& l, cudaStream_t stream) {
     conv_umma_halo_kernel<<<l.grid, kThreads, l.smem_bytes, stream>>>(l.tmA, l.tmB, l.args);
   } else if (l.variant == 4) {
     conv_umma_swapped_kernel<<<l.grid, kThreads, l.smem_bytes, stream>>>(l.tmA, l.tmB, l.tmC, l.args);
+  } else if (l.variant == 5) {
+    conv_umma_halo_swapped_kernel<<<l.grid, kThreads, l.smem_bytes, stream>>>(l.tmA, l.tmB, l.args);
   } else {
     conv_umma_kernel<<<l.grid, kThreads, l.smem_bytes, stream>>>(l.tmA, l.tmB, l.args);
   }

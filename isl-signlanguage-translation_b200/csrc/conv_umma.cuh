@@ -83,6 +83,7 @@ struct ConvArgs {
   int debug_no_loads;
   int n_pix;       // v4: UMMA N = pixels per tile rounded up to 16
   int tma_store;   // v4: the bf16 tile leaves through shared memory + TMA store
+  int tap_rot;     // v5: CTAs start the tap loop at different taps
   __nv_bfloat16* out_bf16;
   long long out_pix_stride;
   float* out_f32;

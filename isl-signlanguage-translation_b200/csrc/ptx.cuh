@@ -46,9 +46,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug must surface as a trapped launch (an error the host sees), never
 // as a hung GPU. 2 s is three orders of magnitude above any legitimate wait in these kernels.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  // fast path: try_wait suspends the thread in hardware for a while, so a handful of attempts covers every
-  // legitimate wait; the (slow) global timer is only consulted after thousands of failed attempts
+// The slow path is a real function call: the issue loops of the conv kernels are executed by a single lane, whose
+// instruction latency is what limits the tensor pipe (build/mma_rate), so the common case - the barrier has already
+// completed - must cost one try_wait and one branch, nothing else.
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+  // try_wait suspends the thread in hardware for a while, so a handful of attempts covers every legitimate wait;
+  // the (slow) global timer is only consulted after thousands of failed attempts
   uint32_t spins = 0;
   uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
@@ -63,6 +66,45 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       }
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
+}
+
+// Position in a ring of `stages` slots, advanced without division: slot index, phase bit of the current lap and
+// the slot's two barrier addresses (full / empty arrays are 8-byte entries).
+struct RingPos {
+  uint32_t s, ph, full, empty;
+  uint32_t full0, empty0, stages;
+  __device__ __forceinline__ RingPos(uint32_t bar_full, uint32_t bar_empty, int n_stages)
+      : s(0), ph(0), full(bar_full), empty(bar_empty), full0(bar_full), empty0(bar_empty), stages(n_stages) {}
+  __device__ __forceinline__ bool advance() {  // true when the ring wrapped
+    ++s;
+    full += 8;
+    empty += 8;
+    if (s == stages) {
+      s = 0;
+      ph ^= 1;
+      full = full0;
+      empty = empty0;
+      return true;
+    }
+    return false;
+  }
+};
+
+// One lane of a fully converged warp (always the same one for a full mask). The issue loops of the conv kernels are
+// executed by the WHOLE warp with warp-uniform state and only the tcgen05 / TMA instructions themselves are
+// predicated on this: the compiler then keeps descriptors and barrier addresses in uniform registers instead of
+// re-broadcasting them from one lane's registers before every instruction (ELECT + 4 x R2UR + BRA.U.ANY each).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 // ---------------------------------------------------------------- TMA
@@ -126,6 +168,15 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Same with the accumulate flag fixed at 1 (no predicate set-up in the issue loop).
+__device__ __forceinline__ void umma_bf16_acc(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.eq.b32 p, 0, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc)
       : "memory");
 }
 // Arrives on the mbarrier once every tcgen05.mma issued so far by this thread has retired.
