@@ -158,7 +158,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="frames per step per rank (0 = workload default)")
-    ap.add_argument("--chunk", type=int, default=4, help="frames per pipeline stage inside a step (0 = no pipelining)")
+    ap.add_argument("--chunk", type=int, default=0, help="split a step into pipeline stages of this many frames (0 = one stage per step)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--weights", default="torch", choices=["torch", "he"], help="random-init distribution (he = noisy-map stress)")
@@ -207,43 +207,36 @@ def main():
     # ---- leg 1: device-resident inputs (value) ---------------------------------------------------------------
     total_steps = args.warmup + args.steps
     dev_frames = [torch.from_numpy(np.stack(frames_for(s))).cuda() for s in range(min(total_steps, 4))]
-    for s in range(args.warmup):
-        flush.zero_()
-        ex.batch_device(dev_frames[s % len(dev_frames)], hand_boxes)
+
+    def run_steps(batches_of, n_steps):
+        """K steps through the two-lane pipeline; returns (device ms between the brackets, results of the last step)."""
+        def feed():
+            for s in range(n_steps):
+                flush.zero_()   # evicts L2 between steps (the per-step working set is far larger than L2 anyway)
+                yield batches_of(s), hand_boxes
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        last = None
+        for res in ex.pipeline(feed()):
+            last = res
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1), last
+
+    run_steps(lambda s: dev_frames[s % len(dev_frames)], args.warmup)   # W untimed steps (both lanes get their buffers)
     sampler = ClockSampler(local)
     sampler.start()
-    barrier()
-    step_events = []
     launches0 = L.islpose_launch_count()
-    for s in range(args.steps):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        ex.batch_device(dev_frames[(args.warmup + s) % len(dev_frames)], hand_boxes)
-        e1.record()
-        step_events.append((e0, e1))
-    barrier()
+    dev_ms, _ = run_steps(lambda s: dev_frames[(args.warmup + s) % len(dev_frames)], args.steps)
     gpu_launches = L.islpose_launch_count() - launches0
     sampler.stop_flag = True
-    dev_ms = sum(a.elapsed_time(b) for a, b in step_events)
 
     # ---- leg 2: host API end to end (e2e) ------------------------------------------------------------------
     host_frames = [frames_for(1000 + s) for s in range(min(args.steps, 4))]
-    for s in range(2):
-        ex.batch(host_frames[s % len(host_frames)], hand_boxes)
-    barrier()
-    e2e_events = []
-    d2h = 0
-    for s in range(args.steps):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        res = ex.batch(host_frames[s % len(host_frames)], hand_boxes)
-        e1.record()
-        e2e_events.append((e0, e1))
-        d2h = sum(c.nbytes + sb.nbytes + sum(p.nbytes for p in hp) for c, sb, hp in res)
-    barrier()
-    e2e_ms = sum(a.elapsed_time(b) for a, b in e2e_events)
+    run_steps(lambda s: host_frames[s % len(host_frames)], 2)
+    e2e_ms, res = run_steps(lambda s: host_frames[s % len(host_frames)], args.steps)
+    d2h = sum(c.nbytes + sb.nbytes + sum(p.nbytes for p in hp) for c, sb, hp in res)
     h2d = B * H * W * 3   # hand crops are cut from the device copy of the frame
 
     # ---- leg 3: the convolution plans of one step on their own (roofline of the tcgen05 kernels) -------------
@@ -353,9 +346,9 @@ def main():
             "config": {"workload": workload_name(args.workload, B), "weights": "seeded random init, %s (no trained weights ship with the reference)" % (
                            "nn.Conv2d default distribution" if WEIGHT_INIT == "torch" else "He-uniform (noisy maps: thousands of peaks)"),
                        "l2": "flushed with a 256 MiB write before every timed step",
-                       "timing": "CUDA events on the launching stream per step, summed; max over ranks",
-                       "pipeline": "%s-frame chunks on two lanes inside a step (post-processing of one chunk under the "
-                                   "convolutions of the next)" % (args.chunk or B),
+                       "timing": "CUDA events on the launching stream around the K steps; max over ranks",
+                       "pipeline": "steps run through KeypointExtractor.pipeline(): two lanes, the post-processing and copies of "
+                                   "one step overlap the convolutions of the next; all K steps start and end inside the timed region",
                        "single_frame_latency_ms": round(single_ms, 2)},
             "clocks": sampler.summary(),
             "e2e": {"value": frames_total / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h)},

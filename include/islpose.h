@@ -63,6 +63,12 @@ int islpose_plan_add_maxpool2x2(islpose_plan* plan, const void* in, void* out, i
 /* fp32 NCHW [n,3,h,w] network input -> bf16 [n,h,w,32] rows of the first layer's 3x3x3 patches (27 + 5 zeros) */
 int islpose_plan_add_im2col3x3(islpose_plan* plan, const float* in_nchw, void* out_nhwc32, int32_t n, int32_t h, int32_t w);
 int islpose_plan_run(const islpose_plan* plan, void* stream);
+/* Measurement aid: runs the plan launch by launch, each one `reps` times back to back between two CUDA events (after
+ * one untimed run), and blocks until done. h_ms / h_flops / h_variant (HOST arrays of num_launches entries; the last
+ * two may be NULL) receive the average milliseconds, the algorithmic FLOPs (0 for non-conv launches) and the conv
+ * kernel variant (-1 max-pool, -2 first-layer gather) of every launch. */
+int islpose_plan_profile(const islpose_plan* plan, void* stream, int32_t reps, float* h_ms, double* h_flops,
+                         int32_t* h_variant);
 int32_t islpose_plan_num_launches(const islpose_plan* plan);
 double islpose_plan_conv_flops(const islpose_plan* plan); /* sum of 2*Cin*Cout*k*k*H*W*N over the slices as given */
 

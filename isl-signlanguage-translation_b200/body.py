@@ -223,14 +223,14 @@ class Body(object):
         """Peaks, PAF scoring and grouping from the per-scale network outputs -> list of (candidate, subset)."""
         return self.post_finish(self.post_enqueue(maps, n, H, W, ws))
 
-    def upload(self, frames):
-        """Host frames -> this call's device staging buffer [n,H,W,3] (through pinned memory)."""
+    def upload(self, frames, lane=0):
+        """Host frames -> this call's device staging buffer [n,H,W,3] (through pinned memory; one buffer per lane)."""
         frames = [np.asarray(f) for f in frames]
         H, W = frames[0].shape[:2]
         for f in frames:
             if f.shape != (H, W, 3) or f.dtype != np.uint8:
                 raise ValueError("Body.batch needs uint8 [H,W,3] frames of one size, got %s %s" % (f.shape, f.dtype))
-        key = (len(frames), H, W)
+        key = (len(frames), H, W, lane)
         stage = self._staging.get(key)
         if stage is None:
             stage = (torch.empty((len(frames), H, W, 3), dtype=torch.uint8).pin_memory(),

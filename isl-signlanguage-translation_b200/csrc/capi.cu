@@ -206,6 +206,37 @@ int islpose_plan_run(const islpose_plan* plan, void* stream) {
   return 0;
 }
 
+int islpose_plan_profile(const islpose_plan* plan, void* stream, int32_t reps, float* h_ms, double* h_flops,
+                         int32_t* h_variant) {
+  if (plan == nullptr || h_ms == nullptr || reps <= 0) return set_err("plan_profile: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaEvent_t e0, e1;
+  if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return set_err("plan_profile: no events");
+  int rc = 0;
+  for (size_t i = 0; i < plan->ops.size() && rc == 0; ++i) {
+    const Op& op = plan->ops[i];
+    // every launch is timed on its own, after all earlier launches of the plan have run once (valid inputs)
+    for (int r = -1; r < reps && rc == 0; ++r) {
+      if (r == 0) cudaEventRecord(e0, st);
+      if (op.kind == kConv) rc = conv_run(op.conv, st);
+      else if (op.kind == kPool) rc = launch_maxpool2x2(op.in, op.n, op.h, op.w, op.c, op.out, st);
+      else rc = launch_im2col3x3(static_cast<const float*>(op.in), op.n, op.h, op.w, op.out, st);
+    }
+    cudaEventRecord(e1, st);
+    if (cudaEventSynchronize(e1) != cudaSuccess) rc = 1;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    h_ms[i] = ms / reps;
+    if (h_flops != nullptr) h_flops[i] = op.kind == kConv ? op.conv.flops : 0.0;
+    if (h_variant != nullptr) h_variant[i] = op.kind == kConv ? op.conv.variant : (op.kind == kPool ? -1 : -2);
+    g_launches.fetch_add(reps + 1, std::memory_order_relaxed);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (rc != 0) return check_cuda("plan_profile") ? 1 : set_err("plan_profile: a launch failed");
+  return 0;
+}
+
 int32_t islpose_plan_num_launches(const islpose_plan* plan) { return plan ? static_cast<int32_t>(plan->ops.size()) : 0; }
 double islpose_plan_conv_flops(const islpose_plan* plan) { return plan ? plan->flops : 0.0; }
 

@@ -76,64 +76,84 @@ class KeypointExtractor(object):
 
     def batch_device(self, frames_dev, hand_boxes, chunk=None):
         """Same as batch() for frames already resident on the device (uint8 cuda tensor [n,H,W,3]). hand_boxes=None
-        runs util.handDetect on every frame's (candidate, subset) as the reference loop does.
-
-        The batch is processed as a software pipeline over chunks of `chunk` frames on two lanes (independent
-        buffers and streams): while the host waits for the body results of chunk i (it needs them for
-        util.handDetect), the body networks of chunk i+1 are already queued, and the hand networks of chunk i
-        are queued before the host waits for chunk i+1. The memory- and latency-bound stages (map accumulation,
-        peaks, grouping, hand key points, the D2H copies) therefore run under the tensor-bound convolutions of
-        the neighbouring chunks. The per-frame dependency body -> handDetect -> hand is unchanged."""
-        import torch
-
+        runs util.handDetect on every frame's (candidate, subset) as the reference loop does. With `chunk` (or
+        self.chunk) set, the batch runs through pipeline() in chunks of that many frames."""
         n = int(frames_dev.shape[0])
         chunk = int(chunk or self.chunk or n)
         if not hasattr(self.body, "enqueue") or n <= chunk:
             return self._batch_device_serial(frames_dev, hand_boxes)
-        bounds = [(a, min(a + chunk, n)) for a in range(0, n, chunk)]
+        parts = [(frames_dev[a:a + chunk], None if hand_boxes is None else hand_boxes[a:a + chunk]) for a in range(0, n, chunk)]
+        out = []
+        for res in self.pipeline(parts):
+            out.extend(res)
+        return out
+
+    def pipeline(self, batches):
+        """Software pipeline over a sequence of batches: yields the result list of every batch, in order.
+
+        batches: iterable of (frames, hand_boxes); frames is a uint8 cuda tensor [n,H,W,3] or a list of numpy frames
+        (uploaded through pinned memory), hand_boxes a per-frame list of boxes or None (= util.handDetect).
+
+        Two lanes (independent buffers and streams) alternate: while the host waits for the body results of batch i
+        (it needs them for util.handDetect), the body networks of batch i+1 are already queued, and the hand networks
+        of batch i are queued before the host waits for batch i+1. The memory- and latency-bound stages (map
+        accumulation, peaks, grouping, hand key points, the copies in both directions) therefore run under the
+        tensor-bound convolutions of the neighbouring batches. The per-frame dependency body -> handDetect -> hand
+        is unchanged, and so are the results."""
+        import torch
+
         lanes = self._lane_streams(torch)
         main = torch.cuda.current_stream()
-        ready = torch.cuda.Event()
-        ready.record(main)
+        it = iter(batches)
 
-        def start_body(ci):
-            a, b = bounds[ci]
-            st = lanes[ci % 2]
+        def start_body(idx):
+            try:
+                frames, boxes = next(it)
+            except StopIteration:
+                return None
+            if not torch.is_tensor(frames):
+                frames = self.body.upload(frames, lane=idx % 2)
+            ready = torch.cuda.Event()
+            ready.record(main)
+            st = lanes[idx % 2]
             with torch.cuda.stream(st):
                 st.wait_event(ready)
-                return self.body.enqueue(frames_dev[a:b], lane=ci % 2)
+                ticket = self.body.enqueue(frames, lane=idx % 2)
+            return frames, boxes, ticket, ready
 
-        results = [None] * n
-        hand_tickets = []
-        nxt = start_body(0)
-        for ci, (a, b) in enumerate(bounds):
-            cur = nxt
-            nxt = start_body(ci + 1) if ci + 1 < len(bounds) else None
-            bodies = self.body.finish(cur)
-            for k, r in enumerate(bodies):
-                results[a + k] = r
+        def finish_hand(pending):
+            bodies, owner, ticket = pending
             if self.hand is None:
-                continue
-            crops, owner = [], []
-            st = lanes[2 + ci % 2]
-            with torch.cuda.stream(st):
-                st.wait_event(ready)
-                for fi in range(a, b):
-                    cand, sub = results[fi]
-                    boxes = hand_boxes[fi] if hand_boxes is not None else util.handDetect(cand, sub, frames_dev[fi])
-                    for (x, y, w, is_left) in boxes:
-                        crops.append(frames_dev[fi, y:y + w, x:x + w, :].contiguous())
-                        owner.append((fi, x, y))
-                hand_tickets.append((owner, self.hand.enqueue(crops, lane=ci % 2) if crops else None))
-        if self.hand is None:
-            return [(c, s, []) for c, s in results]
-        owners, peaks = [], []
-        for owner, t in hand_tickets:
-            owners.extend(owner)
-            peaks.extend(self.hand.finish(t))
+                return [(c, s, []) for c, s in bodies]
+            return self._assemble(bodies, owner, self.hand.finish(ticket))
+
+        idx = 0
+        pending = None
+        nxt = start_body(0)
+        while nxt is not None:
+            frames, boxes, ticket, ready = nxt
+            nxt = start_body(idx + 1)
+            bodies = self.body.finish(ticket)
+            owner, hticket = [], None
+            if self.hand is not None:
+                crops = []
+                st = lanes[2 + idx % 2]
+                with torch.cuda.stream(st):
+                    st.wait_event(ready)
+                    for fi, (cand, sub) in enumerate(bodies):
+                        fb = boxes[fi] if boxes is not None else util.handDetect(cand, sub, frames[fi])
+                        for (x, y, w, is_left) in fb:
+                            crops.append(frames[fi, y:y + w, x:x + w, :].contiguous())
+                            owner.append((fi, x, y))
+                    hticket = self.hand.enqueue(crops, lane=idx % 2) if crops else None
+            if pending is not None:
+                yield finish_hand(pending)
+            pending = (bodies, owner, hticket)
+            idx += 1
+        if pending is not None:
+            yield finish_hand(pending)
         for st in lanes:
             main.wait_stream(st)
-        return self._assemble(results, owners, peaks)
 
     def _lane_streams(self, torch):
         if self._lanes is None:

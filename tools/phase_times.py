@@ -107,6 +107,8 @@ def main():
     counts = ws["counts"].cpu().numpy().reshape(nb, parts)
     print("   peaks per frame: %s" % counts.sum(axis=1).tolist())
 
+    body.post_finish(body.post_enqueue(maps, nb, H, W, ws))   # allocates the result staging buffers
+
     def group():
         body._group(maps, nb, H, W, ws)
     try:
