@@ -356,6 +356,7 @@ static int run_v4_suite() {
   return 0;
 }
 
+static int g_only = -1;  // conv_test <suite> <index>: run one configuration of a suite (profiling)
 static int run_v5_suite() {
   // swapped operands + resident halo, persistent: correctness on awkward shapes first, then timings against v1 / v4
   const Cfg cfgs[] = {
@@ -402,7 +403,9 @@ static int run_v5_suite() {
       {"v1 7x7 128->128 23x31 b2", 2, 23, 31, 128, 128, 0, 128, 7, false, true, 0, 0, 1, 0, 0, 0, 0},
   };
   int fails = 0;
+  int index = -1;
   for (const Cfg& c : cfgs) {
+    if (g_only >= 0 && ++index != g_only) continue;
     const int r = run_cfg(c, true);
     if (r == 3) {
       printf("context lost, stopping\n");
@@ -473,6 +476,7 @@ int main(int argc, char** argv) {
   if (argc > 1 && std::string(argv[1]) == "v3") return run_v3_suite();
   if (argc > 1 && std::string(argv[1]) == "limits") return run_limits_suite();
   if (argc > 1 && std::string(argv[1]) == "v4") return run_v4_suite();
+  if (argc > 2) g_only = atoi(argv[2]);
   if (argc > 1 && std::string(argv[1]) == "v5") return run_v5_suite();
   int fails = 0;
   for (int i = 0; i < n; ++i) {
