@@ -254,7 +254,7 @@ int islpose_resize_pad_normalize(const uint8_t* frames, int32_t n, int32_t H, in
 int64_t islpose_maps_workspace_floats(const islpose_scale* scales, int32_t n_scales, int32_t n, int32_t parts) {
   int64_t total = 0;
   if (scales == nullptr) return 0;
-  for (int s = 0; s < n_scales; ++s) total += static_cast<int64_t>(n) * parts * scales[s].hc * scales[s].wc;
+  for (int s = 0; s < n_scales; ++s) total += static_cast<int64_t>(n) * parts * scales[s].hc * ((scales[s].wc + 3) / 4 * 4);
   return total;
 }
 

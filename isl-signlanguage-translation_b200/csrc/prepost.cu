@@ -173,94 +173,192 @@ heat_accumulate_kernel(const ScaleSet ss, int N, int H, int W, int parts, int q1
   }
 }
 
-// Two-pass variant of the same arithmetic (bit-identical results, ~8x fewer multiply-adds): pass 1 materialises
-// stage 1 - the x8 up-sampled, cropped map of one scale, float32 [N][parts][hc][wc] - with 20 multiply-adds per
-// up-sampled pixel; pass 2 is stage 2 (4x4 taps from that map) plus the division and the float64 accumulation.
+// Two-pass variant of the same arithmetic (bit-identical results): pass 1 materialises stage 1 - the x8 up-sampled,
+// cropped map of one scale, float32 [N][parts][hc][wc]; pass 2 is stage 2 (4x4 taps from that map) plus the division
+// and the float64 accumulation. Both passes were instruction-issue bound in their first form (one thread per value:
+// ~130 / ~174 warp instructions per value, mostly index arithmetic, profiles/r1_ncu_full_post.txt), so both now share
+// work between neighbouring values instead:
+//   pass 1: one thread = one 8 x 8 block of up-sampled values. Up-sampled columns 8b-4 .. 8b+3 read the same four
+//           source columns (and rows likewise), so the block needs ONE 4 x 4 source window, 32 horizontal dot
+//           products (4 source rows x 8 columns) and 64 vertical ones: 10.5 multiply-adds per value instead of 35,
+//           and no per-value index arithmetic. The weights of column/row i of a block are phase (i+4)&7, a constant.
+//   pass 2: one CTA = one 32 x 32 tile of the frame. Per (scale, channel) the horizontal dot products of every
+//           source row the tile needs (<= 37) go through shared memory and are shared by the rows that use them;
+//           cubic coefficients and tap indices are computed once per thread and scale, not per value.
 __global__ void __launch_bounds__(256)
-upsample8_kernel(const float* __restrict__ low, int C, int parts, int gh, int gw, int hc, int wc,
+upsample8_kernel(const float* __restrict__ low, int C, int parts, int gh, int gw, int hc, int wc, int pitch,
                  float* __restrict__ mid) {
   __shared__ float s_tab[8][4];
   fill_phase_table(s_tab);
   __syncthreads();
-  const int u = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int v = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int bx = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int by = blockIdx.y * 8 + (threadIdx.x >> 5);
   const int n = blockIdx.z / parts;
   const int c = blockIdx.z - n * parts;
-  if (u >= wc || v >= hc) return;
-  const int su = ((u + 4) >> 3) - 2, sv = ((v + 4) >> 3) - 2;  // first tap = floor(src) - 1
-  const float* wx = s_tab[u & 7];
-  const float* wy = s_tab[v & 7];
-  const float wxr[4] = {wx[0], wx[1], wx[2], wx[3]};
-  const float wyr[4] = {wy[0], wy[1], wy[2], wy[3]};
+  const int u0 = 8 * bx - 4, v0 = 8 * by - 4;
+  if (u0 >= wc || v0 >= hc) return;
   const float* plane = low + (static_cast<long long>(n) * C + c) * gh * gw;
-  int cx[4];
-#pragma unroll
-  for (int m = 0; m < 4; ++m) cx[m] = clampi(su + m, 0, gw - 1);
-  float t1[4];
+  // the 4 x 4 source window: first tap = floor(src) - 1 = b - 2, replicate border
+  float L[4][4];
 #pragma unroll
   for (int l = 0; l < 4; ++l) {
-    const float* row = plane + static_cast<long long>(clampi(sv + l, 0, gh - 1)) * gw;
-    t1[l] = dot4_lr(__ldg(row + cx[0]), __ldg(row + cx[1]), __ldg(row + cx[2]), __ldg(row + cx[3]), wxr);
+    const float* row = plane + clampi(by - 2 + l, 0, gh - 1) * gw;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) L[l][m] = __ldg(row + clampi(bx - 2 + m, 0, gw - 1));
   }
-  mid[((static_cast<long long>(n) * parts + c) * hc + v) * wc + u] = dot4_rl(t1[0], t1[1], t1[2], t1[3], wyr);
-}
-
-struct MidSet {
-  const float* mid[kMaxScales];  // [N][parts][hc][wc] per scale
-};
-
-__global__ void __launch_bounds__(256)
-resize_accumulate_kernel(const ScaleSet ss, const MidSet ms, int N, int H, int W, int parts, int q1,
-                         double* __restrict__ out) {
-  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
-  const int chunks = (parts + kChunk - 1) / kChunk;
-  const int n = blockIdx.z / chunks;
-  const int c0 = (blockIdx.z % chunks) * kChunk;
-  if (x >= W || y >= H) return;
-  double acc[kChunk];
+  float w[8][4];  // weights of block column / row i: phase (i + 4) & 7
 #pragma unroll
-  for (int i = 0; i < kChunk; ++i) acc[i] = 0.0;
-  const int C = ss.channels;
-  const long long tail_start = (static_cast<long long>(W) * C) / 4 * 4;
-  const float fS = static_cast<float>(ss.count);
-  for (int s = 0; s < ss.count; ++s) {
-    const ScaleGeom& g = ss.g[s];
-    int sx, sy;
-    float fx, fy, wx[4], wy[4];
-    cubic_src(x, g.sx, sx, fx);
-    cubic_coeffs(fx, wx);
-    cubic_src(y, g.sy, sy, fy);
-    cubic_coeffs(fy, wy);
-    int xi[4], yi[4];
+  for (int i = 0; i < 8; ++i) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      xi[k] = clampi(sx - 1 + k, 0, g.wc - 1);
-      yi[k] = clampi(sy - 1 + k, 0, g.hc - 1);
-    }
-    const long long plane = static_cast<long long>(g.hc) * g.wc;
+    for (int k = 0; k < 4; ++k) w[i][k] = s_tab[(i + 4) & 7][k];
+  }
+  float T1[4][8];
 #pragma unroll
-    for (int i = 0; i < kChunk; ++i) {
-      const int c = c0 + i;
-      if (c < parts) {
-        const float* img = ms.mid[s] + (static_cast<long long>(n) * parts + c) * plane;
-        float t2[4];
+  for (int l = 0; l < 4; ++l) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float* row = img + static_cast<long long>(yi[j]) * g.wc;
-          t2[j] = dot4_lr(__ldg(row + xi[0]), __ldg(row + xi[1]), __ldg(row + xi[2]), __ldg(row + xi[3]), wx);
-        }
-        const bool tail = static_cast<long long>(x) * C + c >= tail_start;
-        const float v = tail ? dot4_lr(t2[0], t2[1], t2[2], t2[3], wy) : dot4_rl(t2[0], t2[1], t2[2], t2[3], wy);
-        const double t = static_cast<double>(__fdiv_rn(v, fS));
-        acc[i] = q1 ? __dadd_rn(acc[i], __dadd_rn(acc[i], t)) : __dadd_rn(acc[i], t);
+    for (int i = 0; i < 8; ++i) T1[l][i] = dot4_lr(L[l][0], L[l][1], L[l][2], L[l][3], w[i]);
+  }
+  // rows of `mid` are `pitch` floats apart (wc rounded up to 4), so both halves of a block row are 16-byte aligned;
+  // the pad columns may receive values, nobody reads them
+  float* out = mid + (static_cast<long long>(n) * parts + c) * hc * pitch;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int v = v0 + j;
+    if (v < 0 || v >= hc) continue;
+    float* orow = out + static_cast<long long>(v) * pitch;
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = dot4_rl(T1[0][i], T1[1][i], T1[2][i], T1[3][i], w[j]);
+    if (u0 >= 0) *reinterpret_cast<float4*>(orow + u0) = make_float4(o[0], o[1], o[2], o[3]);  // u0 + 3 < wc holds: u0 < wc, both = 0 mod 4 ... see launcher
+    if (u0 + 7 < pitch) {
+      *reinterpret_cast<float4*>(orow + u0 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    } else {
+#pragma unroll
+      for (int i = 4; i < 8; ++i) {
+        if (u0 + i < wc) orow[u0 + i] = o[i];
       }
     }
   }
+}
+
+struct MidSet {
+  const float* mid[kMaxScales];  // [N][parts][hc][pitch] per scale
+  int pitch[kMaxScales];         // wc rounded up to a multiple of 4 floats
+};
+
+constexpr int kRT = 32;        // frame tile edge of pass 2
+constexpr int kRMaxRows = 180; // source rows a tile may need: 32 * (hc / H) + 4; 2 x 180 x 33 floats = 47.5 KB of shared memory
+constexpr int kRChunk = 5;     // channels per CTA (accumulators stay in registers)
+
+__global__ void __launch_bounds__(256, 2)
+resize_accumulate_kernel(const ScaleSet ss, const MidSet ms, int N, int H, int W, int parts, int q1, int rows_cap,
+                         double* __restrict__ out) {
+  extern __shared__ float s_dyn[];  // [2][rows_cap][kRT + 1]
+  float (*s_t0)[kRT + 1] = reinterpret_cast<float (*)[kRT + 1]>(s_dyn);
+  float (*s_t1)[kRT + 1] = s_t0 + rows_cap;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int x = blockIdx.x * kRT + tx;
+  const int xc = x < W ? x : W - 1;  // threads beyond the frame compute a valid column and store nothing
+  const int y0 = blockIdx.y * kRT;
+  const int chunks = (parts + kRChunk - 1) / kRChunk;
+  const int n = blockIdx.z / chunks;
+  const int c0 = (blockIdx.z - n * chunks) * kRChunk;
+  const int nch = parts - c0 < kRChunk ? parts - c0 : kRChunk;
+  double acc[4][kRChunk];
 #pragma unroll
-  for (int i = 0; i < kChunk; ++i) {
-    const int c = c0 + i;
-    if (c < parts) out[((static_cast<long long>(n) * parts + c) * H + y) * W + x] = acc[i];
+  for (int k = 0; k < 4; ++k) {
+#pragma unroll
+    for (int i = 0; i < kRChunk; ++i) acc[k][i] = 0.0;
+  }
+  const int C = ss.channels;
+  const long long tail_start = (static_cast<long long>(W) * C) / 4 * 4;
+  const float fS = static_cast<float>(ss.count);
+  int buf = 0;
+  for (int s = 0; s < ss.count; ++s) {
+    const ScaleGeom& g = ss.g[s];
+    // this thread's column: stage-2 taps and weights (once per scale)
+    int sx;
+    float fx, wx[4];
+    cubic_src(xc, g.sx, sx, fx);
+    cubic_coeffs(fx, wx);
+    int xi[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) xi[k] = clampi(sx - 1 + k, 0, g.wc - 1);
+    // source rows of the tile: first tap of the first row .. last tap of the last row (clamped, monotonic in y)
+    int sy_first, sy_last;
+    float fdummy;
+    cubic_src(y0, g.sy, sy_first, fdummy);
+    const int y_last = y0 + kRT - 1 < H ? y0 + kRT - 1 : H - 1;
+    cubic_src(y_last, g.sy, sy_last, fdummy);
+    const int r_lo = clampi(sy_first - 1, 0, g.hc - 1);
+    const int r_hi = clampi(sy_last + 2, 0, g.hc - 1);
+    const int nrows = r_hi - r_lo + 1;  // <= rows_cap (sized by the launcher)
+    // this thread's four rows: weights and offsets into the shared rows
+    float wy[4][4];
+    int sy4[4];  // first tap row (unclamped) of this thread's four rows
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int y = y0 + ty + 8 * k;
+      const int yc = y < H ? y : H - 1;
+      int sy;
+      float fy;
+      cubic_src(yc, g.sy, sy, fy);
+      cubic_coeffs(fy, wy[k]);
+      sy4[k] = sy - 1;
+    }
+    const int hc1 = g.hc - 1;
+    const int pitch = ms.pitch[s];
+    const long long plane = static_cast<long long>(g.hc) * pitch;
+    // v / S in float32 (body.py:80-81): for a power of two the multiplication by 1/S gives the identical result
+    const bool pow2 = (ss.count & (ss.count - 1)) == 0;
+    const float rS = 1.0f / fS;
+#pragma unroll
+    for (int i = 0; i < kRChunk; ++i) {
+      if (i < nch) {
+        const int c = c0 + i;
+        const float* img = ms.mid[s] + (static_cast<long long>(n) * parts + c) * plane + static_cast<long long>(r_lo) * pitch;
+        float (*s_t)[kRT + 1] = buf ? s_t1 : s_t0;
+        // horizontal pass: one dot product per (source row, column); rows strided over the 8 warps, five rows (20
+        // independent loads) in flight per thread
+        for (int rb = ty; rb < nrows; rb += 40) {
+          float v[5][4];
+#pragma unroll
+          for (int m = 0; m < 5; ++m) {
+            const int r = rb + 8 * m < nrows ? rb + 8 * m : nrows - 1;
+            const float* row = img + static_cast<long long>(r) * pitch;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[m][k] = __ldg(row + xi[k]);
+          }
+#pragma unroll
+          for (int m = 0; m < 5; ++m) {
+            if (rb + 8 * m < nrows) s_t[rb + 8 * m][tx] = dot4_lr(v[m][0], v[m][1], v[m][2], v[m][3], wx);
+          }
+        }
+        __syncthreads();
+        const bool tail = static_cast<long long>(xc) * C + c >= tail_start;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float t0 = s_t[clampi(sy4[k], 0, hc1) - r_lo][tx], t1 = s_t[clampi(sy4[k] + 1, 0, hc1) - r_lo][tx],
+                      t2 = s_t[clampi(sy4[k] + 2, 0, hc1) - r_lo][tx], t3 = s_t[clampi(sy4[k] + 3, 0, hc1) - r_lo][tx];
+          const float v = tail ? dot4_lr(t0, t1, t2, t3, wy[k]) : dot4_rl(t0, t1, t2, t3, wy[k]);
+          const double t = static_cast<double>(pow2 ? __fmul_rn(v, rS) : __fdiv_rn(v, fS));
+          acc[k][i] = q1 ? __dadd_rn(acc[k][i], __dadd_rn(acc[k][i], t)) : __dadd_rn(acc[k][i], t);
+        }
+        buf ^= 1;  // the next horizontal pass writes the other buffer: one barrier per (scale, channel)
+      }
+    }
+  }
+  if (x < W) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int y = y0 + ty + 8 * k;
+      if (y < H) {
+#pragma unroll
+        for (int i = 0; i < kRChunk; ++i) {
+          if (i < nch) out[((static_cast<long long>(n) * parts + c0 + i) * H + y) * W + x] = acc[k][i];
+        }
+      }
+    }
   }
 }
 
@@ -520,7 +618,7 @@ int launch_maxpool2x2(const void* in, int N, int H, int W, int C, void* out, cud
 
 long long heat_accumulate_workspace_floats(const ScaleSet& ss, int N, int parts) {
   long long total = 0;
-  for (int s = 0; s < ss.count; ++s) total += static_cast<long long>(N) * parts * ss.g[s].hc * ss.g[s].wc;
+  for (int s = 0; s < ss.count; ++s) total += static_cast<long long>(N) * parts * ss.g[s].hc * ((ss.g[s].wc + 3) / 4 * 4);
   return total;
 }
 
@@ -534,14 +632,30 @@ int launch_heat_accumulate(const ScaleSet& ss, int N, int H, int W, int parts, i
   }
   MidSet ms;
   float* cursor = workspace;
+  int rows_cap = 8;
+  for (int s = 0; s < ss.count; ++s) {
+    const ScaleGeom& g = ss.g[s];
+    // a 32-row frame tile must find its source rows in the shared rows: 32 * hc / H + 4 (+1 for rounding)
+    const int need = static_cast<int>(32.0 * g.hc / H) + 6;
+    if (need > rows_cap) rows_cap = need;
+  }
+  if (rows_cap > kRMaxRows) {
+    heat_accumulate_kernel<<<grid, 256, 0, st>>>(ss, N, H, W, parts, q1, out);  // very strong down-scaling: single pass
+    return ISL_LAUNCH_OK();
+  }
   for (int s = 0; s < ss.count; ++s) {
     const ScaleGeom& g = ss.g[s];
     ms.mid[s] = cursor;
-    const dim3 g1((g.wc + 31) / 32, (g.hc + 7) / 8, N * parts);
-    upsample8_kernel<<<g1, 256, 0, st>>>(g.low, ss.channels, parts, g.gh, g.gw, g.hc, g.wc, cursor);
-    cursor += static_cast<long long>(N) * parts * g.hc * g.wc;
+    ms.pitch[s] = (g.wc + 3) / 4 * 4;
+    const int nbx = (g.wc + 4 + 7) / 8, nby = (g.hc + 4 + 7) / 8;  // 8 x 8 blocks with origin (8b - 4, 8b - 4)
+    const dim3 g1((nbx + 31) / 32, (nby + 7) / 8, N * parts);
+    upsample8_kernel<<<g1, 256, 0, st>>>(g.low, ss.channels, parts, g.gh, g.gw, g.hc, g.wc, ms.pitch[s], cursor);
+    cursor += static_cast<long long>(N) * parts * g.hc * ms.pitch[s];
   }
-  resize_accumulate_kernel<<<grid, 256, 0, st>>>(ss, ms, N, H, W, parts, q1, out);
+  const int rchunks = (parts + kRChunk - 1) / kRChunk;
+  const dim3 g2((W + kRT - 1) / kRT, (H + kRT - 1) / kRT, N * rchunks);
+  const size_t smem = sizeof(float) * 2 * rows_cap * (kRT + 1);
+  resize_accumulate_kernel<<<g2, 256, smem, st>>>(ss, ms, N, H, W, parts, q1, rows_cap, out);
   return ISL_LAUNCH_OK();
 }
 
