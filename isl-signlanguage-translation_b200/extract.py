@@ -176,6 +176,18 @@ class KeypointExtractor(object):
         peaks = self.hand.batch_device(crops) if crops else []
         return self._assemble(bodies, owner, peaks)
 
+    def features(self, frames, batch_size=8):
+        """Clip -> float64 [T,156]: the per-frame feature vectors of demo_isl_translate.py's loop (features.py),
+        frames processed in batches through pipeline()."""
+        from . import features as F
+
+        frames = list(frames)
+        mt = getattr(self.body, "model_type", "coco")
+        batches = [(frames[a:a + batch_size], None) for a in range(0, len(frames), batch_size)]
+        runner = self.pipeline(batches) if hasattr(self.body, "enqueue") else (self.batch(b) for b, _ in batches)
+        rows = [F.frame_features(c, s, hp, mt) for res in runner for (c, s, hp) in res]
+        return np.stack(rows) if rows else np.zeros((0, F.N_FEATURES))
+
     def run_sharded(self, frames, rank, world_size, batch_size=8, hand_boxes=None):
         """Processes this rank's shard of `frames` in batches; returns results in shard order."""
         idx = shard_indices(len(frames), rank, world_size)

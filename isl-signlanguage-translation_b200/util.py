@@ -82,3 +82,7 @@ def gaussian_weights(sigma=3.0, truncate=4.0):
     x = np.arange(-radius, radius + 1)
     phi = np.exp(-0.5 / (sigma * sigma) * x ** 2)
     return phi / phi.sum()
+
+
+# feature-vector helpers the reference keeps in util (src/util.py:99-151,187-219)
+from .features import get_bodypose, get_handpose  # noqa: E402,F401

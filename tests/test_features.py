@@ -1,0 +1,64 @@
+"""Feature-vector step against golden vectors produced by the unmodified reference functions
+(tests/golden/make_golden_features.py). Exact equality: the step is index and float64 copy work plus atan2 / sqrt
+on a handful of values, evaluated by the same numpy / math calls as the reference."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import isl_b200  # noqa: F401
+from isl_b200 import features as F
+from isl_b200.extract import KeypointExtractor
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+G = np.load(os.path.join(GOLD, "features.npz"))
+CASES = sorted(set(k.split("/")[0] for k in G.files))
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_features_match_reference(case):
+    d = np.load(os.path.join(GOLD, "body_%s.npz" % case), allow_pickle=True)
+    mt = str(d["model_type"])
+    hands = [h for h in G[case + "/hands"]]
+    circles, sticks = F.get_bodypose(d["candidate"], d["subset"], mt)
+    edges, peaks = F.get_handpose(hands)
+    assert np.array_equal(np.array(circles, dtype=np.float64).reshape(-1, 2), G[case + "/circles"])
+    assert np.array_equal(np.array(sticks, dtype=np.float64).reshape(-1, 4), G[case + "/sticks"])
+    assert [len(e) for e in edges] == G[case + "/n_edges"].tolist()
+    feat = F.populate_features(circles, peaks)
+    assert feat.shape == (156,) and np.array_equal(feat.astype(np.float64), G[case + "/feature"])
+    assert np.array_equal(F.frame_features(d["candidate"], d["subset"], hands, mt), G[case + "/feature"])
+
+
+def test_empty_frame_and_extra_hands():
+    f = F.frame_features(np.array([]), -1 * np.ones((0, 20)), [], "coco")
+    assert f.shape == (156,) and not f.any()
+    hands = [np.full((21, 2), k + 1, dtype=np.int64) for k in range(3)]   # the reference raises on a third hand
+    f = F.frame_features(np.array([]), -1 * np.ones((0, 20)), hands, "coco")
+    assert f[30] == 1 and f[30 + 63] == 2 and f[30 + 42:30 + 63].tolist() == list(range(21))
+
+
+def test_window_slides_oldest_first():
+    w = F.FeatureWindow()
+    for t in range(25):
+        out = w.push(np.full(156, float(t)))
+    assert w.full and out.shape == (20, 156) and out[0, 0] == 5.0 and out[-1, 0] == 24.0
+
+
+def test_clip_features_with_stand_in_estimators():
+    """KeypointExtractor.features on estimators without a device path: order and shape of the clip matrix."""
+    d = np.load(os.path.join(GOLD, "body_coco_p3_s1.npz"), allow_pickle=True)
+
+    class Body(object):
+        model_type = "coco"
+
+        def batch(self, frames):
+            return [(d["candidate"], d["subset"]) if int(f[0, 0, 0]) % 2 == 0 else (np.array([]), -1 * np.ones((0, 20)))
+                    for f in frames]
+
+    frames = [np.full((int(d["h"]), int(d["w"]), 3), t, dtype=np.uint8) for t in range(5)]
+    X = KeypointExtractor(Body(), None).features(frames, batch_size=2)
+    assert X.shape == (5, 156)
+    want = F.frame_features(d["candidate"], d["subset"], [], "coco")
+    assert np.array_equal(X[0], want) and np.array_equal(X[2], want) and not X[1].any()
