@@ -1069,6 +1069,11 @@ conv_umma_halo_swapped_kernel(const __grid_constant__ CUtensorMap tmX, const __g
       ptx::mbar_wait(bar_acc_full + 8 * buf, buf_ph);
       ptx::tc_fence_after();
       const uint32_t acc = tmem_base + buf * 256u + (static_cast<uint32_t>(q * 32) << 16);
+      // Short-K layers (3x3 with 64..128 input channels) are bound by this loop, not by the MMAs, so it is written for
+      // instruction count: one 64-bit row pointer per image row of the tile, pixel offsets i * stride that are
+      // warp-uniform constants, and no per-pixel bounds checks on tiles that lie inside the frame.
+      const long long pstride = a.out_pix_stride;
+      const bool full_w = x0 + 8 <= a.W;
       for (int c = 0; c < a.n_pix; c += 32) {
         uint32_t r[32];
         ptx::tmem_ld_32x32(acc + c, r);
@@ -1077,13 +1082,20 @@ conv_umma_halo_swapped_kernel(const __grid_constant__ CUtensorMap tmX, const __g
         for (int g = 0; g < 4; ++g) {  // 4 image rows of 8 pixels per 32-column chunk
           const int y = y0 + (c >> 3) + g;
           if (c + 8 * g < a.n_pix && y < a.H && ch_ok) {
-            __nv_bfloat16* const row = out + (static_cast<long long>(img) * a.H + y) * a.W * a.out_pix_stride;
+            __nv_bfloat16* const row = out + (static_cast<long long>(img * a.H + y) * a.W + x0) * pstride;
+            if (full_w) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int x = x0 + i;
-              if (x < a.W) {
+              for (int i = 0; i < 8; ++i) {
                 const float v0 = __uint_as_float(r[8 * g + i]) + bias;
-                row[static_cast<long long>(x) * a.out_pix_stride] = __float2bfloat16_rn(v0 > 0.f ? v0 : v0 * slope);
+                row[i * pstride] = __float2bfloat16_rn(v0 > 0.f ? v0 : v0 * slope);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                if (x0 + i < a.W) {
+                  const float v0 = __uint_as_float(r[8 * g + i]) + bias;
+                  row[i * pstride] = __float2bfloat16_rn(v0 > 0.f ? v0 : v0 * slope);
+                }
               }
             }
           }
