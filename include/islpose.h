@@ -62,6 +62,11 @@ int islpose_plan_add_conv(islpose_plan* plan, const islpose_conv_desc* desc);
 int islpose_plan_add_maxpool2x2(islpose_plan* plan, const void* in, void* out, int32_t n, int32_t h, int32_t w, int32_t c);
 /* fp32 NCHW [n,3,h,w] network input -> bf16 [n,h,w,32] rows of the first layer's 3x3x3 patches (27 + 5 zeros) */
 int islpose_plan_add_im2col3x3(islpose_plan* plan, const float* in_nchw, void* out_nhwc32, int32_t n, int32_t h, int32_t w);
+/* conv1_1 (3 -> 64 channels, 3x3, src/model.py 'conv1_1' of all three networks) in one launch straight from the fp32 NCHW
+ * network input: weights bf16 [64][32] with K index (ky*3+kx)*3+c (27 used, 5 zero), bias / slope as in islpose_conv_desc,
+ * out bf16 NHWC with out_cstride (>= 64) channels per pixel. Replaces add_im2col3x3 + a 1x1 add_conv over its output. */
+int islpose_plan_add_first_conv(islpose_plan* plan, const float* in_nchw, const void* weights, const float* bias,
+                                const float* slope, void* out, int32_t out_cstride, int32_t n, int32_t h, int32_t w);
 int islpose_plan_run(const islpose_plan* plan, void* stream);
 /* Measurement aid: runs the plan launch by launch, each one `reps` times back to back between two CUDA events (after
  * one untimed run), and blocks until done. h_ms / h_flops / h_variant (HOST arrays of num_launches entries; the last

@@ -45,6 +45,8 @@ SYMBOLS = {
     "islpose_plan_add_conv": (C.c_int, [C.c_void_p, C.POINTER(ConvDesc)]),
     "islpose_plan_add_maxpool2x2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "islpose_plan_add_im2col3x3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
+    "islpose_plan_add_first_conv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                            C.c_int32, C.c_int32, C.c_int32]),
     "islpose_plan_run": (C.c_int, [C.c_void_p, C.c_void_p]),
     "islpose_plan_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "islpose_plan_num_launches": (C.c_int32, [C.c_void_p]),

@@ -31,14 +31,17 @@ int check_cuda(const char* what) {
   return 0;
 }
 
-enum OpKind { kConv = 0, kPool = 1, kIm2col = 2 };
+enum OpKind { kConv = 0, kPool = 1, kIm2col = 2, kFirst = 3 };
 
 struct Op {
   OpKind kind;
   ConvLaunch conv;  // kConv
-  const void* in;   // kPool / kIm2col
+  const void* in;   // kPool / kIm2col / kFirst
   void* out;
   int n, h, w, c;
+  const void* weights;  // kFirst
+  const float* bias;
+  const float* slope;
 };
 
 const int kCocoA[19] = {1, 1, 2, 3, 5, 6, 1, 8, 9, 1, 11, 12, 1, 0, 14, 0, 15, 2, 5};
@@ -184,19 +187,46 @@ int islpose_plan_add_im2col3x3(islpose_plan* plan, const float* in_nchw, void* o
   return 0;
 }
 
+int islpose_plan_add_first_conv(islpose_plan* plan, const float* in_nchw, const void* weights, const float* bias,
+                                const float* slope, void* out, int32_t out_cstride, int32_t n, int32_t h, int32_t w) {
+  if (plan == nullptr || in_nchw == nullptr || weights == nullptr || bias == nullptr || slope == nullptr || out == nullptr)
+    return set_err("plan_add_first_conv: null argument");
+  if (out_cstride < 64 || out_cstride % 8 != 0 || (reinterpret_cast<uintptr_t>(out) & 15) != 0 ||
+      (reinterpret_cast<uintptr_t>(weights) & 15) != 0)
+    return set_err("plan_add_first_conv: output needs >= 64 channels per pixel (multiple of 8) and 16-byte alignment");
+  Op op;
+  memset(&op, 0, sizeof(op));
+  op.kind = kFirst;
+  op.in = in_nchw;
+  op.out = out;
+  op.n = n;
+  op.h = h;
+  op.w = w;
+  op.c = out_cstride;
+  op.weights = weights;
+  op.bias = bias;
+  op.slope = slope;
+  plan->ops.push_back(op);
+  plan->flops += 2.0 * 32 * 64 * static_cast<double>(n) * h * w;
+  return 0;
+}
+
+static int run_op(const Op& op, cudaStream_t st) {
+  switch (op.kind) {
+    case kConv: return conv_run(op.conv, st);
+    case kPool: return launch_maxpool2x2(op.in, op.n, op.h, op.w, op.c, op.out, st);
+    case kIm2col: return launch_im2col3x3(static_cast<const float*>(op.in), op.n, op.h, op.w, op.out, st);
+    default:
+      return launch_conv_first(static_cast<const float*>(op.in), op.n, op.h, op.w, op.weights, op.bias, op.slope, op.out, op.c, st);
+  }
+}
+
 int islpose_plan_run(const islpose_plan* plan, void* stream) {
   if (plan == nullptr) return set_err("plan_run: null plan");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   for (size_t i = 0; i < plan->ops.size(); ++i) {
     const Op& op = plan->ops[i];
-    int rc = 0;
-    if (op.kind == kConv) {
-      rc = conv_run(op.conv, st);
-    } else if (op.kind == kPool) {
-      rc = launch_maxpool2x2(op.in, op.n, op.h, op.w, op.c, op.out, st);
-    } else {
-      rc = launch_im2col3x3(static_cast<const float*>(op.in), op.n, op.h, op.w, op.out, st);
-    }
+    const int rc = run_op(op, st);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (rc != 0) {
       check_cuda("plan_run");
@@ -218,17 +248,16 @@ int islpose_plan_profile(const islpose_plan* plan, void* stream, int32_t reps, f
     // every launch is timed on its own, after all earlier launches of the plan have run once (valid inputs)
     for (int r = -1; r < reps && rc == 0; ++r) {
       if (r == 0) cudaEventRecord(e0, st);
-      if (op.kind == kConv) rc = conv_run(op.conv, st);
-      else if (op.kind == kPool) rc = launch_maxpool2x2(op.in, op.n, op.h, op.w, op.c, op.out, st);
-      else rc = launch_im2col3x3(static_cast<const float*>(op.in), op.n, op.h, op.w, op.out, st);
+      rc = run_op(op, st);
     }
     cudaEventRecord(e1, st);
     if (cudaEventSynchronize(e1) != cudaSuccess) rc = 1;
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
     h_ms[i] = ms / reps;
-    if (h_flops != nullptr) h_flops[i] = op.kind == kConv ? op.conv.flops : 0.0;
-    if (h_variant != nullptr) h_variant[i] = op.kind == kConv ? op.conv.variant : (op.kind == kPool ? -1 : -2);
+    if (h_flops != nullptr)
+      h_flops[i] = op.kind == kConv ? op.conv.flops : (op.kind == kFirst ? 2.0 * 27 * 64 * static_cast<double>(op.n) * op.h * op.w : 0.0);
+    if (h_variant != nullptr) h_variant[i] = op.kind == kConv ? op.conv.variant : (op.kind == kPool ? -1 : (op.kind == kFirst ? 0 : -2));
     g_launches.fetch_add(reps + 1, std::memory_order_relaxed);
   }
   cudaEventDestroy(e0);

@@ -469,11 +469,18 @@ gauss_window_kernel(const double* __restrict__ heat, int H, int W, const GaussWe
     const int item = threadIdx.x;
     if (item < (kG2SH / kR1) * kG2IW) {
       const int chunk = item / kG2IW, c = item - chunk * kG2IW;
-      const double* col = src + reflect_index(x0 - 1 - kGR + c, W);
+      const int xg = x0 - 1 - kGR + c;
+      const double* col = src + ((xg >= 0 && xg < W) ? xg : reflect_index(xg, W));
       double win[kR1 + 2 * kGR];
       const int ybase = y0 - 1 - kGR + chunk * kR1;
+      if (ybase >= 0 && ybase + kR1 + 2 * kGR <= H) {  // interior: no reflection, no index arithmetic per load
+        const double* p = col + static_cast<long long>(ybase) * W;
 #pragma unroll
-      for (int k = 0; k < kR1 + 2 * kGR; ++k) win[k] = __ldg(col + static_cast<long long>(reflect_index(ybase + k, H)) * W);
+        for (int k = 0; k < kR1 + 2 * kGR; ++k) win[k] = __ldg(p + static_cast<long long>(k) * W);
+      } else {
+#pragma unroll
+        for (int k = 0; k < kR1 + 2 * kGR; ++k) win[k] = __ldg(col + static_cast<long long>(reflect_index(ybase + k, H)) * W);
+      }
 #pragma unroll
       for (int o = 0; o < kR1; ++o) {
         double tmp = __dmul_rn(win[o + kGR], gw.w[kGR]);

@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace islpose {
 namespace ptx {
@@ -49,7 +50,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 // The slow path is a real function call: the issue loops of the conv kernels are executed by a single lane, whose
 // instruction latency is what limits the tensor pipe (build/mma_rate), so the common case - the barrier has already
 // completed - must cost one try_wait and one branch, nothing else.
-__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   // try_wait suspends the thread in hardware for a while, so a handful of attempts covers every legitimate wait;
   // the (slow) global timer is only consulted after thousands of failed attempts
   uint32_t spins = 0;

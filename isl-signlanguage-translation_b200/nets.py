@@ -245,7 +245,10 @@ class _Instance:
         self.flops_algorithmic = algorithmic_flops(net.kind, n, h, w)
         self.input = torch.empty((n, 3, h, w), dtype=torch.float32, device=dev)
         self.bufs = {}
+        fused_first = not net.tuning.get("unfused_first", False)
         for name, (ch, level) in net.program.bufs.items():
+            if name == "x32" and fused_first:
+                continue   # the fused first layer gathers its patches itself
             # physical width rounded up to 64 channels (zeros, never written): every 64-channel box is in bounds
             self.bufs[name] = torch.zeros((n, h >> level, w >> level, _up64(ch) if ch > 32 else ch), dtype=torch.bfloat16,
                                           device=dev)
@@ -257,8 +260,9 @@ class _Instance:
         ci = 0
         for step in net.program.steps:
             if step[0] == "im2col":
-                _lib.check(L.islpose_plan_add_im2col3x3(handle, _lib.ptr(self.input), _lib.ptr(self.bufs[step[1]]), n, h, w),
-                           "islpose_plan_add_im2col3x3")
+                if not fused_first:
+                    _lib.check(L.islpose_plan_add_im2col3x3(handle, _lib.ptr(self.input), _lib.ptr(self.bufs[step[1]]), n, h, w),
+                               "islpose_plan_add_im2col3x3")
             elif step[0] == "pool":
                 src, dst = self.bufs[step[1]], self.bufs[step[2]]
                 _lib.check(L.islpose_plan_add_maxpool2x2(handle, _lib.ptr(src), _lib.ptr(dst), n, src.shape[1], src.shape[2],
@@ -267,6 +271,13 @@ class _Instance:
                 s = step[1]
                 wt, bias, slope = net.packed[ci]
                 ci += 1
+                if s["first"] and fused_first:
+                    # conv1_1 in one launch straight from the float32 network input (csrc/conv_first.cu)
+                    db = self.bufs[s["dst"][0]]
+                    _lib.check(L.islpose_plan_add_first_conv(handle, _lib.ptr(self.input), _lib.ptr(wt), _lib.ptr(bias),
+                                                             _lib.ptr(slope), C.c_void_p(db.data_ptr() + 2 * s["dst"][1]),
+                                                             db.shape[3], n, h, w), "islpose_plan_add_first_conv")
+                    continue
                 sb = self.bufs[s["src"][0]]
                 d = _lib.ConvDesc()
                 d.in_ = sb.data_ptr() + 2 * s["src"][1]

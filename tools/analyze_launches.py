@@ -28,13 +28,13 @@ def main(path, body_kind, body_hw, hand_hw, n_body, n_hand):
         print("  %-52s n=%5d %9.3f ms %5.1f%%  avg %8.1f us" % (k[:52], v[0], v[1] / 1e6, 100 * v[1] / allt, v[1] / v[0] / 1e3))
     bystream = collections.defaultdict(list)
     for r in rows:
-        if any(t in r['Kernel Name'] for t in ('conv_umma', 'maxpool', 'im2col')):
+        if any(t in r['Kernel Name'] for t in ('conv_umma', 'conv_first', 'maxpool', 'im2col')):
             bystream[r['Stream']].append(r)
     last = {}
     for st, lst in bystream.items():
         cur = None
         for r in lst:
-            if 'im2col' in r['Kernel Name']:
+            if 'im2col' in r['Kernel Name'] or 'conv_first' in r['Kernel Name']:
                 cur = []
                 last[(st, r['Grid Size'])] = cur
             elif cur is not None:

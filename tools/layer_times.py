@@ -34,7 +34,11 @@ def main():
                                                fl.ctypes.data_as(C.c_void_p), var.ctypes.data_as(C.c_void_p)), "plan_profile")
     names = []
     for step in net.program.steps:
-        names.append("im2col" if step[0] == "im2col" else ("pool" if step[0] == "pool" else step[1]["layer"]))
+        if step[0] == "im2col":
+            if "x32" in inst.bufs:   # separate gather pass (tuning unfused_first); the fused first layer has none
+                names.append("im2col")
+            continue
+        names.append("pool" if step[0] == "pool" else step[1]["layer"])
     groups = collections.OrderedDict()
     for name, t, f, v in zip(names, ms, fl, var):
         key = name
