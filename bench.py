@@ -355,7 +355,7 @@ def main():
             "gpu_launches": int(gpu_launches),
             "roofline": {"bound": "tensor", "kernel": "conv_umma_* (tcgen05 implicit-GEMM variants): the network replays of "
                                                       "a step run on their own, same chunks / lanes / streams as the step; the "
-                                                      "resize, im2col and max-pool launches are inside the same events",
+                                                      "resize, first-layer and max-pool launches are inside the same events",
                          "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
                          "peak_source": "%s bf16_tflops_sustained (burst %.1f)" % (src, burst),
                          "traffic": CONV_DRAM_TRAFFIC, "conv_share_of_step": conv_ms / max(dev_ms, 1e-9)},
