@@ -53,6 +53,8 @@ typedef struct islpose_conv_desc {
   float* out_f32;       /* fp32 planar NCHW (may be NULL): channel 0 of this layer inside [n][out_f32_channels][h][w] */
   int32_t out_f32_channels;
   int32_t n_tile, stages, tile_w, tile_h; /* tuning overrides, 0 = automatic */
+  int32_t pool;         /* 1: nn.MaxPool2d(2,2,0) fused behind the activation (src/model.py:30-32); out_bf16 is then the pooled
+                           [n][h/2][w/2] buffer. Only for 3x3 / 7x7 layers with >= 64 input and >= 48 output channels */
 } islpose_conv_desc;
 
 int islpose_plan_create(islpose_plan** out);

@@ -62,6 +62,7 @@ struct Cfg {
   bool f32_out, bf16_out;
   int force_n_tile, force_stages;
   int variant, msub, acc_bufs, bo_mode, no_loads;
+  int pool;  // 2x2 max-pool fused into the layer: the bf16 output is compared with the pooled reference
 };
 
 static int run_cfg(const Cfg& c, bool timing) {
@@ -121,6 +122,7 @@ static int run_cfg(const Cfg& c, bool timing) {
   d.acc_bufs = c.acc_bufs;
   d.halo_base_offset_mode = c.bo_mode;
   d.debug_no_loads = c.no_loads;
+  d.pool = c.pool;
 
   ConvLaunch L;
   char err[256];
@@ -150,6 +152,32 @@ static int run_cfg(const Cfg& c, bool timing) {
   CK(cudaMemcpy(h_o16.data(), d_out16, h_o16.size() * 2, cudaMemcpyDeviceToHost));
   double max_ref = 0, err32 = 0, err16 = 0;
   long long bad_pad = 0;
+  if (c.pool) {
+    // the device wrote [N][H/2][W/2][out_cstride]; compare with the 2x2 max of the reference layer
+    const int Hp = c.H / 2, Wp = c.W / 2;
+    for (int n = 0; n < c.N; ++n)
+      for (int y = 0; y < Hp; ++y)
+        for (int x = 0; x < Wp; ++x) {
+          const long long q = (static_cast<long long>(n) * Hp + y) * Wp + x;
+          for (int co = 0; co < c.cout; ++co) {
+            double m = -1e30;
+            for (int dy = 0; dy < 2; ++dy)
+              for (int dx = 0; dx < 2; ++dx) {
+                const long long p = (static_cast<long long>(n) * c.H + 2 * y + dy) * c.W + 2 * x + dx;
+                m = fmax(m, static_cast<double>(h_ref[p * c.cout + co]));
+              }
+            if (fabs(m) > max_ref) max_ref = fabs(m);
+            const double o = __bfloat162float(h_o16[q * out_cstride + out_coff + co]);
+            const double dd = fabs(o - m) / (1.0 + fabs(m));
+            if (!(dd <= err16)) err16 = dd;
+          }
+          const uint16_t* raw = reinterpret_cast<const uint16_t*>(h_o16.data());
+          for (int co = 0; co < out_coff; ++co)
+            if (raw[q * out_cstride + co] != 0x7f7f) ++bad_pad;
+          for (int co = out_coff + (c.cout + 7) / 8 * 8; co < out_cstride; ++co)
+            if (raw[q * out_cstride + co] != 0x7f7f) ++bad_pad;
+        }
+  } else
   for (long long p = 0; p < npix; ++p) {
     for (int co = 0; co < c.cout; ++co) {
       const double r = h_ref[p * c.cout + co];
@@ -400,6 +428,13 @@ static int run_v5_suite() {
       {"v1 7x7 128->128 69x92 b8", 8, 69, 92, 128, 128, 0, 128, 7, false, true, 0, 0, 1, 0, 0, 0, 0},
       {"v5 7x7 128->128 69x92 b8", 8, 69, 92, 128, 128, 0, 128, 7, false, true, 0, 0, 5, 0, 0, 0, 0},
       {"v5 7x7 128->128 23x31 b2", 2, 23, 31, 128, 128, 0, 128, 7, false, true, 0, 0, 5, 0, 0, 0, 0},
+      {"v5 pool 3x3 64->64 46x62 b2", 2, 46, 62, 64, 64, 0, 64, 3, false, true, 0, 0, 5, 0, 0, 0, 0, 1},
+      {"v5 pool 3x3 128->128 40x24 b3", 3, 40, 24, 128, 128, 0, 128, 3, false, true, 0, 0, 5, 0, 0, 0, 0, 1},
+      {"v5 pool 3x3 256->256 92x124 b2", 2, 92, 124, 256, 256, 0, 256, 3, false, true, 0, 0, 5, 0, 0, 0, 0, 1},
+      {"auto 3x3 64->64 368x496 b8", 8, 368, 496, 64, 64, 0, 64, 3, false, true, 0, 0, 0, 0, 0, 0, 0},
+      {"v5 3x3 64->64 368x496 b8", 8, 368, 496, 64, 64, 0, 64, 3, false, true, 0, 0, 5, 0, 0, 0, 0},
+      {"auto 3x3 64->64 736x736 b2", 2, 736, 736, 64, 64, 0, 64, 3, false, true, 0, 0, 0, 0, 0, 0, 0},
+      {"v5 3x3 64->64 736x736 b2", 2, 736, 736, 64, 64, 0, 64, 3, false, true, 0, 0, 5, 0, 0, 0, 0},
       {"v1 7x7 128->128 23x31 b2", 2, 23, 31, 128, 128, 0, 128, 7, false, true, 0, 0, 1, 0, 0, 0, 0},
   };
   int fails = 0;

@@ -1074,6 +1074,39 @@ conv_umma_halo_swapped_kernel(const __grid_constant__ CUtensorMap tmX, const __g
       // warp-uniform constants, and no per-pixel bounds checks on tiles that lie inside the frame.
       const long long pstride = a.out_pix_stride;
       const bool full_w = x0 + 8 <= a.W;
+      if (a.pool) {
+        // nn.MaxPool2d(2, 2) behind the activation (model.py:30-32 after conv1_2 / conv2_2 / conv3_4): a chunk holds 4
+        // image rows x 8 pixels of this thread's channel, i.e. 2 x 4 complete pooling windows (tile origin and height
+        // are even). max() commutes with the monotonic bf16 rounding, so the result equals pooling the stored layer.
+        const int Hp = a.H >> 1, Wp = a.W >> 1;
+        for (int c = 0; c < a.n_pix; c += 32) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(acc + c, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 4; g += 2) {
+            const int yp = (y0 + (c >> 3) + g) >> 1;
+            if (c + 8 * g < a.n_pix && yp < Hp && ch_ok) {
+              __nv_bfloat16* const row = out + (static_cast<long long>(img * Hp + yp) * Wp + (x0 >> 1)) * pstride;
+#pragma unroll
+              for (int i = 0; i < 8; i += 2) {
+                if ((x0 + i) >> 1 < Wp) {
+                  float m = -3.0e38f;
+#pragma unroll
+                  for (int dy = 0; dy < 2; ++dy) {
+#pragma unroll
+                    for (int dx = 0; dx < 2; ++dx) {
+                      const float v0 = __uint_as_float(r[8 * (g + dy) + i + dx]) + bias;
+                      m = fmaxf(m, v0 > 0.f ? v0 : v0 * slope);
+                    }
+                  }
+                  row[(i >> 1) * pstride] = __float2bfloat16_rn(m);
+                }
+              }
+            }
+          }
+        }
+      } else
       for (int c = 0; c < a.n_pix; c += 32) {
         uint32_t r[32];
         ptx::tmem_ld_32x32(acc + c, r);
@@ -1170,14 +1203,17 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   // Automatic choice (measured, profiles/conv_test_v5_r1.log): every 3x3 / 7x7 layer with at least 64 input channels and
   // more than 64 output channels runs fastest on v5 (7x7 128->128: 1419 TFLOP/s against 1277 for v4 and 1085 for v1 on a
   // 92x164x8 grid, 1245 against 938 on 69x92x8; 3x3 256->256: 1358 against 1047). 1x1 layers, the float32 network heads,
-  // the 64-channel full-resolution layers and the 32-channel first layer stay on v1 / v2.
+  // the 32-channel first layer stay on v1 / v2. A 64-output-channel layer (conv1_2) wastes half of the M=128 rows and still
+  // beats the persistent v2 kernel, which is L2-bound on the re-fetched activations (617 against 495 TFLOP/s at 736x736x2).
   static const int env_no_v5 = getenv("ISLPOSE_NO_V5") != nullptr;  // A/B measurement aid
-  const bool auto_v5 = d.variant <= 0 && !env_no_v5 && d.ksize >= 3 && d.in_c >= 64 && d.cout > 64 && d.out_bf16 != nullptr &&
+  const bool auto_v5 = d.variant <= 0 && !env_no_v5 && d.ksize >= 3 && d.in_c >= 64 && d.cout >= 48 && d.out_bf16 != nullptr &&
                        d.out_f32 == nullptr && d.force_n_tile <= 0 && d.force_bw <= 0;
   if (d.variant == 5 || auto_v5) {
     // swapped operands + resident halo, persistent (see the kernel): 8 x th pixel tiles, th even, <= 32
     if (d.ksize < 3) return fail(err, errlen, "conv: the halo variants need k > 1");
     if (d.out_bf16 == nullptr || d.out_f32 != nullptr) return fail(err, errlen, "conv: v5 writes bf16 slices only");
+    if (d.pool && (d.H % 2 != 0 || d.W % 2 != 0)) return fail(err, errlen, "conv: fused 2x2 pooling needs even H, W (%lld x %lld)", d.H, d.W);
+    a.pool = d.pool ? 1 : 0;
     const int kb5 = d.ksize * d.ksize * ((d.in_c + 63) / 64);
     const int n_ct = (d.cout + 127) / 128;
     int th = d.force_bh;
@@ -1264,6 +1300,7 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
     return 0;
   }
 
+  if (d.pool) return fail(err, errlen, "conv: fused pooling is only available in the halo variant (k >= 3, Cin >= 64, Cout >= 48, bf16 output)");
   // Cost model fitted to the measurements in profiles/ (cycles per CTA): a tcgen05.mma of M=128 x N x K=16 costs about
   // 207 + N/2 when the CTA has its SM to itself and 192 + N when two CTAs share the SM; `epi` is the epilogue.
   const int kblocks = d.ksize * d.ksize * ((d.in_c + 63) / 64);

@@ -56,6 +56,7 @@ struct ConvDesc {
   int halo_base_offset_mode;  // v3 bring-up switch: 0 = base offset 0 (correct on B200), 1 = start row's swizzle phase
   int msub;     // v2: pixel sub-tiles per work item sharing one weight stage (0 = automatic, 1 or 2)
   int acc_bufs; // v2: TMEM accumulator buffers (0 = automatic, 1 or 2)
+  int pool;     // 1: nn.MaxPool2d(2,2) fused behind the activation (v5 only): out_bf16 is the [N,H/2,W/2] pooled buffer
 };
 
 // A fully resolved launch (tensor maps built once, reusable for every replay).
@@ -84,6 +85,7 @@ struct ConvArgs {
   int n_pix;       // v4: UMMA N = pixels per tile rounded up to 16
   int tma_store;   // v4: the bf16 tile leaves through shared memory + TMA store
   int tap_rot;     // v5: CTAs start the tap loop at different taps
+  int pool;        // v5: 2x2 max-pool in the epilogue
   __nv_bfloat16* out_bf16;
   long long out_pix_stride;
   float* out_f32;

@@ -258,15 +258,23 @@ class _Instance:
         _lib.check(L.islpose_plan_create(C.byref(handle)), "islpose_plan_create")
         self.handle = handle
         ci = 0
-        for step in net.program.steps:
+        steps = net.program.steps
+        fuse_pool = not net.tuning.get("unfused_pool", False)
+        fused_pools = set()
+        self.op_names = []   # one name per recorded launch (tools/layer_times.py)
+        for si, step in enumerate(steps):
             if step[0] == "im2col":
                 if not fused_first:
                     _lib.check(L.islpose_plan_add_im2col3x3(handle, _lib.ptr(self.input), _lib.ptr(self.bufs[step[1]]), n, h, w),
                                "islpose_plan_add_im2col3x3")
+                    self.op_names.append("im2col")
             elif step[0] == "pool":
+                if si in fused_pools:
+                    continue   # done in the epilogue of the layer before it
                 src, dst = self.bufs[step[1]], self.bufs[step[2]]
                 _lib.check(L.islpose_plan_add_maxpool2x2(handle, _lib.ptr(src), _lib.ptr(dst), n, src.shape[1], src.shape[2],
                                                          src.shape[3]), "islpose_plan_add_maxpool2x2")
+                self.op_names.append("pool")
             else:
                 s = step[1]
                 wt, bias, slope = net.packed[ci]
@@ -277,6 +285,7 @@ class _Instance:
                     _lib.check(L.islpose_plan_add_first_conv(handle, _lib.ptr(self.input), _lib.ptr(wt), _lib.ptr(bias),
                                                              _lib.ptr(slope), C.c_void_p(db.data_ptr() + 2 * s["dst"][1]),
                                                              db.shape[3], n, h, w), "islpose_plan_add_first_conv")
+                    self.op_names.append(s["layer"])
                     continue
                 sb = self.bufs[s["src"][0]]
                 d = _lib.ConvDesc()
@@ -291,7 +300,16 @@ class _Instance:
                 d.ksize = 1 if s["first"] else s["k"]
                 d.bias = bias.data_ptr()
                 d.slope = slope.data_ptr()
-                if s["dst"] is not None:
+                nxt = steps[si + 1] if si + 1 < len(steps) else None
+                if (fuse_pool and nxt is not None and nxt[0] == "pool" and s["dst"] is not None and nxt[1] == s["dst"][0]
+                        and s["k"] >= 3 and s["src"][2] >= 64 and s["cout"] >= 48 and s["f32"] is None and not s["first"]):
+                    # nn.MaxPool2d(2, 2) fused into this layer's epilogue: the full-resolution tensor is never written
+                    db = self.bufs[nxt[2]]
+                    d.out_bf16 = db.data_ptr()
+                    d.out_cstride = db.shape[3]
+                    d.pool = 1
+                    fused_pools.add(si + 1)
+                elif s["dst"] is not None:
                     db = self.bufs[s["dst"][0]]
                     d.out_bf16 = db.data_ptr() + 2 * s["dst"][1]
                     d.out_cstride = db.shape[3]
@@ -302,6 +320,7 @@ class _Instance:
                 cfg = net.tuning
                 d.n_tile, d.stages = cfg.get("n_tile", 0), cfg.get("stages", 0)
                 _lib.check(L.islpose_plan_add_conv(handle, C.byref(d)), "islpose_plan_add_conv(%s)" % s["layer"])
+                self.op_names.append(s["layer"] + ("+pool" if d.pool else ""))
         self.flops = L.islpose_plan_conv_flops(handle)
         self.launches = L.islpose_plan_num_launches(handle)
         # the zero-fills above ran on the current stream, but the plan may be replayed on any stream: make the

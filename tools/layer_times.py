@@ -32,13 +32,7 @@ def main():
     var = np.zeros(nl, dtype=np.int32)
     _lib.check(_lib.lib().islpose_plan_profile(inst.handle, _lib.stream_ptr(), 10, ms.ctypes.data_as(C.c_void_p),
                                                fl.ctypes.data_as(C.c_void_p), var.ctypes.data_as(C.c_void_p)), "plan_profile")
-    names = []
-    for step in net.program.steps:
-        if step[0] == "im2col":
-            if "x32" in inst.bufs:   # separate gather pass (tuning unfused_first); the fused first layer has none
-                names.append("im2col")
-            continue
-        names.append("pool" if step[0] == "pool" else step[1]["layer"])
+    names = inst.op_names
     groups = collections.OrderedDict()
     for name, t, f, v in zip(names, ms, fl, var):
         key = name
