@@ -452,6 +452,38 @@ static int run_v5_suite() {
   return fails ? 1 : 0;
 }
 
+static int run_gemm_suite() {
+  // 1x1 layers that are real GEMMs (body25 Mconv6: 384 -> 512 and 288 -> 256 on the stride-8 grid): which structure wins?
+  const Cfg cfgs[] = {
+      {"auto 1x1 384->512 92x164 b8", 8, 92, 164, 384, 384, 0, 512, 1, false, true, 0, 0, 0, 0, 0},
+      {"v1 nt256 s2", 8, 92, 164, 384, 384, 0, 512, 1, false, true, 256, 2, 1, 0, 0},
+      {"v1 nt128 s3", 8, 92, 164, 384, 384, 0, 512, 1, false, true, 128, 3, 1, 0, 0},
+      {"v2 nt256 m1 a2 s4", 8, 92, 164, 384, 384, 0, 512, 1, false, true, 256, 4, 2, 1, 2},
+      {"v2 nt256 m1 a2 s3", 8, 92, 164, 384, 384, 0, 512, 1, false, true, 256, 3, 2, 1, 2},
+      {"v2 nt128 m2 a2 s4", 8, 92, 164, 384, 384, 0, 512, 1, false, true, 128, 4, 2, 2, 2},
+      {"v2 nt128 m2 a2 s3", 8, 92, 164, 384, 384, 0, 512, 1, false, true, 128, 3, 2, 2, 2},
+      {"v2 nt256 m2 a1 s3", 8, 92, 164, 384, 384, 0, 512, 1, false, true, 256, 3, 2, 2, 1},
+      {"v2 nt128 m1 a2 s4 (2/SM)", 8, 92, 164, 384, 384, 0, 512, 1, false, true, 128, 4, 2, 1, 2},
+      {"auto 1x1 288->256 92x164 b8", 8, 92, 164, 288, 288, 0, 256, 1, false, true, 0, 0, 0, 0, 0},
+      {"v2 nt256 m1 a2 s4 288->256", 8, 92, 164, 288, 288, 0, 256, 1, false, true, 256, 4, 2, 1, 2},
+      {"v2 nt128 m2 a2 s4 288->256", 8, 92, 164, 288, 288, 0, 256, 1, false, true, 128, 4, 2, 2, 2},
+      {"auto 1x1 128->512 92x124 b16", 16, 92, 124, 128, 128, 0, 512, 1, false, true, 0, 0, 0, 0, 0},
+      {"v2 nt128 m2 a2 s4 128->512", 16, 92, 124, 128, 128, 0, 512, 1, false, true, 128, 4, 2, 2, 2},
+      {"auto 1x1 128->128 92x124 b16", 16, 92, 124, 128, 128, 0, 128, 1, false, true, 0, 0, 0, 0, 0},
+      {"v2 nt128 m2 a2 s4 128->128", 16, 92, 124, 128, 128, 0, 128, 1, false, true, 128, 4, 2, 2, 2},
+      {"auto 1x1 512->512 92x164 b8 f32", 8, 92, 164, 512, 512, 0, 52, 1, true, true, 0, 0, 0, 0, 0},
+      {"v2 512->52 m2 a2 s4 f32", 8, 92, 164, 512, 512, 0, 52, 1, true, true, 0, 4, 2, 2, 2},
+  };
+  int fails = 0;
+  for (const Cfg& c : cfgs) {
+    const int r = run_cfg(c, true);
+    if (r == 3) return 3;
+    fails += r;
+  }
+  printf("%s: %d failing configuration(s)\n", fails ? "FAILED" : "DONE", fails);
+  return fails ? 1 : 0;
+}
+
 static int run_limits_suite() {
   // where is the ceiling? same layers with and without TMA traffic (no_loads: results are garbage by design)
   const Cfg cfgs[] = {
@@ -513,6 +545,7 @@ int main(int argc, char** argv) {
   if (argc > 1 && std::string(argv[1]) == "v4") return run_v4_suite();
   if (argc > 2) g_only = atoi(argv[2]);
   if (argc > 1 && std::string(argv[1]) == "v5") return run_v5_suite();
+  if (argc > 1 && std::string(argv[1]) == "gemm") return run_gemm_suite();
   int fails = 0;
   for (int i = 0; i < n; ++i) {
     if (argc > 1 && atoi(argv[1]) != i) continue;

@@ -46,7 +46,7 @@ __device__ __forceinline__ void issue_kblock(uint32_t d, uint64_t da, uint64_t d
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const ConvArgs a) {
+                 const __grid_constant__ CUtensorMap tmC, const ConvArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
@@ -199,8 +199,29 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const float acc = __uint_as_float(r[i]) + s_bias[c + i];
         v[i] = acc > 0.f ? acc : acc * s_slope[c + i];
       }
+      if (a.tma_store) {
+        // The bf16 tile leaves through the (now idle) operand ring: per 64 channels one [pixel][64 ch] block in the
+        // 128-byte-swizzled layout a TMA store expects. A thread owns one pixel row, so direct stores would put 16
+        // bytes into each of 32 different lines per instruction (measured: 1x1 layers with wide outputs stuck at
+        // ~1.1 TB/s of output, 150-450 TFLOP/s); the bulk store writes whole lines and clips pixels outside the
+        // frame and channels beyond the slice.
+        const uint32_t blk = sA0 + static_cast<uint32_t>(c >> 6) * kASlotBytes + static_cast<uint32_t>(row) * 128u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * j + 0], v[8 * j + 1]);
+          __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
+          __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+          const uint32_t chunk = static_cast<uint32_t>(((c & 63) >> 3) + j);
+          const uint32_t addr = blk + ((chunk ^ (static_cast<uint32_t>(row) & 7u)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(*reinterpret_cast<uint32_t*>(&h0)),
+                       "r"(*reinterpret_cast<uint32_t*>(&h1)), "r"(*reinterpret_cast<uint32_t*>(&h2)),
+                       "r"(*reinterpret_cast<uint32_t*>(&h3))
+                       : "memory");
+        }
+      }
       if (valid) {
-        if (a.out_bf16 != nullptr) {
+        if (a.out_bf16 != nullptr && !a.tma_store) {
           __nv_bfloat16* dst = a.out_bf16 + pix * a.out_pix_stride + n0 + c;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -229,6 +250,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (n0 + c + i < a.cout) dst[i * plane] = v[i];
           }
         }
+      }
+    }
+    if (a.tma_store) {
+      ptx::fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
+      if (threadIdx.x == 64) {
+        for (int b = 0; b * 64 < a.n_tile; ++b) {
+          if (n0 + b * 64 < a.cout_store) ptx::tma_store_4d(&tmC, sA0 + b * kASlotBytes, n0 + b * 64, x0, y0, img);
+        }
+        ptx::tma_store_commit();
+        ptx::tma_store_wait_all();
       }
     }
   }
@@ -1474,7 +1506,10 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
     if (r != CUDA_SUCCESS) return fail(err, errlen, "conv: weight tensor map rejected (CUresult %lld)", r);
   }
 
-  if (variant == 4 && d.out_bf16 != nullptr && stages >= 2) {
+  // v1: the staging blocks (16 KB per 64 channels) must fit into the operand ring
+  const bool v1_store = variant == 1 && d.out_bf16 != nullptr && getenv("ISLPOSE_NO_V1_TMA_STORE") == nullptr &&
+                        static_cast<uint32_t>((n_tile + 63) / 64) * kASlotBytes <= stages * per_stage;
+  if ((variant == 4 && d.out_bf16 != nullptr && stages >= 2) || v1_store) {
     cuuint64_t gdim[4] = {static_cast<cuuint64_t>(a.cout_store), static_cast<cuuint64_t>(d.W),
                           static_cast<cuuint64_t>(d.H), static_cast<cuuint64_t>(d.N)};
     cuuint64_t gstr[3] = {static_cast<cuuint64_t>(d.out_cstride) * 2, static_cast<cuuint64_t>(d.out_cstride) * 2 * d.W,
@@ -1526,7 +1561,7 @@ int conv_run(const ConvLaunch& l, cudaStream_t stream) {
   } else if (l.variant == 5) {
     conv_umma_halo_swapped_kernel<<<l.grid, kThreads, l.smem_bytes, stream>>>(l.tmA, l.tmB, l.args);
   } else {
-    conv_umma_kernel<<<l.grid, kThreads, l.smem_bytes, stream>>>(l.tmA, l.tmB, l.args);
+    conv_umma_kernel<<<l.grid, kThreads, l.smem_bytes, stream>>>(l.tmA, l.tmB, l.tmC, l.args);
   }
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
