@@ -37,7 +37,7 @@ WEIGHT_INIT = "torch"   # nn.Conv2d's default init distribution (SURVEY.md secti
 WORKLOADS = {
     # name: (model_type, H, W, hand boxes [x, y, w, is_left], default batch per rank)
     "C2": ("coco", 480, 640, [[400, 250, 109, True], [22, 246, 90, False]], 16),
-    "C3": ("body25", 720, 1280, [[800, 300, 128, True], [300, 300, 128, False]], 8),
+    "C3": ("body25", 720, 1280, [[800, 300, 128, True], [300, 300, 128, False]], 16),
 }
 
 
