@@ -123,6 +123,7 @@ typedef struct islpose_group_buffers {
   const double* scores;
   int64_t pair_cap;        /* scratch elements per (frame, limb); needs nA*nB <= pair_cap, else overflow = 3 */
   double* pair_score;      /* [n*nlimbs*pair_cap] dense nA x nB connection scores (-1 = rejected pair) */
+  double* end_paf;         /* [n*nlimbs*2*cap*2] scratch: the limb's PAF vector at each of its end peaks */
   int32_t* conn_count;     /* [n*nlimbs] */
   int32_t* conn_ij;        /* [n*nlimbs*cap*2] */
   double* conn_score;      /* [n*nlimbs*cap] */

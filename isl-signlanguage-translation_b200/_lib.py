@@ -30,7 +30,7 @@ class Scale(C.Structure):
 
 class GroupBuffers(C.Structure):
     _fields_ = [("cap", C.c_int32), ("counts", C.c_void_p), ("keys", C.c_void_p), ("scores", C.c_void_p),
-                ("pair_cap", C.c_int64), ("pair_score", C.c_void_p), ("conn_count", C.c_void_p), ("conn_ij", C.c_void_p),
+                ("pair_cap", C.c_int64), ("pair_score", C.c_void_p), ("end_paf", C.c_void_p), ("conn_count", C.c_void_p), ("conn_ij", C.c_void_p),
                 ("conn_score", C.c_void_p), ("owner", C.c_void_p), ("max_cand", C.c_int32), ("candidate", C.c_void_p), ("n_cand", C.c_void_p),
                 ("max_person", C.c_int32), ("subset", C.c_void_p), ("n_person", C.c_void_p), ("overflow", C.c_void_p)]
 

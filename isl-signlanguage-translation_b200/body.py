@@ -80,6 +80,7 @@ class Body(object):
                 scores=torch.zeros((n * parts, PEAK_CAP), **f64),
                 pair_cap=PAIR_CAP,
                 pair_score=torch.empty((n * nl, PAIR_CAP), **f64),
+                end_paf=torch.empty((n * nl, 2, PEAK_CAP, 2), **f64),
                 conn_count=torch.zeros((n * nl,), **i32),
                 conn_ij=torch.zeros((n * nl, PEAK_CAP, 2), **i32),
                 conn_score=torch.zeros((n * nl, PEAK_CAP), **f64),
@@ -147,7 +148,7 @@ class Body(object):
         paf_scales = self._scales_struct(maps, 0)
         gb = _lib.GroupBuffers()
         gb.cap, gb.pair_cap, gb.max_cand, gb.max_person = PEAK_CAP, ws["pair_cap"], parts * PEAK_CAP, ws["max_person"]
-        for f in ("counts", "keys", "scores", "pair_score", "conn_count", "conn_ij", "conn_score", "owner", "candidate",
+        for f in ("counts", "keys", "scores", "pair_score", "end_paf", "conn_count", "conn_ij", "conn_score", "owner", "candidate",
                   "n_cand", "subset", "n_person", "overflow"):
             setattr(gb, f, ws[f].data_ptr())
         _lib.check(L.islpose_body_group(paf_scales, len(maps), 1 if self._kind == 'body25' else 0, n, H, W, self.thre2,

@@ -331,6 +331,7 @@ int islpose_body_group(const islpose_scale* paf_scales, int32_t n_scales, int32_
   gb.scores = b->scores;
   gb.pair_cap = b->pair_cap;
   gb.pair_score = b->pair_score;
+  gb.end_paf = b->end_paf;
   gb.conn_count = b->conn_count;
   gb.conn_ij = b->conn_ij;
   gb.conn_score = b->conn_score;
@@ -346,7 +347,7 @@ int islpose_body_group(const islpose_scale* paf_scales, int32_t n_scales, int32_
   if (launch_paf_score(ss, lt, n, H, W, thre2, mid_num, gb, st) != 0)
     return check_cuda("body_group/paf_score") ? 1 : set_err("body_group: peak capacity out of range (cap %d)", gb.cap);
   if (launch_group(lt, n, W, gb, st) != 0) return check_cuda("body_group/group") ? 1 : set_err("body_group: launch failed");
-  g_launches.fetch_add(3, std::memory_order_relaxed);
+  g_launches.fetch_add(4, std::memory_order_relaxed);
   return 0;
 }
 

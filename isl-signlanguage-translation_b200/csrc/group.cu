@@ -13,6 +13,56 @@
 
 namespace islpose {
 
+// paf_avg (never materialised) at one integer frame position for the two PAF channels of a limb: both cubic stages per
+// scale, float32 division by the number of scales, float64 accumulation (body.py:81) - the reference's values exactly.
+__device__ __forceinline__ void paf_at(const ScaleSet& ss, const float (*s_tab)[4], int n, int rx, int ry, int chx, int chy,
+                                       int W, double& vx, double& vy) {
+  const int C = ss.channels;
+  const long long tail_start = (static_cast<long long>(W) * C) / 4 * 4;
+  const float fS = static_cast<float>(ss.count);
+  const bool tailx = static_cast<long long>(rx) * C + chx >= tail_start;
+  const bool taily = static_cast<long long>(rx) * C + chy >= tail_start;
+  vx = 0.0;
+  vy = 0.0;
+  for (int s = 0; s < ss.count; ++s) {
+    const ScaleGeom& g = ss.g[s];
+    Axis2 sx, sy;
+    make_axis2(rx, g.sx, g.wc, g.gw, s_tab, sx);
+    make_axis2(ry, g.sy, g.hc, g.gh, s_tab, sy);
+    const float* img = g.low + static_cast<long long>(n) * C * g.gh * g.gw;
+    const long long plane = static_cast<long long>(g.gh) * g.gw;
+    vx = __dadd_rn(vx, static_cast<double>(__fdiv_rn(sample2(img + chx * plane, g.gw, sx, sy, tailx), fS)));
+    vy = __dadd_rn(vy, static_cast<double>(__fdiv_rn(sample2(img + chy * plane, g.gw, sx, sy, taily), fS)));
+  }
+}
+
+// The first and the last of the 10 line samples of a candidate pair (body.py:148-155) sit ON the two peaks, so their
+// PAF vectors depend on the peak and the limb only, not on the pair: nA + nB evaluations per limb instead of
+// 2 * nA * nB. end_paf[((n * nlimbs + k) * 2 + side) * cap + peak] = (x component, y component).
+__global__ void __launch_bounds__(128)
+paf_endpoints_kernel(const ScaleSet ss, const LimbTable lt, int W, int parts, const GroupBuffers gb) {
+  __shared__ float s_tab[8][4];
+  fill_phase_table(s_tab);
+  __syncthreads();
+  const int n = blockIdx.z;
+  const int k = blockIdx.y >> 1, side = blockIdx.y & 1;
+  const int part = side ? lt.b[k] : lt.a[k];
+  const int cnt = min(gb.counts[n * parts + part], gb.cap);
+  const uint32_t* keys = gb.keys + static_cast<long long>(n * parts + part) * gb.cap;
+  double2* out = reinterpret_cast<double2*>(gb.end_paf) + (static_cast<long long>(n * lt.nlimbs + k) * 2 + side) * gb.cap;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+    const uint32_t key = keys[i];
+    double vx, vy;
+    paf_at(ss, s_tab, n, static_cast<int>(key % W), static_cast<int>(key / W), lt.cx[k], lt.cy[k], W, vx, vy);
+    out[i] = make_double2(vx, vy);
+  }
+}
+
+// One group of 8 lanes per candidate pair: the 8 interior samples (t = 1..8) in parallel, the two end samples from
+// end_paf. A pair whose two end samples both fail criterion1's threshold cannot reach the required 9 of 10
+// (body.py:158) and is rejected before any interior sample is evaluated - on noisy maps that is most pairs. Every
+// group walks its own sequence of pairs and skips the rejected ones, so the four groups of a warp always sample
+// four surviving pairs together. Scores are written into the dense nA x nB matrix exactly as before.
 __global__ void __launch_bounds__(256)
 paf_score_kernel(const ScaleSet ss, const LimbTable lt, int H, int W, int parts, double thre2, const GroupBuffers gb) {
   __shared__ float s_tab[8][4];
@@ -30,67 +80,70 @@ paf_score_kernel(const ScaleSet ss, const LimbTable lt, int H, int W, int parts,
     if (threadIdx.x == 0 && blockIdx.x == 0) atomicMax(gb.overflow, 3);
     return;
   }
+  if (nA > gb.cap || nB > gb.cap) return;  // peak overflow is flagged by the peak kernel
   const uint32_t* keyA = gb.keys + static_cast<long long>(n * parts + pa) * gb.cap;
   const uint32_t* keyB = gb.keys + static_cast<long long>(n * parts + pb) * gb.cap;
-  const int C = ss.channels;
-  const long long tail_start = (static_cast<long long>(W) * C) / 4 * 4;
-  const float fS = static_cast<float>(ss.count);
   const int slot_base = n * lt.nlimbs + k;
+  const double2* endA = reinterpret_cast<const double2*>(gb.end_paf) + static_cast<long long>(slot_base) * 2 * gb.cap;
+  const double2* endB = endA + gb.cap;
+  double* scores = gb.pair_score + static_cast<long long>(slot_base) * gb.pair_cap;
   const int chx = lt.cx[k], chy = lt.cy[k];
 
-  // three pairs per warp: lane = 10 * group + sample; one lane evaluates both PAF channels of its sample
-  // (they share the cubic taps of the sample position)
-  const int grp = lane / 10;
-  const int t = lane - grp * 10;
-  const int gbase = grp * 10;
-  for (long long base = (static_cast<long long>(blockIdx.x) * 8 + warp) * 3; base < total;
-       base += static_cast<long long>(gridDim.x) * 8 * 3) {
-    const long long pair = base + grp;
-    const bool live = grp < 3 && pair < total;
-    double mid = 0.0, norm = 1.0;
-    if (live) {
+  const int grp = lane >> 3;        // 4 pairs per warp
+  const int t = (lane & 7) + 1;     // this lane's interior sample
+  const unsigned gmask = 0xffu << (grp * 8);
+  const long long stride = static_cast<long long>(gridDim.x) * 32;
+  long long pair = (static_cast<long long>(blockIdx.x) * 8 + warp) * 4 + grp;
+  while (true) {
+    // ---- next pair of this group that survives the end-sample test
+    bool have = false;
+    double mid0 = 0.0, mid9 = 0.0, ux = 0.0, uy = 0.0, norm = 1.0;
+    int ax = 0, ay = 0, bx = 0, by = 0;
+    long long dxi = 0, dyi = 0;
+    while (pair < total) {
       const int i = static_cast<int>(pair / nB);
       const int j = static_cast<int>(pair - static_cast<long long>(i) * nB);
       const uint32_t ka = keyA[i], kb = keyB[j];
-      const int ax = ka % W, ay = ka / W, bx = kb % W, by = kb / W;
-      const long long dxi = bx - ax, dyi = by - ay;
+      ax = ka % W, ay = ka / W, bx = kb % W, by = kb / W;
+      dxi = bx - ax, dyi = by - ay;
       norm = fmax(0.001, sqrt(static_cast<double>(dxi * dxi + dyi * dyi)));
-      const double ux = __ddiv_rn(static_cast<double>(dxi), norm);
-      const double uy = __ddiv_rn(static_cast<double>(dyi), norm);
-      // np.linspace(a, b, 10): t * ((b - a) / 9) + a, last sample forced to b
+      ux = __ddiv_rn(static_cast<double>(dxi), norm);
+      uy = __ddiv_rn(static_cast<double>(dyi), norm);
+      const double2 ea = endA[i], eb = endB[j];
+      mid0 = __dadd_rn(__dmul_rn(ea.x, ux), __dmul_rn(ea.y, uy));
+      mid9 = __dadd_rn(__dmul_rn(eb.x, ux), __dmul_rn(eb.y, uy));
+      if (mid0 > thre2 || mid9 > thre2) {
+        have = true;
+        break;
+      }
+      if (t == 1) scores[pair] = -1.0;  // at most 8 of 10 samples can pass: not a candidate
+      pair += stride;
+    }
+    if (!__any_sync(0xffffffffu, have)) break;
+    double mid = 0.0;
+    if (have) {
+      // np.linspace(a, b, 10): t * ((b - a) / 9) + a for the interior samples
       const double stepx = __ddiv_rn(static_cast<double>(dxi), 9.0);
       const double stepy = __ddiv_rn(static_cast<double>(dyi), 9.0);
-      const double xs = t == 9 ? static_cast<double>(bx) : __dadd_rn(__dmul_rn(static_cast<double>(t), stepx), static_cast<double>(ax));
-      const double ys = t == 9 ? static_cast<double>(by) : __dadd_rn(__dmul_rn(static_cast<double>(t), stepy), static_cast<double>(ay));
-      const int rx = static_cast<int>(rint(xs));  // int(round()) = round half to even
-      const int ry = static_cast<int>(rint(ys));
-      const bool tailx = static_cast<long long>(rx) * C + chx >= tail_start;
-      const bool taily = static_cast<long long>(rx) * C + chy >= tail_start;
-      double vx = 0.0, vy = 0.0;
-      for (int s = 0; s < ss.count; ++s) {
-        const ScaleGeom& g = ss.g[s];
-        Axis2 sx, sy;
-        make_axis2(rx, g.sx, g.wc, g.gw, s_tab, sx);
-        make_axis2(ry, g.sy, g.hc, g.gh, s_tab, sy);
-        const float* img = g.low + static_cast<long long>(n) * C * g.gh * g.gw;
-        const long long plane = static_cast<long long>(g.gh) * g.gw;
-        // paf_avg += paf / S  (body.py:81): float32 division, float64 accumulation
-        vx = __dadd_rn(vx, static_cast<double>(__fdiv_rn(sample2(img + chx * plane, g.gw, sx, sy, tailx), fS)));
-        vy = __dadd_rn(vy, static_cast<double>(__fdiv_rn(sample2(img + chy * plane, g.gw, sx, sy, taily), fS)));
-      }
+      const double xs = __dadd_rn(__dmul_rn(static_cast<double>(t), stepx), static_cast<double>(ax));
+      const double ys = __dadd_rn(__dmul_rn(static_cast<double>(t), stepy), static_cast<double>(ay));
+      double vx, vy;
+      paf_at(ss, s_tab, n, static_cast<int>(rint(xs)), static_cast<int>(rint(ys)), chx, chy, W, vx, vy);  // int(round())
       mid = __dadd_rn(__dmul_rn(vx, ux), __dmul_rn(vy, uy));
     }
-    const unsigned above = __ballot_sync(0xffffffffu, live && mid > thre2);
-    double sum = 0.0;  // Python sum(): left to right from 0
+    const unsigned above = __ballot_sync(0xffffffffu, have && mid > thre2) & gmask;
+    double sum = __dadd_rn(0.0, mid0);  // Python sum(): left to right from 0
 #pragma unroll
-    for (int q = 0; q < 10; ++q) sum = __dadd_rn(sum, __shfl_sync(0xffffffffu, mid, (gbase + q) & 31));
-    if (live && t == 0) {
+    for (int q = 0; q < 8; ++q) sum = __dadd_rn(sum, __shfl_sync(0xffffffffu, mid, grp * 8 + q));
+    sum = __dadd_rn(sum, mid9);
+    if (have && t == 1) {
       const double prior = __dadd_rn(__ddiv_rn(sum, 10.0),
                                      fmin(__dsub_rn(__ddiv_rn(__dmul_rn(0.5, static_cast<double>(H)), norm), 1.0), 0.0));
-      const int cnt = __popc((above >> gbase) & 0x3ffu);
+      const int cnt = __popc(above) + (mid0 > thre2 ? 1 : 0) + (mid9 > thre2 ? 1 : 0);
       // > 0.8 * mid_num samples above thre2 and a positive score, else the pair is not a candidate
-      gb.pair_score[static_cast<long long>(slot_base) * gb.pair_cap + pair] = (cnt > 8 && prior > 0.0) ? prior : -1.0;
+      scores[pair] = (cnt > 8 && prior > 0.0) ? prior : -1.0;
     }
+    if (have) pair += stride;
   }
 }
 
@@ -407,6 +460,8 @@ assemble_kernel(const LimbTable lt, int W, const GroupBuffers gb) {
 int launch_paf_score(const ScaleSet& paf, const LimbTable& lt, int N, int H, int W, double thre2, int mid_num,
                      const GroupBuffers& gb, cudaStream_t st) {
   if (mid_num != 10 || gb.cap > kPeakCap) return 1;
+  if (gb.end_paf == nullptr) return 1;
+  paf_endpoints_kernel<<<dim3(8, lt.nlimbs * 2, N), 128, 0, st>>>(paf, lt, W, lt.njoint - 1, gb);
   const dim3 grid(48, lt.nlimbs, N);
   paf_score_kernel<<<grid, 256, 0, st>>>(paf, lt, H, W, lt.njoint - 1, thre2, gb);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;

@@ -45,6 +45,7 @@ struct GroupBuffers {
   // scratch: dense connection scores per (frame, limb): [i*nB+j] = score, or -1 when the pair is rejected
   long long pair_cap;    // elements available per (frame, limb); nA*nB above this raises overflow code 3
   double* pair_score;    // [N*nlimbs*pair_cap]
+  double* end_paf;       // [N*nlimbs*2*cap*2] scratch: PAF vector of each limb at each of its end peaks
   // scratch: chosen connections per (frame, limb)
   int* conn_count;       // [N*nlimbs]
   int* conn_ij;          // [N*nlimbs*cap*2]
