@@ -57,7 +57,7 @@ def peaks():
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant conv kernel from the committed
 # `ncu --set full` capture (profiles/): filled in by hand from the capture, None until one exists for this round
-CONV_DRAM_TRAFFIC = 38.69e6   # v5, 7x7 128->128, 92x164x8: 35.58 MB read + 3.12 MB written (profiles/r1_ncu_full_conv7x7_v5.txt)
+CONV_DRAM_TRAFFIC = 39.79e6   # v5, 7x7 128->128, 92x164x8: 36.10 MB read + 3.69 MB written (profiles/r1_ncu_full_conv7x7_v5.txt)
 
 
 class ClockSampler(threading.Thread):
