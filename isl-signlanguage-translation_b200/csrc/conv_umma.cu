@@ -973,10 +973,15 @@ conv_umma_halo_swapped_kernel(const __grid_constant__ CUtensorMap tmX, const __g
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_g;
+  // Programmatic dependent launch: the set-up above (barriers, TMEM, descriptor prefetch) overlapped the tail of the
+  // previous layer; its output is first touched by the halo loads below, and this layer's stores come after MMAs that
+  // consumed those loads, so one wait in the producer warp orders everything.
+  ptx::pdl_launch_dependents();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (whole warp, one elected lane issues)
     {
+      ptx::pdl_wait();
       ptx::RingPos r(bar_wfull, bar_wempty, a.stages);
       uint32_t sw = sW0;
       uint32_t hb = 0, hph = 0;
@@ -1559,7 +1564,18 @@ int conv_run(const ConvLaunch& l, cudaStream_t stream) {
   } else if (l.variant == 4) {
     conv_umma_swapped_kernel<<<l.grid, kThreads, l.smem_bytes, stream>>>(l.tmA, l.tmB, l.tmC, l.args);
   } else if (l.variant == 5) {
-    conv_umma_halo_swapped_kernel<<<l.grid, kThreads, l.smem_bytes, stream>>>(l.tmA, l.tmB, l.args);
+    static const bool no_pdl = getenv("ISLPOSE_NO_PDL") != nullptr;  // A/B measurement aid
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = l.grid;
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = l.smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = no_pdl ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, conv_umma_halo_swapped_kernel, l.tmA, l.tmB, l.args) == cudaSuccess ? 0 : 1;
   } else {
     conv_umma_kernel<<<l.grid, kThreads, l.smem_bytes, stream>>>(l.tmA, l.tmB, l.tmC, l.args);
   }
