@@ -20,6 +20,7 @@ namespace islpose {
 namespace {
 
 constexpr int kThreads = 192;
+constexpr int kThreadsV1 = 320;  // v1: eight epilogue warps (two per TMEM lane quarter, alternating 32-column chunks)
 constexpr uint32_t kASlotBytes = 128 * 128;  // 128 pixel rows x 64 bf16
 constexpr int kMaxStages = 8;
 constexpr uint32_t kCtrlBytes = 256 + 2 * 256 * 4;  // barriers + bias + slope
@@ -44,7 +45,7 @@ __device__ __forceinline__ void issue_kblock(uint32_t d, uint64_t da, uint64_t d
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreadsV1, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const ConvArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -94,7 +95,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     ptx::tmem_relinquish();
   }
   if (warp >= 2) {
-    for (int i = threadIdx.x - 64; i < a.n_tile; i += kThreads - 64) {
+    for (int i = threadIdx.x - 64; i < a.n_tile; i += kThreadsV1 - 64) {
       s_bias[i] = a.bias[n0 + i];
       s_slope[i] = a.slope[n0 + i];
     }
@@ -189,7 +190,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     ptx::mbar_wait(bar_accum, 0);
     ptx::tc_fence_after();
 
-    for (int c = 0; c < a.n_tile; c += 32) {
+    // Layers with a short K loop (1x1) spend longer here than in the MMAs, and one warp per scheduler issues an
+    // instruction every ~4 cycles at best: two warps share each TMEM lane quarter and take alternate 32-column chunks.
+    for (int c = ((warp - 2) >> 2) * 32; c < a.n_tile; c += 64) {
       uint32_t r[32];
       ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, r);
       ptx::tmem_ld_wait();
@@ -254,7 +257,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     if (a.tma_store) {
       ptx::fence_proxy_async_smem();
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps
       if (threadIdx.x == 64) {
         for (int b = 0; b * 64 < a.n_tile; ++b) {
           if (n0 + b * 64 < a.cout_store) ptx::tma_store_4d(&tmC, sA0 + b * kASlotBytes, n0 + b * 64, x0, y0, img);
@@ -1577,7 +1580,7 @@ int conv_run(const ConvLaunch& l, cudaStream_t stream) {
     cfg.numAttrs = no_pdl ? 0 : 1;
     return cudaLaunchKernelEx(&cfg, conv_umma_halo_swapped_kernel, l.tmA, l.tmB, l.args) == cudaSuccess ? 0 : 1;
   } else {
-    conv_umma_kernel<<<l.grid, kThreads, l.smem_bytes, stream>>>(l.tmA, l.tmB, l.tmC, l.args);
+    conv_umma_kernel<<<l.grid, kThreadsV1, l.smem_bytes, stream>>>(l.tmA, l.tmB, l.tmC, l.args);
   }
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
