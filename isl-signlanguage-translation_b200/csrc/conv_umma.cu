@@ -921,7 +921,7 @@ conv_umma_swapped_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 //   * halo buffers and TMEM accumulators are double buffered and the CTA is persistent (one per SM), so the halo
 //     fetch of the next channel block, the epilogue of the previous work item and the weight stream all overlap
 //     the MMAs. Epilogue lane = output channel; 32 lanes store 32 neighbouring channels of one pixel.
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreadsV1, 1)
 conv_umma_halo_swapped_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                               const ConvArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -962,7 +962,7 @@ conv_umma_halo_swapped_kernel(const __grid_constant__ CUtensorMap tmX, const __g
       ptx::mbar_init(bar_hfull + 8 * b, 1);
       ptx::mbar_init(bar_hempty + 8 * b, 1);
       ptx::mbar_init(bar_acc_full + 8 * b, 1);
-      ptx::mbar_init(bar_acc_empty + 8 * b, 4);  // one arrival per epilogue warp
+      ptx::mbar_init(bar_acc_empty + 8 * b, 8);  // one arrival per epilogue warp
     }
     ptx::mbar_fence_init();
     ptx::prefetch_tensormap(&tmX);
@@ -1089,7 +1089,8 @@ conv_umma_halo_swapped_kernel(const __grid_constant__ CUtensorMap tmX, const __g
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 2..5): lane = output channel
+    // ------------------------------------------------------------ epilogue (warps 2..9): lane = output channel; the two
+    // warps of a TMEM lane quarter take alternate 32-pixel chunks (short-K layers are bound by this loop)
     const int q = warp & 3;
     const int chl = q * 32 + lane;
     uint32_t buf = 0, buf_ph = 0;
@@ -1119,7 +1120,7 @@ conv_umma_halo_swapped_kernel(const __grid_constant__ CUtensorMap tmX, const __g
         // image rows x 8 pixels of this thread's channel, i.e. 2 x 4 complete pooling windows (tile origin and height
         // are even). max() commutes with the monotonic bf16 rounding, so the result equals pooling the stored layer.
         const int Hp = a.H >> 1, Wp = a.W >> 1;
-        for (int c = 0; c < a.n_pix; c += 32) {
+        for (int c = ((warp - 2) >> 2) * 32; c < a.n_pix; c += 64) {
           uint32_t r[32];
           ptx::tmem_ld_32x32(acc + c, r);
           ptx::tmem_ld_wait();
@@ -1147,7 +1148,7 @@ conv_umma_halo_swapped_kernel(const __grid_constant__ CUtensorMap tmX, const __g
           }
         }
       } else
-      for (int c = 0; c < a.n_pix; c += 32) {
+      for (int c = ((warp - 2) >> 2) * 32; c < a.n_pix; c += 64) {
         uint32_t r[32];
         ptx::tmem_ld_32x32(acc + c, r);
         ptx::tmem_ld_wait();
@@ -1570,7 +1571,7 @@ int conv_run(const ConvLaunch& l, cudaStream_t stream) {
     static const bool no_pdl = getenv("ISLPOSE_NO_PDL") != nullptr;  // A/B measurement aid
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = l.grid;
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(kThreadsV1);
     cfg.dynamicSmemBytes = l.smem_bytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
