@@ -1,12 +1,18 @@
-// tcgen05 / TMEM / TMA implicit-GEMM convolution (see conv_umma.cuh for the data layout).
+// tcgen05 / TMEM / TMA implicit-GEMM convolution (see conv_umma.cuh for the data layout, DESIGN.md section 4.1 for
+// the measurements behind every choice).
 //
-// Warp roles inside one 192-thread CTA (one output tile of <=128 pixels x n_tile channels):
-//   warp 0      : TMA producer  (one lane) - walks (tap, 64-channel block) and fills the smem ring
-//   warp 1      : TMEM owner + MMA issuer (one lane) - tcgen05.mma per K=16 slice, tcgen05.commit
-//                 releases ring slots and finally signals the epilogue
-//   warps 2..5  : epilogue - tcgen05.ld the accumulator (warp w may only touch TMEM lanes
-//                 32*(w%4)..+31), bias + ReLU/PReLU, bf16 pack, 16-byte stores into the NHWC slice;
-//                 network heads additionally (or only) store fp32.
+// Variants (conv_prepare picks one per layer):
+//   v5  swapped operands + resident activation halo, persistent: every 3x3 / 7x7 layer with >= 64 input and >= 48
+//       output channels (~97 % of the FLOPs); bias / ReLU / PReLU / bf16 / slice write / 2x2 max-pool in the epilogue
+//   v1  one pixel tile per CTA, two CTAs per SM: 1x1 layers and the float32 network heads
+//   v2  persistent, double-buffered TMEM, two pixel sub-tiles per weight stage: narrow 1x1 heads on large grids
+//   v3, v4  earlier halo / swapped-operand kernels, selectable for A/B measurements (conv_test), not chosen automatically
+//           (v4 only with ISLPOSE_NO_V5)
+// Warp roles in every variant:
+//   warp 0      : TMA producer - the whole warp runs the loop with warp-uniform state, one elected lane issues
+//   warp 1      : TMEM owner + MMA issuer - same pattern; tcgen05.commit releases ring slots and signals the epilogue
+//   warps 2..   : epilogue (4 or 8 warps) - tcgen05.ld the accumulator (warp w may only touch TMEM lanes
+//                 32*(w%4)..+31), bias + ReLU/PReLU, bf16, stores into the NHWC slice; network heads store fp32.
 #include "conv_umma.cuh"
 
 #include <stdio.h>
@@ -26,9 +32,9 @@ constexpr int kMaxStages = 8;
 constexpr uint32_t kCtrlBytes = 256 + 2 * 256 * 4;  // barriers + bias + slope
 
 // The four K=16 MMAs of one 64-channel block, fully unrolled with constant descriptor offsets (+32 bytes along K
-// inside the 128-byte swizzle row = +2 in the >>4 address field). The issue loops run on ONE lane: every instruction
-// in them is on the critical path of the tensor pipe (build/mma_rate: a lean loop issues a K-block in ~70 cycles per
-// MMA; runtime divisions and per-MMA predicate set-up had pushed that to ~270). No division, no variable trip
+// inside the 128-byte swizzle row = +2 in the >>4 address field). Every instruction of an issue loop is on the
+// critical path of the tensor pipe (build/mma_rate: a lean loop issues an MMA every ~70 cycles; runtime divisions and
+// per-MMA operand broadcasts from one lane's registers had pushed that to ~270). No division, no variable trip
 // count, no per-MMA predicate in the common case.
 __device__ __forceinline__ void issue_kblock4(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, bool accumulate_first) {
   ptx::umma_bf16(d, da, db, idesc, accumulate_first ? 1u : 0u);
@@ -524,7 +530,7 @@ conv_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
 // shared memory: the A operand of tap (ky, kx) starts at halo row ky*16 + kx, its 8-row groups (one image row of
 // the tile each) are 16 rows = 2048 B apart, and the swizzle is a function of the absolute shared-memory
 // address (TMA wrote it that way, the MMA reads it that way), so the descriptor's base offset stays 0. Only the weights stream from L2 per tap, which cuts the bytes delivered to the SM per FLOP by ~45 %
-// (7x7) / ~30 % (3x3) - the v1 kernel is bound by L2->SM delivery (profiles/r1_ncu_full_conv7x7_v1.txt).
+// (7x7) / ~30 % (3x3). Superseded by v5 (same idea with the weights as the M operand and a persistent CTA).
 __global__ void __launch_bounds__(kThreads, 2)
 conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const ConvArgs a) {
@@ -1342,8 +1348,8 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   }
 
   if (d.pool) return fail(err, errlen, "conv: fused pooling is only available in the halo variant (k >= 3, Cin >= 64, Cout >= 48, bf16 output)");
-  // Cost model fitted to the measurements in profiles/ (cycles per CTA): a tcgen05.mma of M=128 x N x K=16 costs about
-  // 207 + N/2 when the CTA has its SM to itself and 192 + N when two CTAs share the SM; `epi` is the epilogue.
+  // Legacy v1-versus-v4 model (only reached when v5 is switched off or not applicable): fitted to the first-generation
+  // issue loops, where an MMA cost about 207 + N/2 cycles alone and 192 + N with two CTAs per SM; `epi` is the epilogue.
   const int kblocks = d.ksize * d.ksize * ((d.in_c + 63) / 64);
   auto estimate = [&](long long tiles, int n, double epi) {
     const double per_mma = tiles <= 148 ? 207.0 + n / 2.0 : 192.0 + n;

@@ -229,3 +229,13 @@ def test_pipeline_and_chunks_equal_the_serial_path(dev, coco, hand):
 def test_clip_features_on_device(dev, coco, hand):
     X = KeypointExtractor(coco, hand).features([synth.synth_frame(64, 80, 70 + i) for i in range(5)], batch_size=2)
     assert X.shape == (5, 156) and X.dtype == np.float64 and np.isfinite(X).all()
+
+
+def test_negative_stride_frames_and_rgb_views(dev, coco):
+    """Callers pass views such as frame[:, :, ::-1] (extract_features.py:163): same result as the contiguous copy."""
+    frame = synth.synth_frame(72, 96, 91)
+    view = frame[:, :, ::-1]
+    assert view.strides[2] < 0
+    c1, s1 = coco(view)
+    c2, s2 = coco(np.ascontiguousarray(view))
+    assert c1.shape == c2.shape and np.array_equal(c1, c2) and np.array_equal(s1, s2)
