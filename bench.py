@@ -6,7 +6,8 @@
 A step = one pass of body + hand extraction over one batch of synthetic frames per rank (frames shard across ranks,
 no collective on the data path; scaling is weak). Workloads (BASELINE.json configs):
   C2  coco body + hand, 640x480, scale_search [0.5,1,1.5,2], two fixed hand boxes per frame      (default)
-  C3  body25 + hand, 1280x720, same scales, two 128-px hand boxes per frame
+  C3  body25 + hand, 1280x720, same scales, two 128-px hand boxes per frame (C4's clips are batches of C3 frames)
+  C5  body25 + hand, 1920x1080, same scales, 40 hand boxes per frame (the multi-person stress shape)
 Hand boxes are fixed per workload because random-init weights never produce a person for util.handDetect.
 
 value   frames/s with the frames already resident in HBM (device-timed, max over ranks)
@@ -38,13 +39,16 @@ WORKLOADS = {
     # name: (model_type, H, W, hand boxes [x, y, w, is_left], default batch per rank)
     "C2": ("coco", 480, 640, [[400, 250, 109, True], [22, 246, 90, False]], 16),
     "C3": ("body25", 720, 1280, [[800, 300, 128, True], [300, 300, 128, False]], 16),
+    # C5 (BASELINE.json configs[4]): 1080p, "20+ people" = 40 hand crops per frame on a fixed 8 x 5 lattice, 96..127 px
+    "C5": ("body25", 1080, 1920, [[40 + 230 * (i % 8), 60 + 200 * (i // 8), 96 + (7 * i) % 32, i % 2 == 0] for i in range(40)], 4),
 }
 
 
 def workload_name(wl, batch):
     mt, H, W, boxes, _ = WORKLOADS[wl]
+    sizes = ",".join("%dpx" % b[2] for b in boxes) if len(boxes) <= 4 else "%d..%dpx" % (min(b[2] for b in boxes), max(b[2] for b in boxes))
     return "%s: %s body + hand, %dx%d, scale_search %s, %d hand boxes/frame (%s), batch %d frames/step/rank" % (
-        wl, mt, W, H, SCALES, len(boxes), ",".join("%dpx" % b[2] for b in boxes), batch)
+        wl, mt, W, H, SCALES, len(boxes), sizes, batch)
 
 
 def peaks():
