@@ -265,7 +265,8 @@ def main():
                 lanes[2 + ci % 2].wait_event(ready)
                 crops = [frames_dev[a + i, y:y + w, x:x + w, :].contiguous() for i in range(sub.shape[0]) for (x, y, w, _) in boxes]
                 hand.model.timing = []
-                hand.network_outputs(crops, lane=ci % 2)
+                for ca in range(0, len(crops), hand.MAX_CROPS_PER_REPLAY):   # as Hand.enqueue replays them
+                    hand.network_outputs(crops[ca:ca + hand.MAX_CROPS_PER_REPLAY], lane=ci % 2)
                 flops += sum(t[2] for t in hand.model.timing)
         for st in lanes:
             main.wait_stream(st)

@@ -126,32 +126,38 @@ class Hand(object):
         with torch.cuda.device(self.device):
             return self.batch_device([torch.from_numpy(c).to(self.device, non_blocking=True) for c in crops])
 
+    MAX_CROPS_PER_REPLAY = 32   # crops per network replay: bounds the plan buffers (2.2 GB per 64-channel full-resolution
+                                # buffer at 32 x 736 x 736); more crops run as consecutive replays of the same plans
+
     def enqueue(self, dev_crops, lane=0):
         """Launches the four network scales and the key-point selection of every crop (list of contiguous uint8
         cuda tensors [h,w,3]) without waiting; finish(ticket) returns the list of int64 [21,2] arrays."""
         if not dev_crops:
             return None
         with torch.cuda.device(self.device):
-            per_crop = self.network_outputs(dev_crops, lane)
-            # a crop's post-processing launches only 21 CTAs per kernel: spread the crops over a few streams
             main = torch.cuda.current_stream()
-            fork = torch.cuda.Event()
-            fork.record(main)
-            lanes = min(len(dev_crops), 8)
-            streams = self._streams.setdefault(lane, [])
-            while len(streams) < lanes:
-                streams.append(torch.cuda.Stream(device=self.device))
             outs = []
-            for i in range(len(dev_crops)):
-                side = streams[i % lanes] if lanes > 1 else main
-                with torch.cuda.stream(side):
-                    side.wait_event(fork)
-                    outs.append(self.postprocess(per_crop[i], dev_crops[i].shape[0], dev_crops[i].shape[1]))
-            if lanes > 1:
-                for j in range(lanes):
-                    done = torch.cuda.Event()
-                    done.record(streams[j])
-                    main.wait_event(done)
+            for a in range(0, len(dev_crops), self.MAX_CROPS_PER_REPLAY):
+                part = dev_crops[a:a + self.MAX_CROPS_PER_REPLAY]
+                per_crop = self.network_outputs(part, lane)
+                # a crop's post-processing launches only 21 CTAs per kernel: spread the crops over a few streams; the
+                # join below also keeps the next replay from overwriting network outputs that are still being read
+                fork = torch.cuda.Event()
+                fork.record(main)
+                lanes = min(len(part), 8)
+                streams = self._streams.setdefault(lane, [])
+                while len(streams) < lanes:
+                    streams.append(torch.cuda.Stream(device=self.device))
+                for i in range(len(part)):
+                    side = streams[i % lanes] if lanes > 1 else main
+                    with torch.cuda.stream(side):
+                        side.wait_event(fork)
+                        outs.append(self.postprocess(per_crop[i], part[i].shape[0], part[i].shape[1]))
+                if lanes > 1:
+                    for j in range(lanes):
+                        done = torch.cuda.Event()
+                        done.record(streams[j])
+                        main.wait_event(done)
             stacked = torch.stack(outs)
             host = torch.empty(stacked.shape, dtype=stacked.dtype).pin_memory()
             host.copy_(stacked, non_blocking=True)

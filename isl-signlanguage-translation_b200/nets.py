@@ -246,9 +246,35 @@ class _Instance:
         self.input = torch.empty((n, 3, h, w), dtype=torch.float32, device=dev)
         self.bufs = {}
         fused_first = not net.tuning.get("unfused_first", False)
+        fuse_pool = not net.tuning.get("unfused_pool", False)
+        steps = net.program.steps
+
+        def pool_fusable(si):
+            """conv step si followed by a max-pool of its own output, in a shape the halo kernel takes (conv_prepare)."""
+            s, nxt = steps[si][1], steps[si + 1] if si + 1 < len(steps) else None
+            return (fuse_pool and nxt is not None and nxt[0] == "pool" and s["dst"] is not None and nxt[1] == s["dst"][0]
+                    and s["k"] >= 3 and s["src"][2] >= 64 and s["cout"] >= 48 and s["f32"] is None and not s["first"])
+
+        # buffers some launch actually touches (a fused first layer needs no patch buffer, a fused pool no full-size output)
+        used = set()
+        for si, step in enumerate(steps):
+            if step[0] == "im2col":
+                if not fused_first:
+                    used.add(step[1])
+            elif step[0] == "pool":
+                if not (si > 0 and steps[si - 1][0] == "conv" and pool_fusable(si - 1)):
+                    used.update((step[1], step[2]))
+            else:
+                s = step[1]
+                if not (s["first"] and fused_first):
+                    used.add(s["src"][0])
+                if pool_fusable(si):
+                    used.add(steps[si + 1][2])
+                elif s["dst"] is not None:
+                    used.add(s["dst"][0])
         for name, (ch, level) in net.program.bufs.items():
-            if name == "x32" and fused_first:
-                continue   # the fused first layer gathers its patches itself
+            if name not in used:
+                continue
             # physical width rounded up to 64 channels (zeros, never written): every 64-channel box is in bounds
             self.bufs[name] = torch.zeros((n, h >> level, w >> level, _up64(ch) if ch > 32 else ch), dtype=torch.bfloat16,
                                           device=dev)
@@ -258,8 +284,6 @@ class _Instance:
         _lib.check(L.islpose_plan_create(C.byref(handle)), "islpose_plan_create")
         self.handle = handle
         ci = 0
-        steps = net.program.steps
-        fuse_pool = not net.tuning.get("unfused_pool", False)
         fused_pools = set()
         self.op_names = []   # one name per recorded launch (tools/layer_times.py)
         for si, step in enumerate(steps):
@@ -300,11 +324,9 @@ class _Instance:
                 d.ksize = 1 if s["first"] else s["k"]
                 d.bias = bias.data_ptr()
                 d.slope = slope.data_ptr()
-                nxt = steps[si + 1] if si + 1 < len(steps) else None
-                if (fuse_pool and nxt is not None and nxt[0] == "pool" and s["dst"] is not None and nxt[1] == s["dst"][0]
-                        and s["k"] >= 3 and s["src"][2] >= 64 and s["cout"] >= 48 and s["f32"] is None and not s["first"]):
+                if pool_fusable(si):
                     # nn.MaxPool2d(2, 2) fused into this layer's epilogue: the full-resolution tensor is never written
-                    db = self.bufs[nxt[2]]
+                    db = self.bufs[steps[si + 1][2]]
                     d.out_bf16 = db.data_ptr()
                     d.out_cstride = db.shape[3]
                     d.pool = 1
