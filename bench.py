@@ -106,8 +106,8 @@ def cpu_reference_frame(wl, seed, nets=None):
     mt, H, W, boxes, _ = WORKLOADS[wl]
     if nets is None:
         torch.set_num_threads(os.cpu_count() or 1)
-        nets = (O.make_net_fn(mt, O.make_flat_weights(mt, seed=0, init=WEIGHT_INIT)),
-                O.make_net_fn("hand", O.make_flat_weights("hand", seed=0, init=WEIGHT_INIT)))
+        nets = (O.make_net_fn(mt, synth.make_flat_weights(mt, seed=0, init=WEIGHT_INIT)),
+                O.make_net_fn("hand", synth.make_flat_weights("hand", seed=0, init=WEIGHT_INIT)))
     frame = synth.synth_frame(H, W, seed)
     t0 = time.perf_counter()
     try:
@@ -179,7 +179,6 @@ def main():
     import isl_b200
     from isl_b200 import _lib, synth
     from isl_b200.extract import KeypointExtractor
-    from oracle import openpose_oracle as O  # weights generator only on this path; the oracle runs in cpu_baseline
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -190,8 +189,8 @@ def main():
 
     mt, H, W, boxes, default_batch = WORKLOADS[args.workload]
     B = args.batch or default_batch
-    body = isl_b200.Body(O.make_flat_weights(mt, seed=0, init=WEIGHT_INIT), mt, scale_search=SCALES)
-    hand = isl_b200.Hand(O.make_flat_weights("hand", seed=0, init=WEIGHT_INIT))
+    body = isl_b200.Body(synth.make_flat_weights(mt, seed=0, init=WEIGHT_INIT), mt, scale_search=SCALES)
+    hand = isl_b200.Hand(synth.make_flat_weights("hand", seed=0, init=WEIGHT_INIT))
     ex = KeypointExtractor(body, hand, chunk=args.chunk or None)
     hand_boxes = [boxes] * B
 

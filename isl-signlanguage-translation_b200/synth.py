@@ -102,3 +102,38 @@ def render_hand_maps(points, gh, gw, sigma=1.0, peak=0.9):
         heat[j] = peak * np.exp(-((xs - cx) ** 2 + (ys - cy) ** 2) / (2 * sigma * sigma))
     heat[21] = 1.0 - heat[:21].max(0)
     return heat.astype(np.float32)
+
+
+def make_flat_weights(kind, seed=0, init="torch", gain=1.0, head_gain=1.0):
+    """Seeded random weights in the reference's on-disk format - a flat dict of Caffe layer names
+    ('conv1_1.weight', 'Mprelu1_stage0_L2_0.weight', ...) -> float32 tensors (what torch.load returns for the shipped
+    .pth files, body.py:35-36). No trained weights ship with the reference, so benchmarks and tools run on these.
+      init="torch": the distribution nn.Conv2d / nn.PReLU are constructed with (U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for
+                    weight and bias, PReLU slope 0.25): SURVEY.md section 8d's "random-init weights"
+      init="he":    He-uniform scaled by `gain` (activations stay alive, thousands of peaks: a stress input)
+    Layers come from the launch program (nets.build_program), in network order."""
+    import math
+
+    import torch
+
+    from .nets import build_program
+
+    g = torch.Generator().manual_seed(seed)
+    w = {}
+    for step in build_program(kind).steps:
+        if step[0] != "conv" or step[1]["layer"] + ".weight" in w:
+            continue
+        s = step[1]
+        name, cout, k = s["layer"], s["cout"], s["k"]
+        cin = 3 if s["first"] else (sum(1 for c in s["chan_map"] if c is not None) if s["chan_map"] else s["src"][2])
+        if init == "torch":
+            bound = bias_bound = 1.0 / math.sqrt(cin * k * k)
+        else:
+            bound, bias_bound = gain * math.sqrt(6.0 / (cin * k * k)), 0.05
+            if name.startswith("Mconv7") or name in ("conv5_5_CPM_L1", "conv5_5_CPM_L2", "conv6_2_CPM"):
+                bound *= head_gain
+        w[name + ".weight"] = (torch.rand((cout, cin, k, k), generator=g) * 2 - 1) * bound
+        w[name + ".bias"] = (torch.rand((cout,), generator=g) * 2 - 1) * bias_bound
+        if s["prelu"] is not None:
+            w[s["prelu"] + ".weight"] = torch.full((cout,), 0.25) if init == "torch" else torch.rand((cout,), generator=g) * 0.3
+    return w

@@ -5,12 +5,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import isl_b200
 from isl_b200 import synth
-from oracle import openpose_oracle as O
 
 torch.cuda.set_device(0)
 poison = [torch.full((256 * 1024 * 1024,), float("nan"), device="cuda") for _ in range(8)]   # 8 GiB of NaN
 del poison
-hand = isl_b200.Hand(O.make_flat_weights("hand", seed=2))
+hand = isl_b200.Hand(synth.make_flat_weights("hand", seed=2))
 crops = [synth.synth_frame(64, 64, 5), synth.synth_frame(109, 109, 6), synth.synth_frame(64, 64, 7)]
 dev = [torch.from_numpy(c).cuda() for c in crops]
 per_crop = hand.network_outputs(dev)

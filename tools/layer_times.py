@@ -14,14 +14,13 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import isl_b200  # noqa: E402
-from isl_b200 import _lib  # noqa: E402
-from oracle import openpose_oracle as O  # noqa: E402  (seeded weight generator only)
+from isl_b200 import _lib, synth  # noqa: E402
 
 
 def main():
     kind, n, h, w = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
     torch.cuda.set_device(0)
-    net = isl_b200.PoseNet(kind, O.make_flat_weights(kind, seed=0, init="torch"))
+    net = isl_b200.PoseNet(kind, synth.make_flat_weights(kind, seed=0, init="torch"))
     inst = net.instance(n, h, w)
     inst.input.uniform_(-0.5, 0.5)
     inst.run()

@@ -20,7 +20,6 @@ import bench  # noqa: E402
 import isl_b200  # noqa: E402
 from isl_b200 import _lib, synth  # noqa: E402
 from isl_b200.body import scale_geometry  # noqa: E402
-from oracle import openpose_oracle as O  # noqa: E402  (seeded weight generator only)
 
 
 def timed(fn, reps, flush):
@@ -45,8 +44,8 @@ def main():
     mt, H, W, boxes, _ = bench.WORKLOADS[wl]
     torch.cuda.set_device(0)
     L = _lib.lib()
-    body = isl_b200.Body(O.make_flat_weights(mt, seed=0, init="torch"), mt, scale_search=bench.SCALES)
-    hand = isl_b200.Hand(O.make_flat_weights("hand", seed=0, init="torch"))
+    body = isl_b200.Body(synth.make_flat_weights(mt, seed=0, init="torch"), mt, scale_search=bench.SCALES)
+    hand = isl_b200.Hand(synth.make_flat_weights("hand", seed=0, init="torch"))
     frames = torch.from_numpy(np.stack([synth.synth_frame(H, W, i) for i in range(nb)])).cuda()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
     sustained, burst, hbm, _ = bench.peaks()
