@@ -56,3 +56,19 @@ def test_slices_are_16_byte_aligned_and_inside_their_buffers():
             if s["dst"] is not None:
                 dch, _ = p.bufs[s["dst"][0]]
                 assert s["dst"][1] % 8 == 0 and s["dst"][1] + (s["cout"] + 7) // 8 * 8 <= dch
+
+
+def test_package_weight_generator_matches_the_oracle_generator():
+    """bench.py and the tools draw their seeded weights from isl_b200.synth (the product side may not import oracle/);
+    the tests draw theirs from the oracle. Same seeds must mean the same tensors, or goldens and benchmarks diverge."""
+    import torch
+
+    from isl_b200 import synth
+    from oracle import openpose_oracle as O
+
+    for kind in ("coco", "body25", "hand"):
+        for init in ("torch", "he"):
+            a = synth.make_flat_weights(kind, seed=3, init=init)
+            b = O.make_flat_weights(kind, seed=3, init=init)
+            assert list(a) == list(b)
+            assert all(torch.equal(a[k], b[k]) for k in a)
