@@ -287,7 +287,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 //   * the accumulator is double buffered in TMEM (2 x msub x n_tile columns), so the epilogue of work item w
 //     overlaps the main loop of w+1 and the per-tile set-up (barrier init, TMEM allocation) is paid once per CTA;
 //   * with msub = 2 one weight stage feeds two 128-pixel MMAs: half the weight traffic from L2 per FLOP.
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreadsV1, 2)
 conv_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                             const ConvArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -323,7 +323,7 @@ conv_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(bar_acc_full + 8 * b, 1);
-      ptx::mbar_init(bar_acc_empty + 8 * b, 4);  // one arrival per epilogue warp
+      ptx::mbar_init(bar_acc_empty + 8 * b, 8);  // one arrival per epilogue warp
     }
     ptx::mbar_fence_init();
     ptx::prefetch_tensormap(&tmA);
@@ -433,7 +433,8 @@ conv_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 2..5 = 128 threads)
+    // ------------------------------------------------------------ epilogue (warps 2..9 = 256 threads; the two warps of a
+    // TMEM lane quarter take alternate 32-column chunks)
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int py = row / a.bw;
@@ -447,12 +448,12 @@ conv_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       const int live = min(a.msub, a.m_tiles - mg * a.msub);
       const int buf = local % a.acc_bufs;
       if (n0 != cur_n0) {  // (re)load this channel tile's bias / slope; named barrier 1 = the 4 epilogue warps
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int i = et; i < a.n_tile; i += 128) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int i = et; i < a.n_tile; i += 256) {
           s_bias[i] = a.bias[n0 + i];
           s_slope[i] = a.slope[n0 + i];
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         cur_n0 = n0;
       }
       ptx::mbar_wait(bar_acc_full + 8 * buf, (local / a.acc_bufs) & 1);
@@ -466,7 +467,7 @@ conv_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
         const bool valid = (row < a.bw * a.bh) && (x < a.W) && (y < a.H);
         const long long pix = (static_cast<long long>(img) * a.H + y) * a.W + x;
         const uint32_t acc = tmem_base + buf * acc_cols + sub * a.n_tile + (static_cast<uint32_t>(q * 32) << 16);
-        for (int c = 0; c < a.n_tile; c += 32) {
+        for (int c = ((warp - 2) >> 2) * 32; c < a.n_tile; c += 64) {
           uint32_t rr[32];
           ptx::tmem_ld_32x32(acc + c, rr);
           ptx::tmem_ld_wait();
@@ -1541,7 +1542,7 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   if (variant == 2) {
     int per_sm = static_cast<int>((226u * 1024u) / out->smem_bytes);  // persistent CTAs that fit on one SM
     if (per_sm * a.tmem_cols > 512) per_sm = 512 / a.tmem_cols;
-    if (per_sm > 4) per_sm = 4;
+    if (per_sm > 2) per_sm = 2;  // 320 threads x ~100 registers: two CTAs per SM
     if (per_sm < 1) per_sm = 1;
     const int slots = 148 * per_sm;
     const int ctas = a.work_items < slots ? a.work_items : slots;
@@ -1568,7 +1569,7 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
 
 int conv_run(const ConvLaunch& l, cudaStream_t stream) {
   if (l.variant == 2) {
-    conv_umma_persistent_kernel<<<l.grid, kThreads, l.smem_bytes, stream>>>(l.tmA, l.tmB, l.args);
+    conv_umma_persistent_kernel<<<l.grid, kThreadsV1, l.smem_bytes, stream>>>(l.tmA, l.tmB, l.args);
   } else if (l.variant == 3) {
     conv_umma_halo_kernel<<<l.grid, kThreads, l.smem_bytes, stream>>>(l.tmA, l.tmB, l.args);
   } else if (l.variant == 4) {
