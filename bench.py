@@ -367,6 +367,9 @@ def main():
                                                         "(body maps of one %d-frame chunk, run on their own)" % nb,
                               "achieved": post_bytes_heat / (post_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                               "frac": post_bytes_heat / (post_ms * 1e-3) / 1e9 / hbm_peak,
+                              "limiter": "instruction issue and the FP64 pipe, not HBM: the reference's float32 (no FMA, fixed order) "
+                                         "cubic stages and float64 accumulation / gaussian are reproduced bit for bit "
+                                         "(profiles/r1_ncu_full_post.txt, DESIGN.md section 7)",
                               "ms_per_frame": post_ms / nb, "algorithmic_bytes_per_frame": post_bytes_heat // nb,
                               "reference_dataflow_bytes_per_frame_incl_paf": post_bytes_all // nb},
         }
