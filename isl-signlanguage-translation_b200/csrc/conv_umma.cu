@@ -19,6 +19,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <utility>
+
 #include "ptx.cuh"
 
 namespace islpose {
@@ -110,10 +112,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_g;
+  ptx::pdl_launch_dependents();  // programmatic dependent launch: see the v5 kernel
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (whole warp, one elected lane issues)
     {
+      ptx::pdl_wait();  // the previous layer's output is first touched by the loads below
       const uint32_t tx_bytes = 128u * a.bw * a.bh + 128u * a.n_tile;
       const int total = taps * cblocks;
       const int xb = x0 - a.pad, yb = y0 - a.pad;
@@ -338,10 +342,12 @@ conv_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_g;
   const uint32_t acc_cols = a.msub * a.n_tile;  // columns of one accumulator buffer
+  ptx::pdl_launch_dependents();  // programmatic dependent launch: see the v5 kernel
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (whole warp, one elected lane issues)
     {
+      ptx::pdl_wait();  // the previous layer's output is first touched by the loads below
       ptx::RingPos r(bar_full, bar_empty, a.stages);
       uint32_t sa = sA0, sb = sB0;
       for (int w = blockIdx.x; w < a.work_items; w += gridDim.x) {
@@ -1567,28 +1573,34 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   return 0;
 }
 
+// v1, v2 and v5 are launched with programmatic stream serialization: their set-up (barriers, TMEM allocation,
+// descriptor prefetch, bias loads) may overlap the tail of the previous launch in the stream; each of them executes
+// griddepcontrol.wait before its first access to the previous layer's output.
+template <typename... KArgs, typename... Args>
+static int launch_pdl(void (*kernel)(KArgs...), dim3 grid, int threads, uint32_t smem, cudaStream_t stream, Args&&... args) {
+  static const bool no_pdl = getenv("ISLPOSE_NO_PDL") != nullptr;  // A/B measurement aid
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = no_pdl ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...) == cudaSuccess ? 0 : 1;
+}
+
 int conv_run(const ConvLaunch& l, cudaStream_t stream) {
-  if (l.variant == 2) {
-    conv_umma_persistent_kernel<<<l.grid, kThreadsV1, l.smem_bytes, stream>>>(l.tmA, l.tmB, l.args);
-  } else if (l.variant == 3) {
+  if (l.variant == 2) return launch_pdl(conv_umma_persistent_kernel, l.grid, kThreadsV1, l.smem_bytes, stream, l.tmA, l.tmB, l.args);
+  if (l.variant == 5) return launch_pdl(conv_umma_halo_swapped_kernel, l.grid, kThreadsV1, l.smem_bytes, stream, l.tmA, l.tmB, l.args);
+  if (l.variant == 3) {
     conv_umma_halo_kernel<<<l.grid, kThreads, l.smem_bytes, stream>>>(l.tmA, l.tmB, l.args);
   } else if (l.variant == 4) {
     conv_umma_swapped_kernel<<<l.grid, kThreads, l.smem_bytes, stream>>>(l.tmA, l.tmB, l.tmC, l.args);
-  } else if (l.variant == 5) {
-    static const bool no_pdl = getenv("ISLPOSE_NO_PDL") != nullptr;  // A/B measurement aid
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = l.grid;
-    cfg.blockDim = dim3(kThreadsV1);
-    cfg.dynamicSmemBytes = l.smem_bytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = no_pdl ? 0 : 1;
-    return cudaLaunchKernelEx(&cfg, conv_umma_halo_swapped_kernel, l.tmA, l.tmB, l.args) == cudaSuccess ? 0 : 1;
   } else {
-    conv_umma_kernel<<<l.grid, kThreadsV1, l.smem_bytes, stream>>>(l.tmA, l.tmB, l.tmC, l.args);
+    return launch_pdl(conv_umma_kernel, l.grid, kThreadsV1, l.smem_bytes, stream, l.tmA, l.tmB, l.tmC, l.args);
   }
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
