@@ -188,6 +188,20 @@ class KeypointExtractor(object):
         rows = [F.frame_features(c, s, hp, mt) for res in runner for (c, s, hp) in res]
         return np.stack(rows) if rows else np.zeros((0, F.N_FEATURES))
 
+    def records(self, frames, batch_size=8, first_frame_no=0, **meta):
+        """Clip -> list of per-frame feature rows (features.feature_record = extract_features.py's saveFeature dict)."""
+        from . import features as F
+
+        frames = list(frames)
+        mt = getattr(self.body, "model_type", "coco")
+        batches = [(frames[a:a + batch_size], None) for a in range(0, len(frames), batch_size)]
+        runner = self.pipeline(batches) if hasattr(self.body, "enqueue") else (self.batch(b) for b, _ in batches)
+        rows = []
+        for res in runner:
+            for (c, s, hp) in res:
+                rows.append(F.feature_record(c, s, hp, frame_no=first_frame_no + len(rows), model_type=mt, **meta))
+        return rows
+
     def run_sharded(self, frames, rank, world_size, batch_size=8, hand_boxes=None):
         """Processes this rank's shard of `frames` in batches; returns results in shard order."""
         idx = shard_indices(len(frames), rank, world_size)

@@ -97,6 +97,37 @@ def frame_features(candidate, subset, all_hand_peaks, model_type='coco'):
     return populate_features(circles, peaks).astype(np.float64)
 
 
+def feature_record(candidate, subset, all_hand_peaks, frame_no=0, model_type='body25', transform='original',
+                   filepath=None, label_type=None, label_expression=None):
+    """One frame's row of the feature-extraction loop (extract_features.py:105-141 `saveFeature`, the dict that
+    `saveFeaturesDict` turns into a DataFrame / CSV row): the three extractor outputs as lists plus the derived circles,
+    sticks, hand edges and hand key points. Same keys, same value structures; nothing is written to disk here."""
+    circles, sticks = get_bodypose(candidate, subset, model_type)
+    edges, peaks = get_handpose(all_hand_peaks)
+    return {
+        'transform': transform,
+        'filepath': filepath,
+        'frame_no': frame_no,
+        'type': label_type,
+        'expression': label_expression,
+        'candidate': np.asarray(candidate).tolist(),
+        'subset': np.asarray(subset).tolist(),
+        'all_hand_peaks': [np.asarray(p).tolist() for p in all_hand_peaks],
+        'bodypose_x_ytupple': circles,
+        'bodypose_x_y_sticks': sticks,
+        'handpose_edges': edges,
+        'handpose_peaks': peaks,
+    }
+
+
+def feature_json(candidate, subset, all_hand_peaks):
+    """The per-frame JSON payload the reference writes next to every frame (extract_features.py:112-117)."""
+    import json
+
+    return json.dumps({'candidate': np.asarray(candidate).tolist(), 'subset': np.asarray(subset).tolist(),
+                       'all_hand_peaks': [np.asarray(p).tolist() for p in all_hand_peaks]})
+
+
 class FeatureWindow(object):
     """The classifier's input window: the last WINDOW frames, oldest first (ISL_Model_parameter.py:370-374)."""
 

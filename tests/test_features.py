@@ -62,3 +62,23 @@ def test_clip_features_with_stand_in_estimators():
     assert X.shape == (5, 156)
     want = F.frame_features(d["candidate"], d["subset"], [], "coco")
     assert np.array_equal(X[0], want) and np.array_equal(X[2], want) and not X[1].any()
+
+
+def test_feature_record_has_the_reference_row_structure():
+    """extract_features.py:105-141: keys and value structures of the per-frame row, and the JSON payload of :112-117."""
+    import json
+
+    d = np.load(os.path.join(GOLD, "body_body25_p5_s2.npz"), allow_pickle=True)
+    hands = [h for h in G["coco_p2_s4/hands"]]
+    row = F.feature_record(d["candidate"], d["subset"], hands, frame_no=7, model_type="body25", label_type="train",
+                           label_expression="hello")
+    assert list(row) == ['transform', 'filepath', 'frame_no', 'type', 'expression', 'candidate', 'subset', 'all_hand_peaks',
+                         'bodypose_x_ytupple', 'bodypose_x_y_sticks', 'handpose_edges', 'handpose_peaks']
+    assert row['frame_no'] == 7 and row['transform'] == 'original' and row['type'] == 'train'
+    assert row['candidate'] == d["candidate"].tolist() and row['subset'] == d["subset"].tolist()
+    assert np.array_equal(np.array(row['bodypose_x_ytupple']).reshape(-1, 2), G["body25_p5_s2/circles"])
+    assert np.array_equal(np.array(row['bodypose_x_y_sticks']).reshape(-1, 4), G["body25_p5_s2/sticks"])
+    assert len(row['handpose_peaks']) == 2 and len(row['handpose_peaks'][0]) == 21 and row['handpose_peaks'][0][3][2] == '3'
+    payload = json.loads(F.feature_json(d["candidate"], d["subset"], hands))
+    assert sorted(payload) == ['all_hand_peaks', 'candidate', 'subset'] and payload['subset'] == d["subset"].tolist()
+    json.dumps(row['candidate'])   # every numeric list is JSON-serialisable, as the reference needs for its CSV / JSON
