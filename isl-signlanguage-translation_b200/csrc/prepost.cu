@@ -295,7 +295,7 @@ resize_accumulate_kernel(const ScaleSet ss, const MidSet ms, int N, int H, int W
     const int nrows = r_hi - r_lo + 1;  // <= rows_cap (sized by the launcher)
     // this thread's four rows: weights and offsets into the shared rows
     float wy[4][4];
-    int sy4[4];  // first tap row (unclamped) of this thread's four rows
+    unsigned ro4[4];  // shared-row index of each of the four taps of this thread's four rows, one byte each (< kRMaxRows)
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int y = y0 + ty + 8 * k;
@@ -304,9 +304,11 @@ resize_accumulate_kernel(const ScaleSet ss, const MidSet ms, int N, int H, int W
       float fy;
       cubic_src(yc, g.sy, sy, fy);
       cubic_coeffs(fy, wy[k]);
-      sy4[k] = sy - 1;
+      ro4[k] = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ro4[k] |= static_cast<unsigned>(clampi(sy - 1 + j, 0, g.hc - 1) - r_lo) << (8 * j);
     }
-    const int hc1 = g.hc - 1;
+    const bool x_interior = xi[3] == xi[0] + 3;
     const int pitch = ms.pitch[s];
     const long long plane = static_cast<long long>(g.hc) * pitch;
     // v / S in float32 (body.py:80-81): for a power of two the multiplication by 1/S gives the identical result
@@ -319,15 +321,22 @@ resize_accumulate_kernel(const ScaleSet ss, const MidSet ms, int N, int H, int W
         const float* img = ms.mid[s] + (static_cast<long long>(n) * parts + c) * plane + static_cast<long long>(r_lo) * pitch;
         float (*s_t)[kRT + 1] = buf ? s_t1 : s_t0;
         // horizontal pass: one dot product per (source row, column); rows strided over the 8 warps, five rows (20
-        // independent loads) in flight per thread
+        // independent loads) in flight per thread. 32-bit offsets from the (CTA-uniform) plane pointer; away from the
+        // left / right border the four taps are consecutive floats.
         for (int rb = ty; rb < nrows; rb += 40) {
           float v[5][4];
 #pragma unroll
           for (int m = 0; m < 5; ++m) {
-            const int r = rb + 8 * m < nrows ? rb + 8 * m : nrows - 1;
-            const float* row = img + static_cast<long long>(r) * pitch;
+            const unsigned r = rb + 8 * m < nrows ? rb + 8 * m : nrows - 1;
+            const unsigned off = r * static_cast<unsigned>(pitch);
+            if (x_interior) {
+              const float* p4 = img + (off + static_cast<unsigned>(xi[0]));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) v[m][k] = __ldg(row + xi[k]);
+              for (int k = 0; k < 4; ++k) v[m][k] = __ldg(p4 + k);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) v[m][k] = __ldg(img + (off + static_cast<unsigned>(xi[k])));
+            }
           }
 #pragma unroll
           for (int m = 0; m < 5; ++m) {
@@ -336,10 +345,12 @@ resize_accumulate_kernel(const ScaleSet ss, const MidSet ms, int N, int H, int W
         }
         __syncthreads();
         const bool tail = static_cast<long long>(xc) * C + c >= tail_start;
+        const float* col = &s_t[0][tx];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const float t0 = s_t[clampi(sy4[k], 0, hc1) - r_lo][tx], t1 = s_t[clampi(sy4[k] + 1, 0, hc1) - r_lo][tx],
-                      t2 = s_t[clampi(sy4[k] + 2, 0, hc1) - r_lo][tx], t3 = s_t[clampi(sy4[k] + 3, 0, hc1) - r_lo][tx];
+          // shared rows of this output row's four taps: byte offsets packed per scale (ro4), pitch kRT + 1 floats
+          const float t0 = col[(ro4[k] & 0xffu) * (kRT + 1)], t1 = col[((ro4[k] >> 8) & 0xffu) * (kRT + 1)],
+                      t2 = col[((ro4[k] >> 16) & 0xffu) * (kRT + 1)], t3 = col[(ro4[k] >> 24) * (kRT + 1)];
           const float v = tail ? dot4_lr(t0, t1, t2, t3, wy[k]) : dot4_rl(t0, t1, t2, t3, wy[k]);
           const double t = static_cast<double>(pow2 ? __fmul_rn(v, rS) : __fdiv_rn(v, fS));
           acc[k][i] = q1 ? __dadd_rn(acc[k][i], __dadd_rn(acc[k][i], t)) : __dadd_rn(acc[k][i], t);
