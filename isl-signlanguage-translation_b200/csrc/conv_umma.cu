@@ -1344,7 +1344,11 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
     }
     out->grid = dim3(static_cast<unsigned>(a.work_items < 148 ? a.work_items : 148), 1, 1);
     out->flops = 2.0 * d.in_c * d.cout * d.ksize * d.ksize * static_cast<double>(d.H) * d.W * d.N;
-    static bool attr5 = false;
+    // the opt-in to large dynamic shared memory is per device: one flag per device ordinal
+    static bool attr5_dev[64] = {};
+    int dev5 = 0;
+    cudaGetDevice(&dev5);
+    bool& attr5 = attr5_dev[dev5 & 63];
     if (!attr5) {
       if (cudaFuncSetAttribute(conv_umma_halo_swapped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
           cudaSuccess)
@@ -1558,7 +1562,10 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   }
   out->flops = 2.0 * d.in_c * d.cout * d.ksize * d.ksize * static_cast<double>(d.H) * d.W * d.N;
 
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  bool& attr_set = attr_set_dev[dev & 63];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess)
