@@ -1279,7 +1279,8 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
         // N/2 plus shared-memory contention with the weight stream), never below ~100 (issue rate of one warp)
         const double fit = 76.0 + 2.8 * h;
         const double per_mma = fit > 100.0 ? fit : 100.0;
-        const double cost = static_cast<double>((tiles + 147) / 148) * (kb5 * 4.0 * per_mma + 6000.0);
+        static const double tile_const = getenv("ISLPOSE_TILE_CONST") ? atof(getenv("ISLPOSE_TILE_CONST")) : 6000.0;  // per-tile overhead (cycles)
+        const double cost = static_cast<double>((tiles + 147) / 148) * (kb5 * 4.0 * per_mma + tile_const);
         if (best < 0 || cost < best) {
           best = cost;
           th = h;
