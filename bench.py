@@ -374,9 +374,16 @@ def main():
                               "reference_dataflow_bytes_per_frame_incl_paf": post_bytes_all // nb},
         }
         if world == 1 and not args.no_cpu_baseline:
-            t, _ = cpu_reference_frame(args.workload, 0)
-            line["cpu_baseline"] = {"value": 1.0 / t, "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "port",
-                                    "sample": "1 frame of the workload (body 4 scales + %d hands), %.1f s" % (len(boxes), t)}
+            # bounded sample of the same workload on the host cores: one untimed frame (weights, thread pools), then
+            # frames until about 12 s of CPU work have been timed (at least 2, at most 4)
+            _, nets = cpu_reference_frame(args.workload, 0)
+            ts = []
+            while len(ts) < 2 or (sum(ts) < 12.0 and len(ts) < 4):
+                t, nets = cpu_reference_frame(args.workload, 1 + len(ts), nets)
+                ts.append(t)
+            line["cpu_baseline"] = {"value": len(ts) / sum(ts), "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                    "sample": "%d frames of the workload (body 4 scales + %d hands each) after one untimed frame, "
+                                              "%.1f s of CPU work" % (len(ts), len(boxes), sum(ts))}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
