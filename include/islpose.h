@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define ISLPOSE_ABI_VERSION 1
+#define ISLPOSE_ABI_VERSION 2
 #define ISLPOSE_MAX_SCALES 8
 
 int islpose_abi_version(void);
@@ -57,23 +57,27 @@ typedef struct islpose_conv_desc {
                            [n][h/2][w/2] buffer. Only for 3x3 / 7x7 layers with >= 64 input and >= 48 output channels */
 } islpose_conv_desc;
 
+/* Weight ingestion (src/body.py:35-36, src/util.py:35-44): one nn.Conv2d weight, float32 [cout][cin][k][k] on the device,
+ * -> the `weights` operand of islpose_conv_desc: bf16 [k*k][cout][w_cin], input channels in the order of the activation
+ * slice the layer reads. chan_map (device int32 [in_c], may be NULL = identity): reference input channel at slice channel i,
+ * -1 = pad channel (zero weights). first_layer != 0 packs conv1_1 for islpose_plan_add_first_conv: [1][cout][w_cin = 32],
+ * K index (ky*3+kx)*3+c. Round-to-nearest-even. */
+int islpose_pack_conv_weights(const float* w, int32_t cout, int32_t cin, int32_t ksize, const int32_t* chan_map, int32_t in_c,
+                              int32_t w_cin, int32_t first_layer, void* out_bf16, void* stream);
+
 int islpose_plan_create(islpose_plan** out);
 int islpose_plan_destroy(islpose_plan* plan);
 int islpose_plan_add_conv(islpose_plan* plan, const islpose_conv_desc* desc);
-/* nn.MaxPool2d(2, 2, 0) (src/model.py:30-32) on a full NHWC bf16 buffer */
-int islpose_plan_add_maxpool2x2(islpose_plan* plan, const void* in, void* out, int32_t n, int32_t h, int32_t w, int32_t c);
-/* fp32 NCHW [n,3,h,w] network input -> bf16 [n,h,w,32] rows of the first layer's 3x3x3 patches (27 + 5 zeros) */
-int islpose_plan_add_im2col3x3(islpose_plan* plan, const float* in_nchw, void* out_nhwc32, int32_t n, int32_t h, int32_t w);
 /* conv1_1 (3 -> 64 channels, 3x3, src/model.py 'conv1_1' of all three networks) in one launch straight from the fp32 NCHW
  * network input: weights bf16 [64][32] with K index (ky*3+kx)*3+c (27 used, 5 zero), bias / slope as in islpose_conv_desc,
- * out bf16 NHWC with out_cstride (>= 64) channels per pixel. Replaces add_im2col3x3 + a 1x1 add_conv over its output. */
+ * out bf16 NHWC with out_cstride (>= 64) channels per pixel. */
 int islpose_plan_add_first_conv(islpose_plan* plan, const float* in_nchw, const void* weights, const float* bias,
                                 const float* slope, void* out, int32_t out_cstride, int32_t n, int32_t h, int32_t w);
 int islpose_plan_run(const islpose_plan* plan, void* stream);
 /* Measurement aid: runs the plan launch by launch, each one `reps` times back to back between two CUDA events (after
  * one untimed run), and blocks until done. h_ms / h_flops / h_variant (HOST arrays of num_launches entries; the last
  * two may be NULL) receive the average milliseconds, the algorithmic FLOPs (0 for non-conv launches) and the conv
- * kernel variant (-1 max-pool, -2 first-layer gather) of every launch. */
+ * kernel variant (0 = first-layer kernel) of every launch. */
 int islpose_plan_profile(const islpose_plan* plan, void* stream, int32_t reps, float* h_ms, double* h_flops,
                          int32_t* h_variant);
 int32_t islpose_plan_num_launches(const islpose_plan* plan);
@@ -134,17 +138,37 @@ typedef struct islpose_group_buffers {
   int32_t max_person;      /* row slots per frame: every row ever created, merged-away ones included (<= 65536) */
   double* subset;          /* out [n][max_person][njoint+1] */
   int32_t* n_person;       /* out [n] */
-  int32_t* overflow;       /* out [1]: non-zero if a capacity was exceeded (1 peaks, 2 candidates, 3 pairs, 4 persons) */
+  int32_t* overflow;       /* out [1]: OR of ISLPOSE_OVERFLOW_* bits, one per capacity that was exceeded (never cleared here) */
 } islpose_group_buffers;
+
+#define ISLPOSE_OVERFLOW_PEAKS 1      /* a (frame, part) has more than cap peaks (islpose_body_peaks) */
+#define ISLPOSE_OVERFLOW_CANDIDATES 2 /* a frame has more than max_cand peaks in total */
+#define ISLPOSE_OVERFLOW_PAIRS 4      /* a (frame, limb) has nA*nB > pair_cap */
+#define ISLPOSE_OVERFLOW_PERSONS 8    /* a frame created more than max_person rows */
 
 int islpose_body_group(const islpose_scale* paf_scales, int32_t n_scales, int32_t model_kind, int32_t n, int32_t H,
                        int32_t W, double thre2, int32_t mid_num, const islpose_group_buffers* buffers, void* stream);
 
-/* Hand key points (src/hand.py:58-74): gaussian sigma=3, threshold, 8-connected labelling, heaviest component,
- * first arg-max. heat float64 [planes][H][W] (from islpose_maps_accumulate, planes = hands*21);
- * smoothed/labels/mass: scratch of planes*H*W elements each; out_xy int32 [planes][2] (x, y; 0,0 = not found). */
+/* Hand key points (src/hand.py:51-74), batched over crops of any sizes: per crop and scale both cubic stages and the
+ * float64 mean over the scales (hand.py:51-56), gaussian sigma=3, threshold, 8-connected labelling, the component with the
+ * largest mass of the unsmoothed map (numpy's summation order where components tie to within rounding), first arg-max
+ * (util.npmax). Three launches per 32 crops. h_crops is a HOST array; scales[s].lowres points at THIS crop's network
+ * output, fp32 [22][gh][gw]. workspace: device scratch of islpose_hand_workspace_bytes() bytes, 256-byte aligned.
+ * out_xy int32 [n_crops][21][2] (x, y in crop coordinates; 0,0 = not found). n_scales <= 4 (hand.py:25). */
+typedef struct islpose_hand_crop {
+  int32_t h, w;
+  islpose_scale scales[4];
+} islpose_hand_crop;
+
+int64_t islpose_hand_workspace_bytes(const islpose_hand_crop* h_crops, int32_t n_crops);
+int islpose_hand_keypoints(const islpose_hand_crop* h_crops, int32_t n_crops, int32_t n_scales, const double* h_gauss,
+                           double thre, void* workspace, int64_t workspace_bytes, int32_t* out_xy, void* stream);
+
+/* The selection stage of islpose_hand_keypoints alone (hand.py:58-74) on caller-supplied float64 maps:
+ * heat [planes][H][W] (all planes of one size); labels / mass: scratch of planes*H*W elements each;
+ * out_xy int32 [planes][2]. */
 int islpose_hand_peaks(const double* heat, int32_t planes, int32_t H, int32_t W, const double* h_gauss, double thre,
-                       double* smoothed, int32_t* labels, double* mass, int32_t* out_xy, void* stream);
+                       int32_t* labels, double* mass, int32_t* out_xy, void* stream);
 
 #ifdef __cplusplus
 }

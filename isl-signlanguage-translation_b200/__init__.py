@@ -9,7 +9,8 @@ Everything under the three call signatures runs as hand-written sm_100a CUDA rea
 include/islpose.h (libislpose.so). There is no CPU fallback: without the built library or without a CUDA
 device the constructors raise.
 """
-from . import synth, tables, util  # noqa: F401
+from . import synth, tables, util, weights  # noqa: F401
+from ._lib import IslposeError, configure  # noqa: F401
 from .body import Body  # noqa: F401
 from .hand import Hand  # noqa: F401
 from .nets import PoseNet  # noqa: F401

@@ -4,15 +4,37 @@ There is no CPU fallback: if the library is missing or a call fails, an exceptio
 """
 import ctypes as C
 import os
+import sys
+import warnings
 
-# Scales, lanes and hand crops run on a few dozen streams; with the default of 8 hardware queues unrelated streams
-# would share a queue and serialise. Only effective if set before the CUDA context exists.
-os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
+def configure(max_connections=32):
+    """Opt-in, process-wide: asks the CUDA driver for `max_connections` hardware work queues
+    (CUDA_DEVICE_MAX_CONNECTIONS). Scales, pipeline lanes and hand crops run on a few dozen streams; with the default
+    of 8 queues unrelated streams share a queue and serialise, which costs throughput in KeypointExtractor.pipeline().
+    The variable is only read when the CUDA context is created, so call this before the first CUDA call of the
+    process (bench.py and the tools do). Returns False, with a warning, when a context already exists or the
+    variable is already set to something else; nothing is changed in that case."""
+    cur = os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS")
+    if cur is not None:
+        if cur != str(max_connections):
+            warnings.warn("CUDA_DEVICE_MAX_CONNECTIONS is already %s; leaving it" % cur)
+            return False
+        return True
+    torch = sys.modules.get("torch")
+    if torch is not None and torch.cuda.is_initialized():
+        warnings.warn("isl_b200.configure() called after the CUDA context was created: CUDA_DEVICE_MAX_CONNECTIONS would "
+                      "have no effect, stream overlap in KeypointExtractor.pipeline() is limited to 8 hardware queues")
+        return False
+    os.environ["CUDA_DEVICE_MAX_CONNECTIONS"] = str(max_connections)
+    return True
+
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libislpose.so")
 
 MAX_SCALES = 8
+ABI_VERSION = 2
 
 
 class ConvDesc(C.Structure):
@@ -28,6 +50,13 @@ class Scale(C.Structure):
     _fields_ = [("lowres", C.c_void_p), ("gh", C.c_int32), ("gw", C.c_int32), ("hc", C.c_int32), ("wc", C.c_int32)]
 
 
+class HandCrop(C.Structure):
+    _fields_ = [("h", C.c_int32), ("w", C.c_int32), ("scales", Scale * 4)]
+
+
+OVERFLOW_PEAKS, OVERFLOW_CANDIDATES, OVERFLOW_PAIRS, OVERFLOW_PERSONS = 1, 2, 4, 8
+
+
 class GroupBuffers(C.Structure):
     _fields_ = [("cap", C.c_int32), ("counts", C.c_void_p), ("keys", C.c_void_p), ("scores", C.c_void_p),
                 ("pair_cap", C.c_int64), ("pair_score", C.c_void_p), ("end_paf", C.c_void_p), ("conn_count", C.c_void_p), ("conn_ij", C.c_void_p),
@@ -40,11 +69,11 @@ SYMBOLS = {
     "islpose_abi_version": (C.c_int, []),
     "islpose_last_error": (C.c_char_p, []),
     "islpose_launch_count": (C.c_int64, []),
+    "islpose_pack_conv_weights": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                            C.c_void_p, C.c_void_p]),
     "islpose_plan_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "islpose_plan_destroy": (C.c_int, [C.c_void_p]),
     "islpose_plan_add_conv": (C.c_int, [C.c_void_p, C.POINTER(ConvDesc)]),
-    "islpose_plan_add_maxpool2x2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
-    "islpose_plan_add_im2col3x3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
     "islpose_plan_add_first_conv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                             C.c_int32, C.c_int32, C.c_int32]),
     "islpose_plan_run": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -60,8 +89,11 @@ SYMBOLS = {
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "islpose_body_group": (C.c_int, [C.POINTER(Scale), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double,
                                      C.c_int32, C.POINTER(GroupBuffers), C.c_void_p]),
+    "islpose_hand_workspace_bytes": (C.c_int64, [C.POINTER(HandCrop), C.c_int32]),
+    "islpose_hand_keypoints": (C.c_int, [C.POINTER(HandCrop), C.c_int32, C.c_int32, C.POINTER(C.c_double), C.c_double,
+                                         C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "islpose_hand_peaks": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.c_double,
-                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None
@@ -83,8 +115,9 @@ def lib():
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        if handle.islpose_abi_version() != 1:
-            raise IslposeError("libislpose.so has ABI version %d, expected 1" % handle.islpose_abi_version())
+        if handle.islpose_abi_version() != ABI_VERSION:
+            raise IslposeError("libislpose.so has ABI version %d, expected %d (rebuild it)" % (handle.islpose_abi_version(),
+                                                                                            ABI_VERSION))
         _lib = handle
     return _lib
 

@@ -16,16 +16,11 @@ from . import _lib
 from .nets import PoseNet
 from .tables import model_dims
 from .util import gaussian_weights
+from .weights import load_flat
 
 PEAK_CAP = 1024        # peaks per (frame, part): the kernels' hard limit
 PAIR_CAP = 128 * 1024  # initial nA*nB capacity per (frame, limb); grows (x4) when a frame needs more
 MAX_PERSON = 4096      # initial row slots per frame (rows ever created); grows (x4) up to 65536
-
-
-def _load_flat(model_path):
-    if isinstance(model_path, dict):
-        return model_path
-    return torch.load(model_path, map_location="cpu")
 
 
 def scale_geometry(H, W, scale_search, boxsize):
@@ -52,7 +47,7 @@ class Body(object):
         self.scale_search = list(scale_search) if scale_search is not None else [0.5]
         self.boxsize, self.stride, self.padValue = boxsize, 8, 128
         self.thre1, self.thre2, self.mid_num = thre1, thre2, 10
-        self.model = PoseNet(kind, _load_flat(model_path), device=device, tuning=tuning)
+        self.model = PoseNet(kind, load_flat(model_path), device=device, tuning=tuning)
         self.device = self.model.device
         self._gauss = (C.c_double * 25)(*gaussian_weights().tolist())
         self._work = {}
@@ -153,11 +148,23 @@ class Body(object):
             setattr(gb, f, ws[f].data_ptr())
         _lib.check(L.islpose_body_group(paf_scales, len(maps), 1 if self._kind == 'body25' else 0, n, H, W, self.thre2,
                                         self.mid_num, C.byref(gb), _lib.stream_ptr()), "islpose_body_group")
-        # the three small result tables travel together, asynchronously, into pinned memory
+        # the three small result tables travel together, asynchronously, into pinned memory, and with them the leading
+        # rows of candidate / subset (as many as recent calls needed, with head room): one synchronisation per call
         ws["tail_dev"][:n].copy_(ws["n_cand"])
         ws["tail_dev"][n:2 * n].copy_(ws["n_person"])
         ws["tail_dev"][2 * n:2 * n + 1].copy_(ws["overflow"])
         ws["tail_host"].copy_(ws["tail_dev"], non_blocking=True)
+        self._copy_rows(ws, n)
+
+    def _copy_rows(self, ws, n):
+        rc, rp = ws.setdefault("rows_c", 512), ws.setdefault("rows_p", 64)
+        rc, rp = min(rc, ws["candidate"].shape[1]), min(rp, ws["subset"].shape[1])
+        if ws.get("cand_host") is None or ws["cand_host"].shape[1] != rc:
+            ws["cand_host"] = torch.empty((n, rc, 4), dtype=torch.float64).pin_memory()
+        if ws.get("sub_host") is None or ws["sub_host"].shape[1] != rp:
+            ws["sub_host"] = torch.empty((n, rp, self.njoint + 1), dtype=torch.float64).pin_memory()
+        ws["cand_host"].copy_(ws["candidate"][:, :rc], non_blocking=True)
+        ws["sub_host"].copy_(ws["subset"][:, :rp], non_blocking=True)
 
     def post_enqueue(self, maps, n, H, W, ws):
         """Launches peaks, PAF scoring and grouping for the per-scale network outputs on the current stream (no
@@ -190,29 +197,41 @@ class Body(object):
                 ticket["done"].synchronize()
                 tail = ws["tail_host"].numpy()
                 n_cand, n_person = tail[:n].copy(), tail[n:2 * n].copy()
-                self.last_overflow = int(tail[2 * n])
-                if self.last_overflow == 0:
-                    break
-                ws["overflow"].zero_()
-                if self.last_overflow == 3 and ws["pair_cap"] < PEAK_CAP * PEAK_CAP:
-                    # a limb has more candidate pairs than the scratch matrix holds: enlarge it and redo the grouping
-                    ws["pair_cap"] = min(ws["pair_cap"] * 4, PEAK_CAP * PEAK_CAP)
-                    ws["pair_score"] = torch.empty((ws["conn_count"].numel(), ws["pair_cap"]), dtype=torch.float64,
+                flags = self.last_overflow = int(tail[2 * n])
+                max_c, max_p = int(n_cand.max()) if n else 0, int(n_person.max()) if n else 0
+                redo = False
+                if flags:
+                    ws["overflow"].zero_()
+                    # capacities that cannot grow are reported first: the peak lists were truncated (which peaks survive
+                    # depends on the order of the atomics), so nothing computed from them is returned
+                    if flags & (_lib.OVERFLOW_PEAKS | _lib.OVERFLOW_CANDIDATES):
+                        raise _lib.IslposeError("a body part has more than %d peaks in one frame (overflow flags %d): the "
+                                                "peak lists of this call are incomplete" % (PEAK_CAP, flags))
+                    if flags & _lib.OVERFLOW_PAIRS:
+                        if ws["pair_cap"] >= PEAK_CAP * PEAK_CAP:
+                            raise _lib.IslposeError("pair matrix overflow at its maximum size")
+                        # a limb has more candidate pairs than the scratch matrix holds: enlarge it and redo the grouping
+                        ws["pair_cap"] = min(ws["pair_cap"] * 4, PEAK_CAP * PEAK_CAP)
+                        ws["pair_score"] = torch.empty((ws["conn_count"].numel(), ws["pair_cap"]), dtype=torch.float64,
+                                                       device=self.device)
+                    if flags & _lib.OVERFLOW_PERSONS:
+                        if ws["max_person"] >= 65536:
+                            raise _lib.IslposeError("more than 65536 person rows in one frame")
+                        ws["max_person"] *= 4
+                        ws["subset"] = torch.zeros((n, ws["max_person"], self.njoint + 1), dtype=torch.float64,
                                                    device=self.device)
-                elif self.last_overflow == 4 and ws["max_person"] < 65536:
-                    ws["max_person"] *= 4
-                    ws["subset"] = torch.zeros((n, ws["max_person"], self.njoint + 1), dtype=torch.float64,
-                                               device=self.device)
-                else:
-                    raise _lib.IslposeError("body grouping exceeded a fixed capacity (code %d: 1 = more than %d peaks in "
-                                            "one part, 2 = candidate table, 4 = more than 65536 person rows)" % (
-                                                self.last_overflow, PEAK_CAP))
+                    redo = True
+                elif max_c > ws["cand_host"].shape[1] or max_p > ws["sub_host"].shape[1]:
+                    # more rows than were copied speculatively: fetch them now and copy more next time
+                    ws["rows_c"], ws["rows_p"] = max(ws["rows_c"], 2 * max_c), max(ws["rows_p"], 2 * max_p)
+                    self._copy_rows(ws, n)
+                    torch.cuda.current_stream().synchronize()
+                if not redo:
+                    break
                 self._group(maps, n, H, W, ws)
                 ticket["done"] = torch.cuda.Event()
                 ticket["done"].record()
-            max_c, max_p = int(n_cand.max()) if n else 0, int(n_person.max()) if n else 0
-            cand = ws["candidate"][:, :max(max_c, 1)].cpu().numpy()
-            sub = ws["subset"][:, :max(max_p, 1)].cpu().numpy()
+            cand, sub = ws["cand_host"].numpy(), ws["sub_host"].numpy()
         results = []
         for i in range(n):
             c = cand[i, :n_cand[i]].copy() if n_cand[i] else np.array([])   # body.py:183 gives shape (0,) when empty
@@ -224,8 +243,9 @@ class Body(object):
         """Peaks, PAF scoring and grouping from the per-scale network outputs -> list of (candidate, subset)."""
         return self.post_finish(self.post_enqueue(maps, n, H, W, ws))
 
-    def upload(self, frames, lane=0):
-        """Host frames -> this call's device staging buffer [n,H,W,3] (through pinned memory; one buffer per lane)."""
+    def upload(self, frames, lane=0, after=None):
+        """Host frames -> this call's device staging buffer [n,H,W,3] (through pinned memory; one buffer per lane).
+        `after`: an event the copy must wait for - the last reader of the lane's previous contents."""
         frames = [np.asarray(f) for f in frames]
         H, W = frames[0].shape[:2]
         for f in frames:
@@ -240,6 +260,8 @@ class Body(object):
         host = stage[0].numpy()
         for i, f in enumerate(frames):
             host[i] = f   # also resolves negative-stride views such as frame[:, :, ::-1]
+        if after is not None:
+            torch.cuda.current_stream().wait_event(after)
         stage[1].copy_(stage[0], non_blocking=True)
         return stage[1]
 

@@ -31,12 +31,12 @@ int check_cuda(const char* what) {
   return 0;
 }
 
-enum OpKind { kConv = 0, kPool = 1, kIm2col = 2, kFirst = 3 };
+enum OpKind { kConv = 0, kFirst = 3 };
 
 struct Op {
   OpKind kind;
   ConvLaunch conv;  // kConv
-  const void* in;   // kPool / kIm2col / kFirst
+  const void* in;   // kFirst
   void* out;
   int n, h, w, c;
   const void* weights;  // kFirst
@@ -158,36 +158,6 @@ int islpose_plan_add_conv(islpose_plan* plan, const islpose_conv_desc* d) {
   return 0;
 }
 
-int islpose_plan_add_maxpool2x2(islpose_plan* plan, const void* in, void* out, int32_t n, int32_t h, int32_t w, int32_t c) {
-  if (plan == nullptr || in == nullptr || out == nullptr) return set_err("plan_add_maxpool2x2: null argument");
-  if (c % 8 != 0 || h % 2 != 0 || w % 2 != 0) return set_err("maxpool2x2: need C %% 8 == 0 and even H, W (got %d, %d, %d)", c, h, w);
-  Op op;
-  memset(&op, 0, sizeof(op));
-  op.kind = kPool;
-  op.in = in;
-  op.out = out;
-  op.n = n;
-  op.h = h;
-  op.w = w;
-  op.c = c;
-  plan->ops.push_back(op);
-  return 0;
-}
-
-int islpose_plan_add_im2col3x3(islpose_plan* plan, const float* in_nchw, void* out, int32_t n, int32_t h, int32_t w) {
-  if (plan == nullptr || in_nchw == nullptr || out == nullptr) return set_err("plan_add_im2col3x3: null argument");
-  Op op;
-  memset(&op, 0, sizeof(op));
-  op.kind = kIm2col;
-  op.in = in_nchw;
-  op.out = out;
-  op.n = n;
-  op.h = h;
-  op.w = w;
-  plan->ops.push_back(op);
-  return 0;
-}
-
 int islpose_plan_add_first_conv(islpose_plan* plan, const float* in_nchw, const void* weights, const float* bias,
                                 const float* slope, void* out, int32_t out_cstride, int32_t n, int32_t h, int32_t w) {
   if (plan == nullptr || in_nchw == nullptr || weights == nullptr || bias == nullptr || slope == nullptr || out == nullptr)
@@ -213,13 +183,8 @@ int islpose_plan_add_first_conv(islpose_plan* plan, const float* in_nchw, const 
 }
 
 static int run_op(const Op& op, cudaStream_t st) {
-  switch (op.kind) {
-    case kConv: return conv_run(op.conv, st);
-    case kPool: return launch_maxpool2x2(op.in, op.n, op.h, op.w, op.c, op.out, st);
-    case kIm2col: return launch_im2col3x3(static_cast<const float*>(op.in), op.n, op.h, op.w, op.out, st);
-    default:
-      return launch_conv_first(static_cast<const float*>(op.in), op.n, op.h, op.w, op.weights, op.bias, op.slope, op.out, op.c, st);
-  }
+  if (op.kind == kConv) return conv_run(op.conv, st);
+  return launch_conv_first(static_cast<const float*>(op.in), op.n, op.h, op.w, op.weights, op.bias, op.slope, op.out, op.c, st);
 }
 
 int islpose_plan_run(const islpose_plan* plan, void* stream) {
@@ -257,8 +222,8 @@ int islpose_plan_profile(const islpose_plan* plan, void* stream, int32_t reps, f
     cudaEventElapsedTime(&ms, e0, e1);
     h_ms[i] = ms / reps;
     if (h_flops != nullptr)
-      h_flops[i] = op.kind == kConv ? op.conv.flops : (op.kind == kFirst ? 2.0 * 27 * 64 * static_cast<double>(op.n) * op.h * op.w : 0.0);
-    if (h_variant != nullptr) h_variant[i] = op.kind == kConv ? op.conv.variant : (op.kind == kPool ? -1 : (op.kind == kFirst ? 0 : -2));
+      h_flops[i] = op.kind == kConv ? op.conv.flops : 2.0 * 27 * 64 * static_cast<double>(op.n) * op.h * op.w;
+    if (h_variant != nullptr) h_variant[i] = op.kind == kConv ? op.conv.variant : 0;
     g_launches.fetch_add(reps + 1, std::memory_order_relaxed);
   }
   cudaEventDestroy(e0);
@@ -269,6 +234,19 @@ int islpose_plan_profile(const islpose_plan* plan, void* stream, int32_t reps, f
 
 int32_t islpose_plan_num_launches(const islpose_plan* plan) { return plan ? static_cast<int32_t>(plan->ops.size()) : 0; }
 double islpose_plan_conv_flops(const islpose_plan* plan) { return plan ? plan->flops : 0.0; }
+
+int islpose_pack_conv_weights(const float* w, int32_t cout, int32_t cin, int32_t ksize, const int32_t* chan_map, int32_t in_c,
+                              int32_t w_cin, int32_t first_layer, void* out_bf16, void* stream) {
+  if (w == nullptr || out_bf16 == nullptr) return set_err("pack_conv_weights: null pointer");
+  if (cout <= 0 || cin <= 0 || (ksize != 1 && ksize != 3 && ksize != 7) || in_c <= 0 || w_cin < in_c || w_cin % 8 != 0)
+    return set_err("pack_conv_weights: bad shape (cout %d, cin %d, k %d, slice %d, stride %d)", cout, cin, ksize, in_c, w_cin);
+  if (first_layer && (ksize * ksize * cin > w_cin)) return set_err("pack_conv_weights: first-layer patch of %d values exceeds %d", ksize * ksize * cin, w_cin);
+  if (!first_layer && chan_map == nullptr && cin != in_c) return set_err("pack_conv_weights: slice width %d differs from Cin %d and no channel map was given", in_c, cin);
+  if (launch_pack_conv_weights(w, cout, cin, ksize, chan_map, in_c, w_cin, first_layer, out_bf16, static_cast<cudaStream_t>(stream)) != 0)
+    return check_cuda("pack_conv_weights") ? 1 : set_err("pack_conv_weights: launch failed");
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
 
 int islpose_resize_pad_normalize(const uint8_t* frames, int32_t n, int32_t H, int32_t W, double scale, int32_t rh,
                                  int32_t rw, int32_t hp, int32_t wp, float* out_nchw, uint8_t* out_u8, void* stream) {
@@ -351,18 +329,105 @@ int islpose_body_group(const islpose_scale* paf_scales, int32_t n_scales, int32_
   return 0;
 }
 
+static int fill_gauss(const double* h_gauss, GaussWeights* gw) {
+  if (h_gauss == nullptr) return set_err("hand: null gaussian weights");
+  memcpy(gw->w, h_gauss, sizeof(gw->w));
+  return 0;
+}
+
 int islpose_hand_peaks(const double* heat, int32_t planes, int32_t H, int32_t W, const double* h_gauss, double thre,
-                       double* smoothed, int32_t* labels, double* mass, int32_t* out_xy, void* stream) {
-  if (heat == nullptr || h_gauss == nullptr || smoothed == nullptr || labels == nullptr || mass == nullptr || out_xy == nullptr)
-    return set_err("hand_peaks: null pointer");
+                       int32_t* labels, double* mass, int32_t* out_xy, void* stream) {
+  if (heat == nullptr || labels == nullptr || mass == nullptr || out_xy == nullptr) return set_err("hand_peaks: null pointer");
+  if (planes <= 0 || H <= 0 || W <= 0 || static_cast<int64_t>(H) * W > (1 << 30)) return set_err("hand_peaks: bad sizes");
   GaussWeights gw;
-  memcpy(gw.w, h_gauss, sizeof(gw.w));
+  if (fill_gauss(h_gauss, &gw) != 0) return 1;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (launch_gauss_smooth(heat, planes, H, W, gw, smoothed, st) != 0)
-    return check_cuda("hand_peaks/gauss") ? 1 : set_err("hand_peaks: launch failed");
-  if (launch_hand_peaks(heat, smoothed, planes, H, W, thre, labels, mass, out_xy, st) != 0)
-    return check_cuda("hand_peaks") ? 1 : set_err("hand_peaks: launch failed");
-  g_launches.fetch_add(2, std::memory_order_relaxed);
+  // the planes are handed to the batched kernels as "crops" of up to 21 planes each
+  const int64_t plane = static_cast<int64_t>(H) * W;
+  for (int p0 = 0; p0 < planes;) {
+    HandBatch hb;
+    memset(&hb, 0, sizeof(hb));
+    hb.parts = planes - p0 < 21 ? planes - p0 : 21;
+    hb.channels = 22;
+    while (hb.n_crops < kHandMaxCrops && p0 + hb.parts <= planes) {
+      HandCropDev& c = hb.crop[hb.n_crops++];
+      c.H = H;
+      c.W = W;
+      c.heat = const_cast<double*>(heat) + p0 * plane;
+      c.labels = labels + p0 * plane;
+      c.mass = mass + p0 * plane;
+      c.out_xy = out_xy + p0 * 2;
+      p0 += hb.parts;
+    }
+    if (launch_hand_keypoints(hb, false, gw, thre, st) != 0)
+      return check_cuda("hand_peaks") ? 1 : set_err("hand_peaks: launch failed");
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+  }
+  return 0;
+}
+
+int64_t islpose_hand_workspace_bytes(const islpose_hand_crop* h_crops, int32_t n_crops) {
+  int64_t total = 0;
+  if (h_crops == nullptr) return 0;
+  for (int i = 0; i < n_crops; ++i) {
+    const int64_t elems = 21LL * h_crops[i].h * h_crops[i].w;
+    total += ((elems * 8 + 255) / 256 * 256) * 2 + (elems * 4 + 255) / 256 * 256;  // heat, mass (float64), labels (int32)
+  }
+  return total;
+}
+
+int islpose_hand_keypoints(const islpose_hand_crop* h_crops, int32_t n_crops, int32_t n_scales, const double* h_gauss,
+                           double thre, void* workspace, int64_t workspace_bytes, int32_t* out_xy, void* stream) {
+  if (h_crops == nullptr || workspace == nullptr || out_xy == nullptr) return set_err("hand_keypoints: null pointer");
+  if (n_crops <= 0) return set_err("hand_keypoints: no crops");
+  if (n_scales < 1 || n_scales > kHandMaxScales)
+    return set_err("hand_keypoints: between 1 and %d scales are supported (hand.py:25 uses 4), got %d", kHandMaxScales, n_scales);
+  if (workspace_bytes < islpose_hand_workspace_bytes(h_crops, n_crops))
+    return set_err("hand_keypoints: workspace of %lld bytes is too small (need %lld)", static_cast<long long>(workspace_bytes),
+                   static_cast<long long>(islpose_hand_workspace_bytes(h_crops, n_crops)));
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return set_err("hand_keypoints: workspace must be 256-byte aligned");
+  GaussWeights gw;
+  if (fill_gauss(h_gauss, &gw) != 0) return 1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* cursor = static_cast<uint8_t*>(workspace);
+  for (int c0 = 0; c0 < n_crops; c0 += kHandMaxCrops) {
+    HandBatch hb;
+    memset(&hb, 0, sizeof(hb));
+    hb.n_crops = n_crops - c0 < kHandMaxCrops ? n_crops - c0 : kHandMaxCrops;
+    hb.n_scales = n_scales;
+    hb.channels = 22;
+    hb.parts = 21;
+    for (int i = 0; i < hb.n_crops; ++i) {
+      const islpose_hand_crop& in = h_crops[c0 + i];
+      HandCropDev& c = hb.crop[i];
+      if (in.h <= 0 || in.w <= 0 || static_cast<int64_t>(in.h) * in.w > (1 << 26))
+        return set_err("hand_keypoints: crop %d has a bad size %dx%d", c0 + i, in.h, in.w);
+      c.H = in.h;
+      c.W = in.w;
+      for (int s = 0; s < n_scales; ++s) {
+        const islpose_scale& sc = in.scales[s];
+        if (sc.lowres == nullptr || sc.gh <= 0 || sc.gw <= 0 || sc.hc <= 0 || sc.wc <= 0 || sc.hc > sc.gh * 8 || sc.wc > sc.gw * 8)
+          return set_err("hand_keypoints: crop %d scale %d: inconsistent geometry (grid %dx%d, crop %dx%d)", c0 + i, s, sc.gh,
+                         sc.gw, sc.hc, sc.wc);
+        c.low[s] = sc.lowres;
+        c.gh[s] = sc.gh;
+        c.gw[s] = sc.gw;
+        c.hc[s] = sc.hc;
+        c.wc[s] = sc.wc;
+      }
+      const int64_t elems = 21LL * in.h * in.w;
+      c.heat = reinterpret_cast<double*>(cursor);
+      cursor += (elems * 8 + 255) / 256 * 256;
+      c.mass = reinterpret_cast<double*>(cursor);
+      cursor += (elems * 8 + 255) / 256 * 256;
+      c.labels = reinterpret_cast<int*>(cursor);
+      cursor += (elems * 4 + 255) / 256 * 256;
+      c.out_xy = out_xy + static_cast<int64_t>(c0 + i) * 21 * 2;
+    }
+    if (launch_hand_keypoints(hb, true, gw, thre, st) != 0)
+      return check_cuda("hand_keypoints") ? 1 : set_err("hand_keypoints: launch failed");
+    g_launches.fetch_add(3, std::memory_order_relaxed);
+  }
   return 0;
 }
 

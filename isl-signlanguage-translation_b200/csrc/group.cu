@@ -77,7 +77,7 @@ paf_score_kernel(const ScaleSet ss, const LimbTable lt, int H, int W, int parts,
   const int nB = gb.counts[n * parts + pb];
   const long long total = static_cast<long long>(nA) * nB;
   if (total > gb.pair_cap) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) atomicMax(gb.overflow, 3);
+    if (threadIdx.x == 0 && blockIdx.x == 0) atomicOr(gb.overflow, kOverflowPairs);
     return;
   }
   if (nA > gb.cap || nB > gb.cap) return;  // peak overflow is flagged by the peak kernel
@@ -317,7 +317,7 @@ assemble_kernel(const LimbTable lt, int W, const GroupBuffers gb) {
     }
     s_off[parts] = run;
     gb.n_cand[n] = run < gb.max_cand ? run : gb.max_cand;
-    if (run > gb.max_cand) atomicMax(gb.overflow, 2);
+    if (run > gb.max_cand) atomicOr(gb.overflow, kOverflowCandidates);
   }
   __syncthreads();
   double* cand = gb.candidate + static_cast<long long>(n) * gb.max_cand * 4;
@@ -435,7 +435,7 @@ assemble_kernel(const LimbTable lt, int W, const GroupBuffers gb) {
           }
           ++slots;
         } else if (lane == 0) {
-          atomicMax(gb.overflow, 4);
+          atomicOr(gb.overflow, kOverflowPersons);
         }
       }
       __syncwarp();

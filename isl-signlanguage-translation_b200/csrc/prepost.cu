@@ -1,15 +1,10 @@
 // Memory-bound kernels either side of the networks:
 //   resize_pad_norm   body.py:53-56 / hand.py:37-40   uint8 cubic resize + pad(128) + x/256-0.5 -> fp32 NCHW
-//   im2col3x3         first layer's 3x3x3 patches -> bf16 [N,h,w,32] so conv1_1 runs as a 1x1 GEMM (K=27->32)
-//   maxpool2x2        model.py:30-32, NHWC bf16
 //   heat_accumulate   body.py:69-72,80 / hand.py:51-56  two cubic resizes + scale accumulation, float64 planes
-//   gauss_nms         body.py:88-107  scipy gaussian_filter(sigma=3) + 4-neighbour NMS + threshold -> peak lists
-//   gauss_smooth      hand.py:61      same filter, smoothed plane written out
+//   gauss_nms         body.py:88-107  scipy gaussian_filter(sigma=3) (gauss.cuh) + 4-neighbour NMS + threshold -> peak lists
 //   sort_peaks        np.nonzero row-major order for the atomically appended peak lists
 #include "prepost.cuh"
 
-#include <cuda_bf16.h>
-#include <stdlib.h>
 
 #include "cubic.cuh"
 
@@ -63,67 +58,6 @@ __global__ void resize_pad_norm_kernel(const uint8_t* __restrict__ in, int N, in
   for (int c = 0; c < 3; ++c) {
     out_nchw[(static_cast<long long>(n) * 3 + c) * plane + pix] = __fsub_rn(__fdiv_rn(static_cast<float>(v[c]), 256.f), 0.5f);
     if (out_u8 != nullptr) out_u8[(static_cast<long long>(n) * plane + pix) * 3 + c] = static_cast<uint8_t>(v[c]);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------ im2col
-__global__ void im2col3x3_kernel(const float* __restrict__ in, int N, int h, int w, __nv_bfloat16* __restrict__ out) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y * blockDim.y + threadIdx.y;
-  const int n = blockIdx.z;
-  if (x >= w || y >= h) return;
-  const long long plane = static_cast<long long>(h) * w;
-  const float* img = in + static_cast<long long>(n) * 3 * plane;
-  __align__(16) __nv_bfloat16 v[32];
-#pragma unroll
-  for (int ky = 0; ky < 3; ++ky) {
-#pragma unroll
-    for (int kx = 0; kx < 3; ++kx) {
-      const int yy = y + ky - 1, xx = x + kx - 1;
-      const bool in_img = yy >= 0 && yy < h && xx >= 0 && xx < w;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float f = in_img ? __ldg(img + c * plane + static_cast<long long>(yy) * w + xx) : 0.f;
-        v[(ky * 3 + kx) * 3 + c] = __float2bfloat16_rn(f);
-      }
-    }
-  }
-#pragma unroll
-  for (int i = 27; i < 32; ++i) v[i] = __float2bfloat16_rn(0.f);
-  uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<long long>(n) * plane + static_cast<long long>(y) * w + x) * 32);
-  const uint4* src = reinterpret_cast<const uint4*>(v);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) dst[i] = src[i];
-}
-
-// ------------------------------------------------------------------------------------------------ max pool
-__global__ void maxpool2x2_kernel(const __nv_bfloat16* __restrict__ in, int N, int H, int W, int C,
-                                  __nv_bfloat16* __restrict__ out) {
-  const int c8 = C / 8;
-  const int Ho = H / 2, Wo = W / 2;
-  const long long total = static_cast<long long>(N) * Ho * Wo * c8;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int cg = i % c8;
-    long long p = i / c8;
-    const int xo = p % Wo;
-    p /= Wo;
-    const int yo = p % Ho;
-    const int n = p / Ho;
-    const __nv_bfloat16* base = in + ((static_cast<long long>(n) * H + 2 * yo) * W + 2 * xo) * C + cg * 8;
-    const uint4 a = *reinterpret_cast<const uint4*>(base);
-    const uint4 b = *reinterpret_cast<const uint4*>(base + C);
-    const uint4 c = *reinterpret_cast<const uint4*>(base + static_cast<long long>(W) * C);
-    const uint4 d = *reinterpret_cast<const uint4*>(base + static_cast<long long>(W) * C + C);
-    uint4 r;
-    const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
-    const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
-    const __nv_bfloat162* pc = reinterpret_cast<const __nv_bfloat162*>(&c);
-    const __nv_bfloat162* pd = reinterpret_cast<const __nv_bfloat162*>(&d);
-    __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) pr[k] = __hmax2(__hmax2(pa[k], pb[k]), __hmax2(pc[k], pd[k]));
-    *reinterpret_cast<uint4*>(out + ((static_cast<long long>(n) * Ho + yo) * Wo + xo) * C + cg * 8) = r;
   }
 }
 
@@ -373,176 +307,17 @@ resize_accumulate_kernel(const ScaleSet ss, const MidSet ms, int N, int H, int W
   }
 }
 
-// ------------------------------------------------------------------------------------------------ gaussian
-__device__ __forceinline__ int reflect_index(int e, int n) {
-  // scipy mode='reflect' (d c b a | a b c d | d c b a), valid for any distance
-  const int period = 2 * n;
-  int m = e % period;
-  if (m < 0) m += period;
-  return m >= n ? period - 1 - m : m;
-}
-
-constexpr int kGT = 32;              // output tile edge
-constexpr int kGS = kGT + 2;         // smoothed tile edge (1-pixel ring for the NMS neighbours)
-constexpr int kGR = 12;              // filter radius: int(4.0 * 3 + 0.5)
-constexpr int kGI = kGS + 2 * kGR;   // input tile edge
-
-// NI_Correlate1D, symmetric branch: centre first, then the pairs from the outermost inwards.
-#define ISL_GAUSS_1D(CENTER, PAIR)                                                    \
-  double tmp = __dmul_rn((CENTER), gw.w[kGR]);                                        \
-  _Pragma("unroll") for (int jj = -kGR; jj < 0; ++jj) {                               \
-    tmp = __dadd_rn(tmp, __dmul_rn(PAIR, gw.w[kGR + jj]));                            \
-  }
-
-template <bool kNms>
-__global__ void __launch_bounds__(256)
-gauss_kernel(const double* __restrict__ heat, int planes, int H, int W, const GaussWeights gw, double thre,
-             int cap, int* __restrict__ counts, uint32_t* __restrict__ keys, double* __restrict__ scores,
-             double* __restrict__ smoothed) {
-  __shared__ double s_in[kGI][kGI + 1];   // later reused for the smoothed tile
-  __shared__ double s_v[kGS][kGI + 1];
-  const int plane_id = blockIdx.z;  // n * planes + part
-  const double* src = heat + static_cast<long long>(plane_id) * H * W;
-  const int x0 = blockIdx.x * kGT, y0 = blockIdx.y * kGT;
-  for (int i = threadIdx.x; i < kGI * kGI; i += blockDim.x) {
-    const int r = i / kGI, c = i - r * kGI;
-    s_in[r][c] = src[static_cast<long long>(reflect_index(y0 - 1 - kGR + r, H)) * W + reflect_index(x0 - 1 - kGR + c, W)];
-  }
-  __syncthreads();
-  // axis 0 first (scipy filters the axes in order)
-  for (int i = threadIdx.x; i < kGS * kGI; i += blockDim.x) {
-    const int r = i / kGI, c = i - r * kGI;
-    ISL_GAUSS_1D(s_in[r + kGR][c], __dadd_rn(s_in[r + kGR + jj][c], s_in[r + kGR - jj][c]))
-    s_v[r][c] = tmp;
-  }
-  __syncthreads();
-  double (*s_s)[kGI + 1] = s_in;  // smoothed tile [kGS][kGS] overlays the input tile
-  for (int i = threadIdx.x; i < kGS * kGS; i += blockDim.x) {
-    const int r = i / kGS, c = i - r * kGS;
-    const int ys = y0 - 1 + r, xs = x0 - 1 + c;
-    double val = 0.0;  // outside the frame the NMS neighbours are zero (body.py:90-97)
-    if (ys >= 0 && ys < H && xs >= 0 && xs < W) {
-      ISL_GAUSS_1D(s_v[r][c + kGR], __dadd_rn(s_v[r][c + kGR + jj], s_v[r][c + kGR - jj]))
-      val = tmp;
-    }
-    s_s[r][c] = val;
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < kGT * kGT; i += blockDim.x) {
-    const int r = i / kGT, c = i - r * kGT;
-    const int y = y0 + r, x = x0 + c;
-    if (y >= H || x >= W) continue;
-    const double v = s_s[r + 1][c + 1];
-    if (kNms) {
-      if (v >= s_s[r][c + 1] && v >= s_s[r + 2][c + 1] && v >= s_s[r + 1][c] && v >= s_s[r + 1][c + 2] && v > thre) {
-        const int slot = atomicAdd(counts + plane_id, 1);
-        if (slot < cap) {
-          keys[static_cast<long long>(plane_id) * cap + slot] = static_cast<uint32_t>(y) * W + x;
-          scores[static_cast<long long>(plane_id) * cap + slot] = src[static_cast<long long>(y) * W + x];
-        }
-      }
-    } else {
-      smoothed[static_cast<long long>(plane_id) * H * W + static_cast<long long>(y) * W + x] = v;
-    }
-  }
-}
-
-// Sliding-window variant of the same filter (bit-identical: the very same __dmul_rn/__dadd_rn sequence per output).
-// gauss_kernel above reads 25 shared-memory doubles per output and per axis, which makes it shared-memory-bandwidth
-// bound; here a thread produces kR1 (axis 0) / kR2 (axis 1) consecutive outputs from one register window of
-// kR + 24 inputs, i.e. 2.5 / 3.2 loads per output, which leaves the FP64 pipe as the limiter.
-//   pass 1 (axis 0): lanes = adjacent columns, inputs straight from global memory (coalesced, reflect per index),
-//                    results into s_v[32][90]
-//   pass 2 (axis 1): lanes = rows (odd pitch: conflict-free), window from s_v, results into s_s[32][66]
-//   pass 3: NMS / store of the 30 x 64 interior
-constexpr int kG2W = 64;                 // output tile width
-constexpr int kG2H = 30;                 // output tile height
-constexpr int kG2SW = kG2W + 2;          // smoothed tile (1-pixel ring)
-constexpr int kG2SH = kG2H + 2;          // 32
-constexpr int kG2IW = kG2SW + 2 * kGR;   // 90 columns enter pass 1
-constexpr int kR1 = 16;                  // axis-0 outputs per thread (2 chunks cover 32 rows)
-constexpr int kR2 = 11;                  // axis-1 outputs per thread (6 chunks cover 66 columns)
-constexpr int kG2Threads = 192;
-static_assert(kG2SH % kR1 == 0 && kG2SW % kR2 == 0, "tile / chunk mismatch");
-static_assert((kG2SH / kR1) * kG2IW <= kG2Threads && (kG2SW / kR2) * kG2SH <= kG2Threads, "one work item per thread");
-
-template <bool kNms>
+// ------------------------------------------------------------------------------------------------ gaussian + NMS
+// body.py:88-107 on every (frame, part) plane: gauss.cuh's sliding-window filter, then the 4-neighbour NMS against
+// zero-filled borders and the threshold; peaks are appended to the plane's list (sorted afterwards).
 __global__ void __launch_bounds__(kG2Threads)
-gauss_window_kernel(const double* __restrict__ heat, int H, int W, const GaussWeights gw, double thre, int cap,
-                    int* __restrict__ counts, uint32_t* __restrict__ keys, double* __restrict__ scores,
-                    double* __restrict__ smoothed) {
-  __shared__ double s_v[kG2SH][kG2IW + 1];   // pitch 91 doubles (odd)
-  __shared__ double s_s[kG2SH][kG2SW + 1];   // pitch 67 doubles (odd)
-  const int plane_id = blockIdx.z;
-  const double* src = heat + static_cast<long long>(plane_id) * H * W;
-  const int x0 = blockIdx.x * kG2W, y0 = blockIdx.y * kG2H;
-  {
-    const int item = threadIdx.x;
-    if (item < (kG2SH / kR1) * kG2IW) {
-      const int chunk = item / kG2IW, c = item - chunk * kG2IW;
-      const int xg = x0 - 1 - kGR + c;
-      const double* col = src + ((xg >= 0 && xg < W) ? xg : reflect_index(xg, W));
-      double win[kR1 + 2 * kGR];
-      const int ybase = y0 - 1 - kGR + chunk * kR1;
-      if (ybase >= 0 && ybase + kR1 + 2 * kGR <= H) {  // interior: no reflection, no index arithmetic per load
-        const double* p = col + static_cast<long long>(ybase) * W;
-#pragma unroll
-        for (int k = 0; k < kR1 + 2 * kGR; ++k) win[k] = __ldg(p + static_cast<long long>(k) * W);
-      } else {
-#pragma unroll
-        for (int k = 0; k < kR1 + 2 * kGR; ++k) win[k] = __ldg(col + static_cast<long long>(reflect_index(ybase + k, H)) * W);
-      }
-#pragma unroll
-      for (int o = 0; o < kR1; ++o) {
-        double tmp = __dmul_rn(win[o + kGR], gw.w[kGR]);
-#pragma unroll
-        for (int jj = -kGR; jj < 0; ++jj)
-          tmp = __dadd_rn(tmp, __dmul_rn(__dadd_rn(win[o + kGR + jj], win[o + kGR - jj]), gw.w[kGR + jj]));
-        s_v[chunk * kR1 + o][c] = tmp;
-      }
-    }
-  }
-  __syncthreads();
-  {
-    const int item = threadIdx.x;
-    if (item < (kG2SW / kR2) * kG2SH) {
-      const int chunk = item / kG2SH, r = item - chunk * kG2SH;
-      const int c0 = chunk * kR2;
-      double win[kR2 + 2 * kGR];
-#pragma unroll
-      for (int k = 0; k < kR2 + 2 * kGR; ++k) win[k] = s_v[r][c0 + k];
-      const int ys = y0 - 1 + r;
-      const bool row_in = ys >= 0 && ys < H;
-#pragma unroll
-      for (int o = 0; o < kR2; ++o) {
-        double tmp = __dmul_rn(win[o + kGR], gw.w[kGR]);
-#pragma unroll
-        for (int jj = -kGR; jj < 0; ++jj)
-          tmp = __dadd_rn(tmp, __dmul_rn(__dadd_rn(win[o + kGR + jj], win[o + kGR - jj]), gw.w[kGR + jj]));
-        const int xs = x0 - 1 + c0 + o;
-        // outside the frame the NMS neighbours are zero (body.py:90-97)
-        s_s[r][c0 + o] = (row_in && xs >= 0 && xs < W) ? tmp : 0.0;
-      }
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < kG2H * kG2W; i += kG2Threads) {
-    const int r = i / kG2W, c = i - r * kG2W;
-    const int y = y0 + r, x = x0 + c;
-    if (y >= H || x >= W) continue;
-    const double v = s_s[r + 1][c + 1];
-    if (kNms) {
-      if (v >= s_s[r][c + 1] && v >= s_s[r + 2][c + 1] && v >= s_s[r + 1][c] && v >= s_s[r + 1][c + 2] && v > thre) {
-        const int slot = atomicAdd(counts + plane_id, 1);
-        if (slot < cap) {
-          keys[static_cast<long long>(plane_id) * cap + slot] = static_cast<uint32_t>(y) * W + x;
-          scores[static_cast<long long>(plane_id) * cap + slot] = src[static_cast<long long>(y) * W + x];
-        }
-      }
-    } else {
-      smoothed[static_cast<long long>(plane_id) * H * W + static_cast<long long>(y) * W + x] = v;
-    }
-  }
+gauss_nms_kernel(const double* __restrict__ heat, int H, int W, const GaussWeights gw, double thre, int cap,
+                 int* __restrict__ counts, uint32_t* __restrict__ keys, double* __restrict__ scores) {
+  __shared__ GaussSmem sm;
+  const int plane_id = blockIdx.z;  // n * parts + part
+  gauss_window_tile<kGaussPeaks>(sm, heat + static_cast<long long>(plane_id) * H * W, H, W, blockIdx.x * kG2W, blockIdx.y * kG2H,
+                                 gw, thre, cap, counts + plane_id, keys + static_cast<long long>(plane_id) * cap,
+                                 scores + static_cast<long long>(plane_id) * cap, nullptr);
 }
 
 // One CTA per (frame, part): bitonic sort of the appended peaks by y*W+x = np.nonzero order.
@@ -556,7 +331,7 @@ sort_peaks_kernel(int cap, int* __restrict__ counts, uint32_t* __restrict__ keys
   int n = counts[id];
   if (n > cap) {
     if (threadIdx.x == 0) {
-      atomicExch(overflow, 1);
+      atomicOr(overflow, kOverflowPeaks);
       counts[id] = cap;
     }
     n = cap;
@@ -599,38 +374,12 @@ sort_peaks_kernel(int cap, int* __restrict__ counts, uint32_t* __restrict__ keys
 // ------------------------------------------------------------------------------------------------ launchers
 #define ISL_LAUNCH_OK() (cudaGetLastError() == cudaSuccess ? 0 : 1)
 
-// ISLPOSE_GAUSS=1 selects the first-generation tile kernel (kept for A/B measurements; results are identical)
-static int gauss_variant() {
-  static const int v = [] {
-    const char* e = getenv("ISLPOSE_GAUSS");
-    return (e != nullptr && e[0] == '1') ? 1 : 2;
-  }();
-  return v;
-}
-
 int launch_resize_pad_norm(const uint8_t* frames, int N, int H, int W, double scale, int rh, int rw, int hp, int wp,
                            float* out_nchw, uint8_t* out_u8, cudaStream_t st) {
   const dim3 block(32, 8);
   const dim3 grid((wp + 31) / 32, (hp + 7) / 8, N);
   const double inv = 1.0 / scale;  // resize(): scale_x = 1. / inv_scale_x with inv_scale_x = fx
   resize_pad_norm_kernel<<<grid, block, 0, st>>>(frames, N, H, W, rh, rw, hp, wp, inv, inv, out_nchw, out_u8);
-  return ISL_LAUNCH_OK();
-}
-
-int launch_im2col3x3(const float* in, int N, int h, int w, void* out, cudaStream_t st) {
-  const dim3 block(32, 8);
-  const dim3 grid((w + 31) / 32, (h + 7) / 8, N);
-  im2col3x3_kernel<<<grid, block, 0, st>>>(in, N, h, w, static_cast<__nv_bfloat16*>(out));
-  return ISL_LAUNCH_OK();
-}
-
-int launch_maxpool2x2(const void* in, int N, int H, int W, int C, void* out, cudaStream_t st) {
-  const long long total = static_cast<long long>(N) * (H / 2) * (W / 2) * (C / 8);
-  long long blocks = (total + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  if (blocks < 1) blocks = 1;
-  maxpool2x2_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in), N, H, W, C,
-                                                                   static_cast<__nv_bfloat16*>(out));
   return ISL_LAUNCH_OK();
 }
 
@@ -681,26 +430,9 @@ int launch_gauss_nms(const double* heat, int planes_total, int H, int W, const G
                      int* counts, uint32_t* keys, double* scores, int* overflow, cudaStream_t st) {
   if (cap > kSortCap) return 1;
   if (cudaMemsetAsync(counts, 0, sizeof(int) * planes_total, st) != cudaSuccess) return 1;
-  if (gauss_variant() == 1) {
-    const dim3 grid((W + kGT - 1) / kGT, (H + kGT - 1) / kGT, planes_total);
-    gauss_kernel<true><<<grid, 256, 0, st>>>(heat, 0, H, W, gw, thre, cap, counts, keys, scores, nullptr);
-  } else {
-    const dim3 grid((W + kG2W - 1) / kG2W, (H + kG2H - 1) / kG2H, planes_total);
-    gauss_window_kernel<true><<<grid, kG2Threads, 0, st>>>(heat, H, W, gw, thre, cap, counts, keys, scores, nullptr);
-  }
+  const dim3 grid((W + kG2W - 1) / kG2W, (H + kG2H - 1) / kG2H, planes_total);
+  gauss_nms_kernel<<<grid, kG2Threads, 0, st>>>(heat, H, W, gw, thre, cap, counts, keys, scores);
   sort_peaks_kernel<<<planes_total, 512, 0, st>>>(cap, counts, keys, scores, overflow);
-  return ISL_LAUNCH_OK();
-}
-
-int launch_gauss_smooth(const double* heat, int planes_total, int H, int W, const GaussWeights& gw, double* smoothed,
-                        cudaStream_t st) {
-  if (gauss_variant() == 1) {
-    const dim3 grid((W + kGT - 1) / kGT, (H + kGT - 1) / kGT, planes_total);
-    gauss_kernel<false><<<grid, 256, 0, st>>>(heat, 0, H, W, gw, 0.0, 0, nullptr, nullptr, nullptr, smoothed);
-  } else {
-    const dim3 grid((W + kG2W - 1) / kG2W, (H + kG2H - 1) / kG2H, planes_total);
-    gauss_window_kernel<false><<<grid, kG2Threads, 0, st>>>(heat, H, W, gw, 0.0, 0, nullptr, nullptr, nullptr, smoothed);
-  }
   return ISL_LAUNCH_OK();
 }
 

@@ -4,12 +4,9 @@
 #include <stdint.h>
 
 #include "cubic.cuh"
+#include "gauss.cuh"
 
 namespace islpose {
-
-struct GaussWeights {
-  double w[25];  // scipy _gaussian_kernel1d(sigma=3, radius=12), computed by the host in float64
-};
 
 // limbSeq / mapIdx of the body model (body.py:109-126)
 struct LimbTable {
@@ -21,19 +18,22 @@ struct LimbTable {
 
 int launch_resize_pad_norm(const uint8_t* frames, int N, int H, int W, double scale, int rh, int rw, int hp, int wp,
                            float* out_nchw, uint8_t* out_u8, cudaStream_t st);
-int launch_im2col3x3(const float* in, int N, int h, int w, void* out, cudaStream_t st);
 // conv_first.cu: conv1_1 (3 -> 64, 3x3) straight from the float32 NCHW network input; weights bf16 [64][32] with K index
 // (ky*3+kx)*3+c (27 used), out bf16 NHWC with out_cstride channels per pixel
 int launch_conv_first(const float* in, int N, int h, int w, const void* weights, const float* bias, const float* slope,
                       void* out, int out_cstride, cudaStream_t st);
-int launch_maxpool2x2(const void* in, int N, int H, int W, int C, void* out, cudaStream_t st);
 long long heat_accumulate_workspace_floats(const ScaleSet& ss, int N, int parts);
 int launch_heat_accumulate(const ScaleSet& ss, int N, int H, int W, int parts, int q1, double* out, float* workspace,
                            long long workspace_floats, cudaStream_t st);
 int launch_gauss_nms(const double* heat, int planes_total, int H, int W, const GaussWeights& gw, double thre, int cap,
                      int* counts, uint32_t* keys, double* scores, int* overflow, cudaStream_t st);
-int launch_gauss_smooth(const double* heat, int planes_total, int H, int W, const GaussWeights& gw, double* smoothed,
-                        cudaStream_t st);
+
+// pack.cu: float32 [cout][cin][k][k] -> bf16 [k*k][cout][w_cin] in buffer channel order (conv1_1: [1][cout][32])
+int launch_pack_conv_weights(const float* w, int cout, int cin, int ksize, const int* chan_map, int in_c, int w_cin, int first,
+                             void* out, cudaStream_t st);
+
+// Capacity flags OR-ed into the `overflow` word (one bit each, so that one cannot mask another)
+enum { kOverflowPeaks = 1, kOverflowCandidates = 2, kOverflowPairs = 4, kOverflowPersons = 8 };
 
 // group.cu
 struct GroupBuffers {
@@ -64,8 +64,27 @@ int launch_paf_score(const ScaleSet& paf, const LimbTable& lt, int N, int H, int
                      const GroupBuffers& gb, cudaStream_t st);
 int launch_group(const LimbTable& lt, int N, int W, const GroupBuffers& gb, cudaStream_t st);
 
-// hand.cu
-int launch_hand_peaks(const double* heat, const double* smoothed, int planes_total, int H, int W, double thre,
-                      int* labels, double* mass, int32_t* out_xy, cudaStream_t st);
+// hand.cu: key points of up to kHandMaxCrops crops (of any sizes) per launch chain
+constexpr int kHandMaxCrops = 32;
+constexpr int kHandMaxScales = 4;  // hand.py:25 fixes the list at four scales
+struct HandCropDev {
+  int H, W;                          // crop size
+  const float* low[kHandMaxScales];  // this crop's network output per scale: fp32 [channels][gh][gw]
+  int gh[kHandMaxScales], gw[kHandMaxScales];  // stride-8 grid
+  int hc[kHandMaxScales], wc[kHandMaxScales];  // up-sampled extent after cropping the pad
+  double* heat;                      // [parts][H][W] float64 mean over the scales (hand.py:56)
+  int* labels;                       // [parts][H][W] scratch
+  double* mass;                      // [parts][H][W] scratch
+  int32_t* out_xy;                   // [parts][2]
+};
+struct HandBatch {
+  int n_crops;
+  int n_scales;
+  int channels;  // 22: the row length OpenCV sees is W * channels
+  int parts;     // 21 planes are evaluated (hand.py:58)
+  HandCropDev crop[kHandMaxCrops];
+};
+// compute_heat = false: crop[i].heat already holds the float64 maps (islpose_hand_peaks)
+int launch_hand_keypoints(const HandBatch& hb, bool compute_heat, const GaussWeights& gw, double thre, cudaStream_t st);
 
 }  // namespace islpose

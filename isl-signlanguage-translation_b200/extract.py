@@ -105,6 +105,7 @@ class KeypointExtractor(object):
         lanes = self._lane_streams(torch)
         main = torch.cuda.current_stream()
         it = iter(batches)
+        crops_cut = [None, None]   # per lane: the hand crops of the lane's previous batch have been copied out of its staging buffer
 
         def start_body(idx):
             try:
@@ -112,7 +113,9 @@ class KeypointExtractor(object):
             except StopIteration:
                 return None
             if not torch.is_tensor(frames):
-                frames = self.body.upload(frames, lane=idx % 2)
+                # the lane's staging buffer is about to be overwritten: its last readers are the body kernels of batch
+                # idx - 2 (finished: their results were collected) and the crop copies of that batch on the hand stream
+                frames = self.body.upload(frames, lane=idx % 2, after=crops_cut[idx % 2])
             ready = torch.cuda.Event()
             ready.record(main)
             st = lanes[idx % 2]
@@ -145,6 +148,9 @@ class KeypointExtractor(object):
                         for (x, y, w, is_left) in fb:
                             crops.append(frames[fi, y:y + w, x:x + w, :].contiguous())
                             owner.append((fi, x, y))
+                    cut = torch.cuda.Event()
+                    cut.record(st)
+                    crops_cut[idx % 2] = cut
                     hticket = self.hand.enqueue(crops, lane=idx % 2) if crops else None
             if pending is not None:
                 yield finish_hand(pending)

@@ -10,9 +10,10 @@ import numpy as np
 import torch
 
 from . import _lib
-from .body import _load_flat, scale_geometry
+from .body import scale_geometry
 from .nets import PoseNet
 from .util import gaussian_weights
+from .weights import load_flat
 
 
 def _pow2_at_least(n):
@@ -23,32 +24,38 @@ def _pow2_at_least(n):
 
 
 class Hand(object):
+    MAX_CROPS_PER_REPLAY = 32   # crops per network replay: bounds the plan buffers (2.2 GB per 64-channel full-resolution
+                                # buffer at 32 x 736 x 736); more crops run as consecutive replays of the same plans
+
     def __init__(self, model_path, device=None, tuning=None):
-        self.model = PoseNet('hand', _load_flat(model_path), device=device, tuning=tuning)
+        self.model = PoseNet('hand', load_flat(model_path), device=device, tuning=tuning)
         self.device = self.model.device
         self.scale_search = [0.5, 1.0, 1.5, 2.0]   # hand.py:25
         self.boxsize, self.stride, self.padValue, self.thre = 368, 8, 128, 0.05
         self._gauss = (C.c_double * 25)(*gaussian_weights().tolist())
         self._streams = {}   # lane -> side streams
+        self._work = {}      # lane -> (uint8 scratch tensor for the key-point kernels, int32 results)
 
     def __call__(self, oriImg):
         return self.batch([oriImg])[0]
 
     def network_outputs(self, crops_dev, lane=0):
         """crops_dev: list of uint8 cuda tensors [h,w,3]. Crops whose network inputs have the same shape (all square
-        crops do: 184, 368, 552, 736) share a batched plan per scale. Returns per crop a list of
-        (heat tensor, plane offset in elements, geometry)."""
+        crops do: 184, 368, 552, 736) share one batched replay per scale, sized for exactly that many crops: the plan
+        records its launches over the leading images of a power-of-two sized set of buffers, so no padded image is
+        ever computed. Returns per crop a list of (heat tensor, plane offset in elements, geometry)."""
         L = _lib.lib()
         geoms = [scale_geometry(c.shape[0], c.shape[1], self.scale_search, self.boxsize) for c in crops_dev]
         per_crop = [[] for _ in crops_dev]
         # plan instances are created (and their buffers zero-filled) before the streams fork
-        group_sizes = {}
-        for g in geoms:
-            for si in range(len(self.scale_search)):
-                key = (si, g[si][3], g[si][4])
-                group_sizes[key] = group_sizes.get(key, 0) + 1
-        for (si, hp, wp), cnt in group_sizes.items():
-            self.model.instance(_pow2_at_least(cnt), hp, wp, lane)
+        groups_of = []
+        for si in range(len(self.scale_search)):
+            groups = {}
+            for ci, g in enumerate(geoms):
+                groups.setdefault((g[si][3], g[si][4]), []).append(ci)
+            groups_of.append(groups)
+            for (hp, wp), members in groups.items():
+                self.model.instance(len(members), hp, wp, lane, exact_of=_pow2_at_least(len(members)))
         streams = self._streams.setdefault(lane, [])
         main = torch.cuda.current_stream()
         timing = self.model.timing
@@ -60,16 +67,13 @@ class Hand(object):
         flops = launches = 0
         used = 0
         for si in range(len(self.scale_search)):
-            groups = {}
-            for ci, g in enumerate(geoms):
-                groups.setdefault((g[si][3], g[si][4]), []).append(ci)
-            for (hp, wp), members in groups.items():
+            for (hp, wp), members in groups_of[si].items():
                 # every (scale, input shape) group is an independent network replay: one stream each
                 while len(streams) <= used:
                     streams.append(torch.cuda.Stream(device=self.device))
                 side = streams[used]
                 used += 1
-                inst = self.model.instance(_pow2_at_least(len(members)), hp, wp, lane)
+                inst = self.model.instance(len(members), hp, wp, lane, exact_of=_pow2_at_least(len(members)))
                 with torch.cuda.stream(side):
                     side.wait_event(fork)
                     for slot, ci in enumerate(members):
@@ -82,7 +86,7 @@ class Hand(object):
                     done = torch.cuda.Event()
                     done.record(side)
                     main.wait_event(done)
-                flops += inst.flops_algorithmic * len(members) // inst.n
+                flops += inst.flops_algorithmic
                 launches += inst.launches + len(members)
                 plane = 22 * (hp // 8) * (wp // 8)
                 for slot, ci in enumerate(members):
@@ -92,29 +96,35 @@ class Hand(object):
             timing.append((t0, t1, flops, launches))
         return per_crop
 
-    def postprocess(self, maps, h, w):
-        """maps: [(heat tensor, element offset, (rh, rw, hp, wp))] for one crop -> int array [21,2]."""
+    def keypoints(self, per_crop, sizes, out, lane=0):
+        """per_crop[i]: [(heat tensor, element offset, (rh, rw, hp, wp))] per scale, sizes[i] = (h, w) of crop i;
+        out: int32 cuda tensor [len(sizes), 21, 2] that receives (x, y). Three launches for up to 32 crops, on the
+        current stream, inside one scratch buffer per lane."""
         L = _lib.lib()
-        st = _lib.stream_ptr()
-        dev = self.device
-        arr = (_lib.Scale * len(maps))()
-        for i, (t, off, (rh, rw, hp, wp)) in enumerate(maps):
-            arr[i].lowres = t.data_ptr() + 4 * off
-            arr[i].gh, arr[i].gw, arr[i].hc, arr[i].wc = hp // 8, wp // 8, rh, rw
-        heat = torch.empty((21, h, w), dtype=torch.float64, device=dev)
-        smoothed = torch.empty((21, h, w), dtype=torch.float64, device=dev)
-        labels = torch.empty((21, h, w), dtype=torch.int32, device=dev)
-        mass = torch.empty((21, h, w), dtype=torch.float64, device=dev)
-        out = torch.zeros((21, 2), dtype=torch.int32, device=dev)
-        # small crops: one pass (fewer launches); large crops: materialise the up-sampled maps first (less arithmetic)
-        mid = None
-        if h * w >= 256 * 256:
-            mid = torch.empty((L.islpose_maps_workspace_floats(arr, len(maps), 1, 21),), dtype=torch.float32, device=dev)
-        _lib.check(L.islpose_maps_accumulate(arr, len(maps), 22, 1, h, w, 21, 0, _lib.ptr(heat), _lib.ptr(mid),
-                                             mid.numel() if mid is not None else 0, st), "islpose_maps_accumulate")
-        _lib.check(L.islpose_hand_peaks(_lib.ptr(heat), 21, h, w, self._gauss, self.thre, _lib.ptr(smoothed),
-                                        _lib.ptr(labels), _lib.ptr(mass), _lib.ptr(out), st), "islpose_hand_peaks")
-        return out
+        n = len(sizes)
+        crops = (_lib.HandCrop * n)()
+        for i, (maps, (h, w)) in enumerate(zip(per_crop, sizes)):
+            crops[i].h, crops[i].w = h, w
+            for s, (t, off, (rh, rw, hp, wp)) in enumerate(maps):
+                sc = crops[i].scales[s]
+                sc.lowres = t.data_ptr() + 4 * off
+                sc.gh, sc.gw, sc.hc, sc.wc = hp // 8, wp // 8, rh, rw
+        need = L.islpose_hand_workspace_bytes(crops, n)
+        ws = self._work.get(lane)
+        if ws is None or ws.numel() < need:
+            # the previous (smaller) buffer may still be in use by launches in flight on this lane: let the caching
+            # allocator keep it alive for them (record_stream) instead of synchronising
+            if ws is not None:
+                ws.record_stream(torch.cuda.current_stream())
+            ws = self._work[lane] = torch.empty((int(need * 1.25) + 256,), dtype=torch.uint8, device=self.device)
+        _lib.check(L.islpose_hand_keypoints(crops, n, len(self.scale_search), self._gauss, self.thre, _lib.ptr(ws), ws.numel(),
+                                            _lib.ptr(out), _lib.stream_ptr()), "islpose_hand_keypoints")
+
+    def postprocess(self, maps, h, w):
+        """maps: [(heat tensor, element offset, (rh, rw, hp, wp))] for one crop -> int32 cuda tensor [21,2]."""
+        out = torch.zeros((1, 21, 2), dtype=torch.int32, device=self.device)
+        self.keypoints([maps], [(h, w)], out)
+        return out[0]
 
     def batch(self, crops):
         crops = [np.ascontiguousarray(c) for c in crops]
@@ -126,9 +136,6 @@ class Hand(object):
         with torch.cuda.device(self.device):
             return self.batch_device([torch.from_numpy(c).to(self.device, non_blocking=True) for c in crops])
 
-    MAX_CROPS_PER_REPLAY = 32   # crops per network replay: bounds the plan buffers (2.2 GB per 64-channel full-resolution
-                                # buffer at 32 x 736 x 736); more crops run as consecutive replays of the same plans
-
     def enqueue(self, dev_crops, lane=0):
         """Launches the four network scales and the key-point selection of every crop (list of contiguous uint8
         cuda tensors [h,w,3]) without waiting; finish(ticket) returns the list of int64 [21,2] arrays."""
@@ -136,34 +143,18 @@ class Hand(object):
             return None
         with torch.cuda.device(self.device):
             main = torch.cuda.current_stream()
-            outs = []
+            out = torch.zeros((len(dev_crops), 21, 2), dtype=torch.int32, device=self.device)
             for a in range(0, len(dev_crops), self.MAX_CROPS_PER_REPLAY):
                 part = dev_crops[a:a + self.MAX_CROPS_PER_REPLAY]
                 per_crop = self.network_outputs(part, lane)
-                # a crop's post-processing launches only 21 CTAs per kernel: spread the crops over a few streams; the
-                # join below also keeps the next replay from overwriting network outputs that are still being read
-                fork = torch.cuda.Event()
-                fork.record(main)
-                lanes = min(len(part), 8)
-                streams = self._streams.setdefault(lane, [])
-                while len(streams) < lanes:
-                    streams.append(torch.cuda.Stream(device=self.device))
-                for i in range(len(part)):
-                    side = streams[i % lanes] if lanes > 1 else main
-                    with torch.cuda.stream(side):
-                        side.wait_event(fork)
-                        outs.append(self.postprocess(per_crop[i], part[i].shape[0], part[i].shape[1]))
-                if lanes > 1:
-                    for j in range(lanes):
-                        done = torch.cuda.Event()
-                        done.record(streams[j])
-                        main.wait_event(done)
-            stacked = torch.stack(outs)
-            host = torch.empty(stacked.shape, dtype=stacked.dtype).pin_memory()
-            host.copy_(stacked, non_blocking=True)
+                # the key-point kernels run on the main stream, so the next replay (whose network streams fork from
+                # main) cannot overwrite network outputs that are still being read
+                self.keypoints(per_crop, [(c.shape[0], c.shape[1]) for c in part], out[a:a + len(part)], lane)
+            host = torch.empty(out.shape, dtype=out.dtype).pin_memory()
+            host.copy_(out, non_blocking=True)
             done = torch.cuda.Event()
             done.record(main)
-        return dict(host=host, done=done, n=len(dev_crops), keep=(outs, stacked, dev_crops))
+        return dict(host=host, done=done, n=len(dev_crops), keep=(out, dev_crops))
 
     def finish(self, ticket):
         if ticket is None:

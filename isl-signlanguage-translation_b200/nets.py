@@ -202,84 +202,57 @@ def _up64(c):
     return (c + 63) // 64 * 64
 
 
-def _pack_weight(w, chan_map, in_c, first):
-    """nn.Conv2d weight [cout, cin, k, k] float32 -> bf16 [k*k, cout, up64(in_c)] in the buffer's channel order
-    (zero beyond in_c, so that a 64-channel TMA box never leaves the tensor)."""
-    packed = _pack_weight_exact(w, chan_map, in_c, first)
-    if packed.shape[2] % 64 == 0 or first:
-        return packed
-    out = torch.zeros((packed.shape[0], packed.shape[1], _up64(in_c)), dtype=packed.dtype)
-    out[:, :, :in_c] = packed
-    return out.contiguous()
-
-
-def _pack_weight_exact(w, chan_map, in_c, first):
-    cout, cin, k, _ = w.shape
-    if first:  # conv1_1 as a 1x1 GEMM over gathered patches: K index = (ky*3+kx)*3 + c
-        packed = torch.zeros((1, cout, in_c), dtype=torch.float32)
-        packed[0, :, :27] = w.permute(0, 2, 3, 1).reshape(cout, 27)
-        return packed.to(torch.bfloat16).contiguous()
-    taps = w.permute(2, 3, 0, 1).reshape(k * k, cout, cin)  # [tap, cout, cin]
-    if chan_map is None:
-        if cin != in_c:
-            raise ValueError("slice width %d does not match Cin %d" % (in_c, cin))
-        return taps.to(torch.bfloat16).contiguous()
-    packed = torch.zeros((k * k, cout, in_c), dtype=torch.float32)
-    idx = [(i, c) for i, c in enumerate(chan_map) if c is not None]
-    dst = torch.tensor([i for i, _ in idx], dtype=torch.long)
-    srcc = torch.tensor([c for _, c in idx], dtype=torch.long)
-    if sorted(srcc.tolist()) != list(range(cin)):
-        raise ValueError("channel map does not cover Cin=%d exactly once" % cin)
-    packed[:, :, dst] = taps[:, :, srcc]
-    return packed.to(torch.bfloat16).contiguous()
-
-
 class _Instance:
-    """One (batch, h, w) instantiation: device buffers + the C launch plan."""
+    """One (batch, h, w) instantiation: device buffers + the C launch plan.
 
-    def __init__(self, net, n, h, w):
+    `share` = an instance of the same (h, w) with a batch size >= n: this one then records its plan over the leading n
+    images of that instance's buffers (NHWC / NCHW batch prefixes are contiguous) and owns no memory of its own - an
+    exact-size replay for the cost of a few hundred tensor-map encodings."""
+
+    def __init__(self, net, n, h, w, share=None):
         L = _lib.lib()
         dev = net.device
         self.net = net
         self.n, self.h, self.w = n, h, w
         self.flops_algorithmic = algorithmic_flops(net.kind, n, h, w)
-        self.input = torch.empty((n, 3, h, w), dtype=torch.float32, device=dev)
-        self.bufs = {}
-        fused_first = not net.tuning.get("unfused_first", False)
-        fuse_pool = not net.tuning.get("unfused_pool", False)
         steps = net.program.steps
 
         def pool_fusable(si):
-            """conv step si followed by a max-pool of its own output, in a shape the halo kernel takes (conv_prepare)."""
+            """conv step si followed by a max-pool of its own output (all three pools of all three networks are)."""
             s, nxt = steps[si][1], steps[si + 1] if si + 1 < len(steps) else None
-            return (fuse_pool and nxt is not None and nxt[0] == "pool" and s["dst"] is not None and nxt[1] == s["dst"][0]
+            return (nxt is not None and nxt[0] == "pool" and s["dst"] is not None and nxt[1] == s["dst"][0]
                     and s["k"] >= 3 and s["src"][2] >= 64 and s["cout"] >= 48 and s["f32"] is None and not s["first"])
 
-        # buffers some launch actually touches (a fused first layer needs no patch buffer, a fused pool no full-size output)
-        used = set()
-        for si, step in enumerate(steps):
-            if step[0] == "im2col":
-                if not fused_first:
-                    used.add(step[1])
-            elif step[0] == "pool":
-                if not (si > 0 and steps[si - 1][0] == "conv" and pool_fusable(si - 1)):
-                    used.update((step[1], step[2]))
-            else:
-                s = step[1]
-                if not (s["first"] and fused_first):
-                    used.add(s["src"][0])
-                if pool_fusable(si):
-                    used.add(steps[si + 1][2])
-                elif s["dst"] is not None:
-                    used.add(s["dst"][0])
-        for name, (ch, level) in net.program.bufs.items():
-            if name not in used:
-                continue
-            # physical width rounded up to 64 channels (zeros, never written): every 64-channel box is in bounds
-            self.bufs[name] = torch.zeros((n, h >> level, w >> level, _up64(ch) if ch > 32 else ch), dtype=torch.bfloat16,
-                                          device=dev)
-        gh, gw = h // 8, w // 8
-        self.outputs = [torch.empty((n, ch, gh, gw), dtype=torch.float32, device=dev) for _, ch in net.program.outputs]
+        if share is not None:
+            if share.h != h or share.w != w or share.n < n or share.net is not net:
+                raise ValueError("cannot share buffers of a %dx%dx%d instance for %dx%dx%d" % (share.n, share.h, share.w, n, h, w))
+            self.input = share.input[:n]
+            self.bufs = {k: v[:n] for k, v in share.bufs.items()}
+            self.outputs = [o[:n] for o in share.outputs]
+            self._keep = share
+        else:
+            self.input = torch.empty((n, 3, h, w), dtype=torch.float32, device=dev)
+            self.bufs = {}
+            # buffers some launch actually touches (the fused first layer needs no patch buffer, a fused pool no
+            # full-size output)
+            used = set()
+            for si, step in enumerate(steps):
+                if step[0] == "conv":
+                    s = step[1]
+                    if not s["first"]:
+                        used.add(s["src"][0])
+                    if pool_fusable(si):
+                        used.add(steps[si + 1][2])
+                    elif s["dst"] is not None:
+                        used.add(s["dst"][0])
+            for name, (ch, level) in net.program.bufs.items():
+                if name not in used:
+                    continue
+                # physical width rounded up to 64 channels (zeros, never written): every 64-channel box is in bounds
+                self.bufs[name] = torch.zeros((n, h >> level, w >> level, _up64(ch) if ch > 32 else ch), dtype=torch.bfloat16,
+                                              device=dev)
+            gh, gw = h // 8, w // 8
+            self.outputs = [torch.empty((n, ch, gh, gw), dtype=torch.float32, device=dev) for _, ch in net.program.outputs]
         handle = C.c_void_p()
         _lib.check(L.islpose_plan_create(C.byref(handle)), "islpose_plan_create")
         self.handle = handle
@@ -288,66 +261,60 @@ class _Instance:
         self.op_names = []   # one name per recorded launch (tools/layer_times.py)
         for si, step in enumerate(steps):
             if step[0] == "im2col":
-                if not fused_first:
-                    _lib.check(L.islpose_plan_add_im2col3x3(handle, _lib.ptr(self.input), _lib.ptr(self.bufs[step[1]]), n, h, w),
-                               "islpose_plan_add_im2col3x3")
-                    self.op_names.append("im2col")
-            elif step[0] == "pool":
-                if si in fused_pools:
-                    continue   # done in the epilogue of the layer before it
-                src, dst = self.bufs[step[1]], self.bufs[step[2]]
-                _lib.check(L.islpose_plan_add_maxpool2x2(handle, _lib.ptr(src), _lib.ptr(dst), n, src.shape[1], src.shape[2],
-                                                         src.shape[3]), "islpose_plan_add_maxpool2x2")
-                self.op_names.append("pool")
-            else:
-                s = step[1]
-                wt, bias, slope = net.packed[ci]
-                ci += 1
-                if s["first"] and fused_first:
-                    # conv1_1 in one launch straight from the float32 network input (csrc/conv_first.cu)
-                    db = self.bufs[s["dst"][0]]
-                    _lib.check(L.islpose_plan_add_first_conv(handle, _lib.ptr(self.input), _lib.ptr(wt), _lib.ptr(bias),
-                                                             _lib.ptr(slope), C.c_void_p(db.data_ptr() + 2 * s["dst"][1]),
-                                                             db.shape[3], n, h, w), "islpose_plan_add_first_conv")
-                    self.op_names.append(s["layer"])
-                    continue
-                sb = self.bufs[s["src"][0]]
-                d = _lib.ConvDesc()
-                d.in_ = sb.data_ptr() + 2 * s["src"][1]
-                d.in_c = s["src"][2]
-                d.in_cstride = sb.shape[3]
-                d.in_c_readable = sb.shape[3] - s["src"][1]
-                d.w_cin = wt.shape[2]
-                d.n, d.h, d.w = n, sb.shape[1], sb.shape[2]
-                d.weights = wt.data_ptr()
-                d.cout = wt.shape[1]
-                d.ksize = 1 if s["first"] else s["k"]
-                d.bias = bias.data_ptr()
-                d.slope = slope.data_ptr()
-                if pool_fusable(si):
-                    # nn.MaxPool2d(2, 2) fused into this layer's epilogue: the full-resolution tensor is never written
-                    db = self.bufs[steps[si + 1][2]]
-                    d.out_bf16 = db.data_ptr()
-                    d.out_cstride = db.shape[3]
-                    d.pool = 1
-                    fused_pools.add(si + 1)
-                elif s["dst"] is not None:
-                    db = self.bufs[s["dst"][0]]
-                    d.out_bf16 = db.data_ptr() + 2 * s["dst"][1]
-                    d.out_cstride = db.shape[3]
-                if s["f32"] is not None:
-                    o = self.outputs[s["f32"]]
-                    d.out_f32 = o.data_ptr()
-                    d.out_f32_channels = o.shape[1]
-                cfg = net.tuning
-                d.n_tile, d.stages = cfg.get("n_tile", 0), cfg.get("stages", 0)
-                _lib.check(L.islpose_plan_add_conv(handle, C.byref(d)), "islpose_plan_add_conv(%s)" % s["layer"])
-                self.op_names.append(s["layer"] + ("+pool" if d.pool else ""))
+                continue   # conv1_1 gathers its patches itself (csrc/conv_first.cu)
+            if step[0] == "pool":
+                if si not in fused_pools:
+                    raise _lib.IslposeError("max-pool after %r cannot be fused into its producer" % (steps[si - 1],))
+                continue   # done in the epilogue of the layer before it
+            s = step[1]
+            wt, bias, slope = net.packed[ci]
+            ci += 1
+            if s["first"]:
+                # conv1_1 in one launch straight from the float32 network input (csrc/conv_first.cu)
+                db = self.bufs[s["dst"][0]]
+                _lib.check(L.islpose_plan_add_first_conv(handle, _lib.ptr(self.input), _lib.ptr(wt), _lib.ptr(bias),
+                                                         _lib.ptr(slope), C.c_void_p(db.data_ptr() + 2 * s["dst"][1]),
+                                                         db.shape[3], n, h, w), "islpose_plan_add_first_conv")
+                self.op_names.append(s["layer"])
+                continue
+            sb = self.bufs[s["src"][0]]
+            d = _lib.ConvDesc()
+            d.in_ = sb.data_ptr() + 2 * s["src"][1]
+            d.in_c = s["src"][2]
+            d.in_cstride = sb.shape[3]
+            d.in_c_readable = sb.shape[3] - s["src"][1]
+            d.w_cin = wt.shape[2]
+            d.n, d.h, d.w = n, sb.shape[1], sb.shape[2]
+            d.weights = wt.data_ptr()
+            d.cout = wt.shape[1]
+            d.ksize = s["k"]
+            d.bias = bias.data_ptr()
+            d.slope = slope.data_ptr()
+            if pool_fusable(si):
+                # nn.MaxPool2d(2, 2) fused into this layer's epilogue: the full-resolution tensor is never written
+                db = self.bufs[steps[si + 1][2]]
+                d.out_bf16 = db.data_ptr()
+                d.out_cstride = db.shape[3]
+                d.pool = 1
+                fused_pools.add(si + 1)
+            elif s["dst"] is not None:
+                db = self.bufs[s["dst"][0]]
+                d.out_bf16 = db.data_ptr() + 2 * s["dst"][1]
+                d.out_cstride = db.shape[3]
+            if s["f32"] is not None:
+                o = self.outputs[s["f32"]]
+                d.out_f32 = o.data_ptr()
+                d.out_f32_channels = o.shape[1]
+            cfg = net.tuning
+            d.n_tile, d.stages = cfg.get("n_tile", 0), cfg.get("stages", 0)
+            _lib.check(L.islpose_plan_add_conv(handle, C.byref(d)), "islpose_plan_add_conv(%s)" % s["layer"])
+            self.op_names.append(s["layer"] + ("+pool" if d.pool else ""))
         self.flops = L.islpose_plan_conv_flops(handle)
         self.launches = L.islpose_plan_num_launches(handle)
         # the zero-fills above ran on the current stream, but the plan may be replayed on any stream: make the
         # buffers (in particular their never-written zero pad channels) globally visible before first use
-        torch.cuda.current_stream().synchronize()
+        if share is None:
+            torch.cuda.current_stream().synchronize()
 
     def run(self):
         _lib.check(_lib.lib().islpose_plan_run(self.handle, _lib.stream_ptr()), "islpose_plan_run")
@@ -378,61 +345,142 @@ def algorithmic_flops(kind, n, h, w):
     return total
 
 
-class PoseNet:
-    """Callable network with the reference nn.Module's interface surface (model.py), backed by launch plans."""
+class _LayerParams(torch.nn.Module):
+    """Holds one Caffe layer's tensors so that the module's state-dict keys are the flat Caffe names of the weight
+    files ('conv1_1.weight', 'conv1_1.bias', 'Mprelu1_stage0_L2_0.weight', ...)."""
+
+    def __init__(self, weight, bias=None):
+        super().__init__()
+        self.weight = torch.nn.Parameter(weight, requires_grad=False)
+        if bias is not None:
+            self.bias = torch.nn.Parameter(bias, requires_grad=False)
+
+
+class PoseNet(torch.nn.Module):
+    """The reference nn.Module's interface (model.py: bodypose_model / bodypose_25_model / handpose_model) backed by
+    launch plans: `model(data float32 [N,3,h,w]) -> (PAF, heat)` / `-> heat`, float32 NCHW on the module's device.
+
+    It is a real torch.nn.Module - float32 parameters under the flat Caffe names, state_dict / load_state_dict /
+    named_parameters / eval / to(device) / cuda(device) - so wrappers that only know nn.Module keep working
+    (keras.layers.TorchModuleWrapper in ISL_Model_parameter.py:44-47, `.to(device)` in extract_features_mp.py:150,
+    `for param in self.parameters()` in model.py:167-168). The kernels read bf16 copies of the parameters packed
+    tap-major in buffer channel order; load_state_dict() and to() refresh them. There is no CPU path: to('cpu'),
+    half() or double() raise."""
 
     def __init__(self, kind, flat_weights, device=None, tuning=None):
+        super().__init__()
         if not torch.cuda.is_available():
             raise _lib.IslposeError("PoseNet needs a CUDA device (sm_100a); there is no CPU path")
         _lib.lib()
         self.kind = kind
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        if self.device.type != "cuda":
+            raise _lib.IslposeError("PoseNet runs on CUDA devices only, got %s" % (self.device,))
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.program = build_program(kind)
         self.tuning = dict(tuning or {})
-        self._flat = {k: v.detach().to(torch.float32).cpu() for k, v in flat_weights.items()}
-        self.packed = []
+        seen = set()
         for step in self.program.steps:
-            if step[0] != "conv":
+            if step[0] != "conv" or step[1]["layer"] in seen:
                 continue
             s = step[1]
-            w = self._flat[s["layer"] + ".weight"]
-            b = self._flat[s["layer"] + ".bias"]
-            cout = w.shape[0]
-            if cout != s["cout"] or w.shape[2] != s["k"]:
+            seen.add(s["layer"])
+            w = torch.as_tensor(flat_weights[s["layer"] + ".weight"]).detach().to(torch.float32)
+            b = torch.as_tensor(flat_weights[s["layer"] + ".bias"]).detach().to(torch.float32)
+            cin = 3 if s["first"] else (sum(1 for c in s["chan_map"] if c is not None) if s["chan_map"] else s["src"][2])
+            if tuple(w.shape) != (s["cout"], cin, s["k"], s["k"]) or tuple(b.shape) != (s["cout"],):
                 raise ValueError("%s: weight shape %s does not match the %s network" % (s["layer"], tuple(w.shape), kind))
-            wt = _pack_weight(w, s["chan_map"], s["src"][2], s["first"]).to(self.device)
-            bias = torch.zeros(512, dtype=torch.float32)
-            bias[:cout] = b
-            slope = torch.zeros(512, dtype=torch.float32)
-            if s["act"] == NONE:
-                slope[:cout] = 1.0
-            elif s["act"] == PRELU:
-                slope[:cout] = self._flat[s["prelu"] + ".weight"]
-            self.packed.append((wt, bias.to(self.device), slope.to(self.device)))
+            self.add_module(s["layer"], _LayerParams(w.to(self.device), b.to(self.device)))
+            if s["prelu"] is not None:
+                a = torch.as_tensor(flat_weights[s["prelu"] + ".weight"]).detach().to(torch.float32)
+                self.add_module(s["prelu"], _LayerParams(a.to(self.device)))
+        self.packed = []
         self._instances = {}
         self.timing = None   # set to a list: Body / Hand append (start, end, flops, launches) per network phase (fork to join)
+        self._chan_maps = {}
+        self._pack()
+        self.eval()
 
-    # ---- reference nn.Module surface -------------------------------------------------------------------
-    def parameters(self):
-        return iter(self._flat.values())
+    def _pack(self):
+        """float32 parameters -> the kernels' operands: bf16 [tap][cout][cin of the buffer slice, padded to 64], float32
+        bias and negative-side slope (0 = ReLU, 1 = none, PReLU weight otherwise), packed on the device
+        (csrc/pack.cu). Existing plans keep pointing at the old tensors, so they are dropped."""
+        L = _lib.lib()
+        self._instances = {}
+        packed = []
+        with torch.cuda.device(self.device):
+            st = _lib.stream_ptr()
+            for step in self.program.steps:
+                if step[0] != "conv":
+                    continue
+                s = step[1]
+                lp = getattr(self, s["layer"])
+                w, b = lp.weight.data, lp.bias.data
+                cout, cin, k = w.shape[0], w.shape[1], w.shape[2]
+                in_c = s["src"][2]
+                w_cin = in_c if (s["first"] or in_c % 64 == 0) else _up64(in_c)
+                cmap = None
+                if s["chan_map"] is not None:
+                    key = tuple(-1 if c is None else c for c in s["chan_map"])
+                    if sorted(c for c in key if c >= 0) != list(range(cin)):
+                        raise ValueError("channel map of %s does not cover Cin=%d exactly once" % (s["layer"], cin))
+                    cmap = self._chan_maps.get(key)
+                    if cmap is None:
+                        cmap = self._chan_maps[key] = torch.tensor(key, dtype=torch.int32, device=self.device)
+                elif not s["first"] and cin != in_c:
+                    raise ValueError("%s: slice width %d does not match Cin %d" % (s["layer"], in_c, cin))
+                taps = 1 if s["first"] else k * k
+                wt = torch.empty((taps, cout, w_cin), dtype=torch.bfloat16, device=self.device)
+                _lib.check(L.islpose_pack_conv_weights(_lib.ptr(w.contiguous()), cout, cin, k, _lib.ptr(cmap), in_c, w_cin,
+                                                       1 if s["first"] else 0, _lib.ptr(wt), st), "islpose_pack_conv_weights")
+                bias = torch.zeros(512, dtype=torch.float32, device=self.device)
+                bias[:cout] = b
+                slope = torch.zeros(512, dtype=torch.float32, device=self.device)
+                if s["act"] == NONE:
+                    slope[:cout] = 1.0
+                elif s["act"] == PRELU:
+                    slope[:cout] = getattr(self, s["prelu"]).weight.data
+                packed.append((wt, bias, slope))
+            torch.cuda.current_stream().synchronize()
+        self.packed = packed
 
-    def state_dict(self):
-        return dict(self._flat)
+    # ---- nn.Module surface -----------------------------------------------------------------------------
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        out = super().load_state_dict(state_dict, strict=strict, **kw)
+        self._pack()
+        return out
 
-    def eval(self):
-        return self
+    def _apply(self, fn, *args, **kw):
+        """to() / cuda() / float() arrive here. The parameters must stay float32 on a CUDA device; moving to another
+        GPU re-packs the operands there."""
+        probe = fn(torch.empty(0, dtype=torch.float32, device=self.device))
+        if probe.device.type != "cuda":
+            raise _lib.IslposeError("PoseNet has no CPU path: cannot move it to %s" % (probe.device,))
+        if probe.dtype != torch.float32:
+            raise _lib.IslposeError("PoseNet keeps float32 parameters (bf16 operands are derived from them), not %s" % (probe.dtype,))
+        out = super()._apply(fn, *args, **kw)
+        if probe.device != self.device:
+            self.device = probe.device
+            self._chan_maps = {}
+            self._pack()
+        return out
 
-    def cuda(self, device=None):
-        return self
-
-    def to(self, *args, **kwargs):
-        return self
-
-    def instance(self, n, h, w, lane=0):
+    def instance(self, n, h, w, lane=0, exact_of=None):
         """The plan (and its activation buffers) for one input shape. `lane` selects an independent copy, so that
-        two batches of the same shape can be in flight at once."""
+        two batches of the same shape can be in flight at once. exact_of = a batch capacity >= n: the plan for n
+        images runs inside the buffers of the (capacity, h, w, lane) instance instead of allocating its own."""
         if h % 8 or w % 8:
             raise ValueError("network input must be a multiple of 8 in both dimensions, got %dx%d" % (h, w))
+        if exact_of is not None and exact_of != n:
+            key = (n, h, w, lane, exact_of)
+            inst = self._instances.get(key)
+            if inst is None:
+                parent = self.instance(exact_of, h, w, lane)
+                with torch.cuda.device(self.device):
+                    inst = _Instance(self, n, h, w, share=parent)
+                self._instances[key] = inst
+            return inst
         key = (n, h, w, lane)
         inst = self._instances.get(key)
         if inst is None:
@@ -445,13 +493,13 @@ class PoseNet:
         """Runs the plan for `data`'s shape; returns the plan's own float32 output tensors (overwritten by the
         next call with the same shape)."""
         n, c, h, w = data.shape
-        inst = self.instance(n, h, w)
-        inst.input.copy_(data)
-        inst.run()
+        with torch.cuda.device(self.device):
+            inst = self.instance(n, h, w)
+            inst.input.copy_(data)
+            inst.run()
         return inst.outputs
 
-    def __call__(self, data):
-        outs = [o.clone() for o in self.forward_into(data.to(self.device, torch.float32))]
+    def forward(self, data):
+        with torch.no_grad():
+            outs = [o.clone() for o in self.forward_into(data.to(self.device, torch.float32))]
         return outs[0] if self.kind == "hand" else (outs[0], outs[1])
-
-    forward = __call__

@@ -419,12 +419,27 @@ def make_flat_weights(kind, seed=0, gain=1.0, head_gain=1.0, init="he"):
     return w
 
 
-def net_forward(kind, weights, x):
-    """fp32 forward on CPU. x: torch.float32 [N,3,h,w]. Returns (PAF, heat) for bodies, heat for the hand."""
+def net_forward(kind, weights, x, emulate_bf16=False, device=None):
+    """fp32 forward (model.py), on CPU unless `device` says otherwise. x: torch.float32 [N,3,h,w]. Returns (PAF, heat)
+    for bodies, heat for the hand.
+
+    emulate_bf16: a numerical model of the CUDA path, for tests that want to separate its two error sources - bf16
+    operands (modelled here: weights, the network input and every stored activation rounded to bf16, fp32 accumulation,
+    bias / activation in fp32, the last stage's outputs left in fp32) from accumulation order (not modelled)."""
     import torch
     import torch.nn.functional as F
 
     spec = {l[0]: l for l in net_layers(kind)}
+    if device is not None:
+        weights = {k: v.to(device) for k, v in weights.items()}
+        x = x.to(device)
+    rnd = (lambda t: t.to(torch.bfloat16).to(torch.float32)) if emulate_bf16 else (lambda t: t)
+    if emulate_bf16:
+        weights = {k: (rnd(v) if v.ndim == 4 else v) for k, v in weights.items()}
+        x = rnd(x)
+    last = {"coco": ("Mconv7_stage6_L1", "Mconv7_stage6_L2"), "hand": ("Mconv7_stage6",),
+            "body25": ("Mconv7_stage3_L2", "Mconv7_stage1_L1")}[kind]
+    f32_outs = {}
 
     def conv(name, t):
         _, _, _, k, act, prelu = spec[name]
@@ -433,7 +448,9 @@ def net_forward(kind, weights, x):
             t = F.relu(t)
         elif act == "prelu":
             t = F.prelu(t, weights[prelu + ".weight"])
-        return t
+        if name in last:
+            f32_outs[name] = t   # the network heads leave in fp32; what later stages read of them is the bf16 copy
+        return rnd(t)
 
     def backbone(t, names):
         for n in names:
@@ -450,13 +467,13 @@ def net_forward(kind, weights, x):
             for st in range(2, 7):
                 cat = torch.cat([outs[0], outs[1], feat], 1)  # model.py:308-324
                 outs = [backbone(cat, ["Mconv%d_stage%d_L%d" % (i, st, br) for i in range(1, 8)]) for br in (1, 2)]
-            return outs[0], outs[1]
+            return f32_outs[last[0]], f32_outs[last[1]]
         if kind == "hand":
             feat = backbone(x, prefix + ["conv4_3", "conv4_4", "conv5_1", "conv5_2", "conv5_3_CPM"])
             out = backbone(feat, ["conv6_1_CPM", "conv6_2_CPM"])
             for st in range(2, 7):
                 out = backbone(torch.cat([out, feat], 1), ["Mconv%d_stage%d" % (i, st) for i in range(1, 8)])
-            return out
+            return f32_outs[last[0]]
         if kind == "body25":
             feat = backbone(x, prefix + ["conv4_3_CPM", "conv4_4_CPM"])
 
@@ -476,8 +493,8 @@ def net_forward(kind, weights, x):
                 paf = stage(t, 2, st)
                 t = torch.cat([feat, paf], 1)
             heat0 = stage(t, 1, 0)
-            heat = stage(torch.cat([feat, heat0, paf], 1), 1, 1)
-            return paf, heat
+            stage(torch.cat([feat, heat0, paf], 1), 1, 1)
+            return f32_outs[last[0]], f32_outs[last[1]]
     raise ValueError(kind)
 
 
@@ -725,11 +742,11 @@ def hand_call(net_fn, img, backend="restated"):
 # ----------------------------------------------------------------------------------------------------------
 
 
-def make_net_fn(kind, weights):
+def make_net_fn(kind, weights, emulate_bf16=False):
     import torch
 
     def fn(data):
-        out = net_forward(kind, weights, torch.from_numpy(np.ascontiguousarray(data)).float())
+        out = net_forward(kind, weights, torch.from_numpy(np.ascontiguousarray(data)).float(), emulate_bf16=emulate_bf16)
         if kind == "hand":
             return out[0].numpy()
         return out[0][0].numpy(), out[1][0].numpy()

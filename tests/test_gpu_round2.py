@@ -1,0 +1,370 @@
+"""GPU tests added in round 2: whole-network parity at the shapes bench.py times, the batched / deterministic hand key
+points, weight files on disk, the nn.Module surface of `.model`, capacity flags."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import isl_b200  # noqa: E402
+from isl_b200 import _lib, nets, synth, weights  # noqa: E402
+from isl_b200.body import scale_geometry  # noqa: E402
+from isl_b200.extract import KeypointExtractor  # noqa: E402
+from oracle import openpose_oracle as O  # noqa: E402
+from packref import pack_reference, write_caffemodel  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def dev():
+    torch.cuda.set_device(0)
+    return torch.device("cuda:0")
+
+
+# ---------------------------------------------------------------------------------------------------- networks
+# Tolerances, relative to max|reference| per output (measured on B200, see gpurun_out/net_parity.json):
+#   against the fp32 network (torch conv2d, TF32 off): bf16 operand rounding through up to 50 layers
+#   against the bf16-emulating oracle (same operand rounding, fp32 accumulation): what is left is accumulation order
+#   and the occasional activation that rounds to the other bf16 neighbour
+NET_TOL_FP32 = 3e-2
+NET_TOL_EMULATED = 1.5e-2
+_net_report = {}
+
+
+@pytest.mark.parametrize("kind,h,w,n", [("coco", 736, 984, 16), ("body25", 736, 1312, 16), ("hand", 736, 736, 32),
+                                        ("body25", 184, 328, 3), ("hand", 368, 368, 5)])
+def test_whole_network_at_bench_shapes(dev, kind, h, w, n):
+    """The shapes bench.py times (C2 / C3 largest scale at batch 16, 32 hand crops) plus odd batch sizes: different tile
+    heights, stage counts and waves than the toy shapes of test_gpu_parity.py (conv_prepare)."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    flat = O.make_flat_weights(kind, seed=3)
+    net = isl_b200.PoseNet(kind, flat)
+    x = torch.from_numpy(np.random.RandomState(5).uniform(-0.5, 0.5, (n, 3, h, w)).astype(np.float32)).to(dev)
+    got = net.forward_into(x)
+    got = [g.clone() for g in got]
+    del net
+    torch.cuda.empty_cache()
+    report = {}
+    for name, emu, tol in (("fp32", False, NET_TOL_FP32), ("bf16_emulated", True, NET_TOL_EMULATED)):
+        refs = []
+        step = 4 if h * w > 500000 else n   # bound the fp32 reference's activation memory
+        for a in range(0, n, step):
+            out = O.net_forward(kind, flat, x[a:a + step], emulate_bf16=emu, device=dev)
+            refs.append([out] if kind == "hand" else list(out))
+        refs = [torch.cat([r[i] for r in refs]) for i in range(len(refs[0]))]
+        for i, (r, g) in enumerate(zip(refs, got)):
+            assert g.shape == r.shape
+            scale = float(r.abs().max())
+            emax = float((g - r).abs().max()) / scale
+            emean = float((g - r).abs().mean()) / scale
+            report["%s_out%d" % (name, i)] = dict(max_rel=emax, mean_rel=emean, ref_max=scale)
+            assert emax <= tol, (kind, name, i, emax)
+            assert emean <= tol / 8, (kind, name, i, emean)
+        del refs
+        torch.cuda.empty_cache()
+    _net_report["%s_%dx%dx%d" % (kind, h, w, n)] = report
+    import json
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(_net_report, open(os.path.join(ROOT, "gpurun_out", "net_parity.json"), "w"), indent=1, sort_keys=True)
+
+
+def test_fp32_gpu_reference_equals_cpu_reference(dev):
+    """The torch-CUDA fp32 network used as the checker above is the same function as the oracle's CPU network."""
+    torch.backends.cudnn.allow_tf32 = False
+    flat = O.make_flat_weights("coco", seed=3)
+    x = torch.from_numpy(np.random.RandomState(5).uniform(-0.5, 0.5, (1, 3, 64, 88)).astype(np.float32))
+    a = O.net_forward("coco", flat, x)
+    b = O.net_forward("coco", flat, x, device=dev)
+    for p, q in zip(a, b):
+        assert float((p - q.cpu()).abs().max()) <= 1e-4 * float(p.abs().max())
+
+
+@pytest.mark.parametrize("kind", ["coco", "body25", "hand"])
+def test_device_weight_packing_bit_exact(dev, kind):
+    flat = O.make_flat_weights(kind, seed=0)
+    net = isl_b200.PoseNet(kind, flat)
+    convs = [s[1] for s in net.program.steps if s[0] == "conv"]
+    assert len(convs) == len(net.packed)
+    for s, (wt, bias, slope) in zip(convs, net.packed):
+        ref = pack_reference(flat[s["layer"] + ".weight"], s["chan_map"], s["src"][2], s["first"])
+        assert wt.shape == ref.shape, s["layer"]
+        assert torch.equal(wt.cpu().view(torch.int16), ref.view(torch.int16)), s["layer"]
+        assert torch.equal(bias[:s["cout"]].cpu(), flat[s["layer"] + ".bias"])
+
+
+# ---------------------------------------------------------------------------------------------------- hand key points
+def _hand_maps(hand, w, pts, dev):
+    maps = []
+    for (m, rh, rw, hp, wp) in scale_geometry(w, w, hand.scale_search, hand.boxsize):
+        t = torch.from_numpy(synth.render_hand_maps(pts, hp // 8, wp // 8))[None].contiguous().to(dev)
+        maps.append((t, 0, (rh, rw, hp, wp)))
+    return maps
+
+
+@pytest.fixture(scope="module")
+def hand(dev):
+    return isl_b200.Hand(O.make_flat_weights("hand", seed=0))
+
+
+def test_hand_keypoints_batched_over_crops_of_different_sizes(dev, hand):
+    """One islpose_hand_keypoints call for crops of five sizes == one call per crop == the oracle."""
+    sizes = [109, 64, 150, 20, 233, 64, 97]
+    pts = [np.random.RandomState(40 + i).uniform(0.1, 0.9, (21, 2)) for i in range(len(sizes))]
+    pts[3][5] = -1
+    per_crop = [_hand_maps(hand, w, p, dev) for w, p in zip(sizes, pts)]
+    out = torch.zeros((len(sizes), 21, 2), dtype=torch.int32, device=dev)
+    hand.keypoints(per_crop, [(w, w) for w in sizes], out)
+    got = out.cpu().numpy()
+    for i, (w, p) in enumerate(zip(sizes, pts)):
+        single = hand.postprocess(per_crop[i], w, w).cpu().numpy()
+        assert np.array_equal(got[i], single)
+        crop = synth.synth_frame(w, w, i)
+        want = O.hand_call(lambda d: synth.render_hand_maps(p, d.shape[2] // 8, d.shape[3] // 8), crop)
+        assert np.array_equal(got[i].astype(np.int64), want), (i, w)
+
+
+def _hand_peaks_direct(heat, dev, thre=0.05):
+    """islpose_hand_peaks on caller-made float64 planes [planes, H, W] -> int array [planes, 2]."""
+    planes, H, W = heat.shape
+    hd = torch.from_numpy(np.ascontiguousarray(heat)).to(dev)
+    lab = torch.empty((planes, H, W), dtype=torch.int32, device=dev)
+    mass = torch.empty((planes, H, W), dtype=torch.float64, device=dev)
+    out = torch.full((planes, 2), -7, dtype=torch.int32, device=dev)
+    gw = (C.c_double * 25)(*isl_b200.util.gaussian_weights().tolist())
+    _lib.check(_lib.lib().islpose_hand_peaks(_lib.ptr(hd), planes, H, W, gw, thre, _lib.ptr(lab), _lib.ptr(mass), _lib.ptr(out),
+                                             _lib.stream_ptr()), "islpose_hand_peaks")
+    return out.cpu().numpy()
+
+
+def _oracle_planes(heat):
+    planes, H, W = heat.shape
+    out = []
+    for a in range(0, planes, 21):
+        blk = heat[a:a + 21]
+        full = np.zeros((H, W, 22))
+        full[:, :, :len(blk)] = np.transpose(blk, (1, 2, 0))
+        out.append(O.hand_peaks(full.copy())[:len(blk)])
+    return np.concatenate(out)
+
+
+def test_hand_component_mass_ties_follow_numpy_summation_order(dev):
+    """Components whose masses agree to within rounding: the kept component must be the one np.argmax over numpy's
+    pairwise sums picks (hand.py:68), every time. Each plane holds several copies of one blob (identical values, so the
+    masses differ by summation order only, if at all) at positions that give the copies different raster interleavings,
+    plus planes where one copy is heavier by one ulp-scale amount."""
+    rng = np.random.RandomState(7)
+    H, W = 150, 170
+    planes = []
+    yy, xx = np.mgrid[0:41, 0:41]
+    for k in range(42):
+        blob = 0.9 * np.exp(-((yy - 20) ** 2 + (xx - 20) ** 2) / (2 * (4.0 + 0.1 * k) ** 2)) * (1 + 0.01 * rng.standard_normal((41, 41)))
+        plane = np.zeros((H, W))
+        spots = [(5, 7), (60 + k % 5, 100), (100, 20 + k % 7)]
+        for j, (y0, x0) in enumerate(spots):
+            b = blob.copy()
+            if k % 3 == 1 and j == 1:
+                b[20, 20] += 2e-13      # decides the arg-max only if the sums are exact to the last bits
+            if k % 3 == 2 and j == 2:
+                b = b[::-1, ::-1].copy()   # same multiset of values, different raster order
+            plane[y0:y0 + 41, x0:x0 + 41] = b
+        planes.append(plane)
+    heat = np.stack(planes)
+    want = _oracle_planes(heat)
+    first = _hand_peaks_direct(heat, dev)
+    assert np.array_equal(first.astype(np.int64), want)
+    for _ in range(50):   # identical bits on every run (ADVICE: the float64 atomics must not decide anything)
+        assert np.array_equal(_hand_peaks_direct(heat, dev), first)
+
+
+def test_hand_exact_count_replays_equal_single_crops(dev):
+    """3 and 5 crops run as exact-size plans inside the 4- / 8-image buffers: same key points as one crop at a time."""
+    hand = isl_b200.Hand(O.make_flat_weights("hand", seed=2))
+    crops = [synth.synth_frame(64, 64, 50 + i) for i in range(5)]
+    single = [hand(c) for c in crops]
+    for k in (3, 5):
+        got = hand.batch(crops[:k])
+        for a, b in zip(got, single):
+            assert np.array_equal(a, b)
+
+
+# ---------------------------------------------------------------------------------------------------- weight files
+def test_weight_files_on_disk_through_the_constructors(dev, tmp_path):
+    """Body(model_path) / Hand(model_path) with real files (body.py:35-36, hand.py:20): torch zip archive, legacy torch
+    stream, Caffe protobuf and the packed blob all give the networks the in-memory dict gives."""
+    flat = O.make_flat_weights("coco", seed=4)
+    frame = synth.synth_frame(96, 128, 3)
+    want = isl_b200.Body(flat, "coco")
+    x = torch.from_numpy(np.random.RandomState(1).uniform(-0.5, 0.5, (1, 3, 48, 64)).astype(np.float32)).to(dev)
+    ref_out = [o.clone() for o in want.model(x)]
+    ref_cs = want(frame)
+    paths = {}
+    paths["zip"] = str(tmp_path / "body_pose_model.pth")
+    torch.save(flat, paths["zip"])
+    paths["legacy"] = str(tmp_path / "legacy.pth")
+    torch.save(flat, paths["legacy"], _use_new_zipfile_serialization=False)
+    paths["caffe"] = str(tmp_path / "pose.caffemodel")
+    write_caffemodel(paths["caffe"], flat)
+    paths["packed"] = str(tmp_path / "body.islpose")
+    weights.write_packed(paths["packed"], flat)
+    for fmt, p in paths.items():
+        loaded = weights.load_flat(p)
+        assert sorted(loaded) == sorted(flat), fmt
+        body = isl_b200.Body(p, "coco")
+        outs = body.model(x)
+        for a, b in zip(outs, ref_out):
+            assert torch.equal(a, b), fmt   # bf16 operands are identical bits in every format
+        c, s = body(frame)
+        assert np.array_equal(c, ref_cs[0]) and np.array_equal(s, ref_cs[1])
+    hflat = O.make_flat_weights("hand", seed=5)
+    hp = str(tmp_path / "hand_pose_model.pth")
+    torch.save(hflat, hp)
+    crop = synth.synth_frame(64, 64, 9)
+    assert np.array_equal(isl_b200.Hand(hp)(crop), isl_b200.Hand(hflat)(crop))
+
+
+# ---------------------------------------------------------------------------------------------------- nn.Module surface
+class TorchModuleWrapperStandIn(object):
+    """What keras.layers.TorchModuleWrapper does with a module (keras/src/utils/torch_utils.py; used by the reference in
+    ISL_Model_parameter.py:44-47): requires an nn.Module, moves it to the backend device, tracks its parameters,
+    toggles train / eval from `trainable`, forwards call() to the module."""
+
+    def __init__(self, module, device):
+        if not isinstance(module, torch.nn.Module):
+            raise ValueError("`TorchModuleWrapper` can only wrap `torch.nn.Module` instances")
+        self.module = module.to(device)
+        self.variables = [(name, p) for name, p in self.module.named_parameters()]
+        self.trainable = False
+        self.module.eval()
+
+    def call(self, *args):
+        return self.module(*args)
+
+
+def test_model_is_an_nn_module(dev):
+    flat = O.make_flat_weights("body25", seed=6)
+    body = isl_b200.Body(flat, "body25")
+    m = body.model
+    assert isinstance(m, torch.nn.Module)
+    sd = m.state_dict()
+    assert sorted(sd) == sorted(flat)                                  # the flat Caffe names of the weight files
+    assert all(torch.equal(sd[k].cpu(), flat[k]) for k in flat)
+    assert all(not p.requires_grad and p.device == dev for p in m.parameters())   # model.py:167-168
+    assert isl_b200.util.transfer(m, flat).keys() == flat.keys()
+    wrapped = TorchModuleWrapperStandIn(m, dev)
+    assert len(wrapped.variables) == len(flat)
+    x = torch.from_numpy(np.random.RandomState(2).uniform(-0.5, 0.5, (1, 3, 48, 72)).astype(np.float32)).to(dev)
+    with torch.no_grad():
+        paf, heat = wrapped.call(x)                                    # ISL_Model_parameter.py:84-85
+    assert paf.shape == (1, 52, 6, 9) and heat.shape == (1, 26, 6, 9)
+    ref = O.net_forward("body25", flat, x.cpu())
+    assert float((paf.cpu() - ref[0]).abs().max()) <= 5e-2 * float(ref[0].abs().max())
+    # load_state_dict re-packs the kernels' operands
+    other = O.make_flat_weights("body25", seed=7)
+    m.load_state_dict(other)
+    paf2, _ = m(x)
+    ref2 = O.net_forward("body25", other, x.cpu())
+    assert float((paf2.cpu() - ref2[0]).abs().max()) <= 5e-2 * float(ref2[0].abs().max())
+    assert float((paf2 - paf).abs().max()) > 0
+    # there is no CPU path and no other dtype
+    with pytest.raises(_lib.IslposeError):
+        m.to("cpu")
+    with pytest.raises(_lib.IslposeError):
+        m.half()
+    assert m.to(dev) is m and m.cuda() is m and m.float() is m
+
+
+def test_model_moves_between_gpus(dev):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("one GPU")
+    flat = O.make_flat_weights("hand", seed=8)
+    m = isl_b200.PoseNet("hand", flat)
+    x = torch.from_numpy(np.random.RandomState(3).uniform(-0.5, 0.5, (1, 3, 64, 64)).astype(np.float32))
+    a = m(x.to(dev)).cpu()
+    m.to("cuda:1")
+    assert m.device == torch.device("cuda:1")
+    b = m(x.to("cuda:1")).cpu()
+    assert torch.equal(a, b)
+
+
+# ---------------------------------------------------------------------------------------------------- capacities
+def test_overflow_flags_do_not_mask_each_other(dev):
+    """A frame whose peak lists overflow AND whose pair matrix is too small must still report the peak overflow
+    (atomicMax of codes let 3 overwrite 1). Peaks: a lattice of bumps, cap = 16 per part."""
+    H, W, parts, cap = 96, 128, 18, 16
+    yy, xx = np.mgrid[0:H, 0:W]
+    plane = 0.5 + 0.4 * np.cos(yy * np.pi / 8) * np.cos(xx * np.pi / 8)    # a maximum every 16 px: 6 x 8 = 48 > cap
+    heat = torch.from_numpy(np.repeat(plane[None], parts, 0).copy()).to(dev)
+    counts = torch.zeros(parts, dtype=torch.int32, device=dev)
+    keys = torch.zeros((parts, cap), dtype=torch.int32, device=dev)
+    scores = torch.zeros((parts, cap), dtype=torch.float64, device=dev)
+    flags = torch.zeros(1, dtype=torch.int32, device=dev)
+    L = _lib.lib()
+    gw = (C.c_double * 25)(*isl_b200.util.gaussian_weights().tolist())
+    _lib.check(L.islpose_body_peaks(_lib.ptr(heat), parts, H, W, gw, 0.1, cap, _lib.ptr(counts), _lib.ptr(keys), _lib.ptr(scores),
+                                    _lib.ptr(flags), _lib.stream_ptr()), "body_peaks")
+    assert int(flags.item()) == _lib.OVERFLOW_PEAKS
+    assert int(counts.max().item()) == cap
+    # grouping with a pair matrix of 4 entries per limb: ORs its own bit in, the peak bit stays
+    nl = 19
+    paf = torch.zeros((1, 38, H // 8, W // 8), dtype=torch.float32, device=dev)
+    sc = (_lib.Scale * 1)()
+    sc[0].lowres, sc[0].gh, sc[0].gw, sc[0].hc, sc[0].wc = paf.data_ptr(), H // 8, W // 8, H, W
+    gb = _lib.GroupBuffers()
+    bufs = dict(counts=counts, keys=keys, scores=scores, pair_score=torch.empty((nl, 4), dtype=torch.float64, device=dev),
+                end_paf=torch.empty((nl, 2, cap, 2), dtype=torch.float64, device=dev),
+                conn_count=torch.zeros(nl, dtype=torch.int32, device=dev), conn_ij=torch.zeros((nl, cap, 2), dtype=torch.int32, device=dev),
+                conn_score=torch.zeros((nl, cap), dtype=torch.float64, device=dev),
+                owner=torch.zeros((parts * cap, 2), dtype=torch.int32, device=dev),
+                candidate=torch.zeros((parts * cap, 4), dtype=torch.float64, device=dev), n_cand=torch.zeros(1, dtype=torch.int32, device=dev),
+                subset=torch.zeros((64, 20), dtype=torch.float64, device=dev), n_person=torch.zeros(1, dtype=torch.int32, device=dev),
+                overflow=flags)
+    gb.cap, gb.pair_cap, gb.max_cand, gb.max_person = cap, 4, parts * cap, 64
+    for k, v in bufs.items():
+        setattr(gb, k, v.data_ptr())
+    _lib.check(L.islpose_body_group(sc, 1, 0, 1, H, W, 0.05, 10, C.byref(gb), _lib.stream_ptr()), "body_group")
+    assert int(flags.item()) == _lib.OVERFLOW_PEAKS | _lib.OVERFLOW_PAIRS
+
+
+def test_body_raises_on_peak_overflow_and_recovers(dev, monkeypatch):
+    """Through the public API: more than PEAK_CAP peaks in one part is an IslposeError (never a silently truncated,
+    run-to-run varying result), and the same Body keeps working afterwards."""
+    from isl_b200 import body as body_mod
+    monkeypatch.setattr(body_mod, "PEAK_CAP", 8)
+    body = isl_b200.Body(O.make_flat_weights("coco", seed=1), "coco")
+    H, W = 96, 128
+    sk = synth.synth_skeletons("coco", 12, 3)
+    maps = []
+    for (m, rh, rw, hp, wp) in scale_geometry(H, W, body.scale_search, body.boxsize):
+        paf, heat = synth.render_maps("coco", sk, hp // 8, wp // 8)
+        maps.append((torch.from_numpy(paf)[None].contiguous().to(dev), torch.from_numpy(heat)[None].contiguous().to(dev), (rh, rw, hp, wp)))
+    with pytest.raises(_lib.IslposeError):
+        body.postprocess(maps, 1, H, W, body._workspace(1, H, W))
+    sk2 = synth.synth_skeletons("coco", 2, 3)
+    maps2 = []
+    for (m, rh, rw, hp, wp) in scale_geometry(H, W, body.scale_search, body.boxsize):
+        paf, heat = synth.render_maps("coco", sk2, hp // 8, wp // 8)
+        maps2.append((torch.from_numpy(paf)[None].contiguous().to(dev), torch.from_numpy(heat)[None].contiguous().to(dev), (rh, rw, hp, wp)))
+    (cand, sub), = body.postprocess(maps2, 1, H, W, body._workspace(1, H, W))
+    assert len(cand) >= 30
+
+
+def test_pipeline_with_host_frames_equals_batch(dev):
+    """KeypointExtractor.pipeline() with numpy frames (the staging buffers of a lane are reused every second batch):
+    same results as the plain batch call, batch after batch."""
+    body = isl_b200.Body(O.make_flat_weights("coco", seed=1, init="he"), "coco", scale_search=[0.5])
+    hand = isl_b200.Hand(O.make_flat_weights("hand", seed=2))
+    ex = KeypointExtractor(body, hand)
+    boxes = [[10, 12, 60, True], [70, 30, 52, False]]
+    batches = [[synth.synth_frame(120, 160, 100 + 3 * b + i) for i in range(3)] for b in range(6)]
+    want = [ex.batch(fr, [boxes] * 3) for fr in batches]
+    got = list(ex.pipeline((fr, [boxes] * 3) for fr in batches))
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        for (c1, s1, h1), (c2, s2, h2) in zip(g, w):
+            assert c1.shape == c2.shape and np.array_equal(c1, c2) and np.array_equal(s1, s2)
+            assert all(np.array_equal(p, q) for p, q in zip(h1, h2))

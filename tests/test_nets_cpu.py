@@ -6,6 +6,7 @@ import torch
 import isl_b200  # noqa: F401
 from isl_b200 import nets
 from oracle import openpose_oracle as O
+from packref import pack_reference
 
 
 @pytest.mark.parametrize("kind,layers,gflop", [("coco", 92, 271.87), ("body25", 114, 161.15), ("hand", 52, 206.38)])
@@ -18,6 +19,7 @@ def test_program_covers_every_layer_and_flops_match_survey(kind, layers, gflop):
 
 @pytest.mark.parametrize("kind", ["coco", "body25", "hand"])
 def test_weight_packing_is_a_permutation_of_the_reference_weights(kind):
+    """The packing rule (tests/packref.py; the device kernel csrc/pack.cu is compared with it bit for bit on the GPU)."""
     flat = O.make_flat_weights(kind, seed=0)
     spec = {l[0]: l for l in O.net_layers(kind)}
     for step in nets.build_program(kind).steps:
@@ -27,7 +29,7 @@ def test_weight_packing_is_a_permutation_of_the_reference_weights(kind):
         w = flat[s["layer"] + ".weight"]
         _, cin, cout, k, act, prelu = spec[s["layer"]]
         assert s["cout"] == cout and s["k"] == k and s["act"] == act and s["prelu"] == prelu
-        packed = nets._pack_weight(w, s["chan_map"], s["src"][2], s["first"]).float()
+        packed = pack_reference(w, s["chan_map"], s["src"][2], s["first"]).float()
         assert packed.shape[1] == cout and packed.shape[2] % 8 == 0 and packed.shape[2] >= s["src"][2]
         # every reference weight appears exactly once (bf16-rounded), the rest is zero
         ref = w.to(torch.bfloat16).float()
