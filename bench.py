@@ -1,14 +1,19 @@
 #!/usr/bin/env python
 """Benchmark of the OpenPose keypoint-extraction hot path (body + hand) - one JSON line on stdout.
 
-    python bench.py --gpus N --steps K --warmup W [--workload C2|C3] [--batch B] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--workload C2|C3|C4|C5] [--batch B] [--no-sub] [--impl reference]
 
 A step = one pass of body + hand extraction over one batch of synthetic frames per rank (frames shard across ranks,
 no collective on the data path; scaling is weak). Workloads (BASELINE.json configs):
   C2  coco body + hand, 640x480, scale_search [0.5,1,1.5,2], two fixed hand boxes per frame      (default)
-  C3  body25 + hand, 1280x720, same scales, two 128-px hand boxes per frame (C4's clips are batches of C3 frames)
-  C5  body25 + hand, 1920x1080, same scales, 40 hand boxes per frame (the multi-person stress shape)
+  C3  body25 + hand, 1280x720, same scales, two 128-px hand boxes per frame, batch 32 (configs[2])
+  C4  the frame loop of the reference's extract_features*.py on C3-shaped frames: 30-frame clips of host frames, sharded
+      by frame index over the ranks (KeypointExtractor.run_sharded), per-frame feature rows, results gathered on rank 0
+      and merged in frame order inside the timed region (configs[3]); one clip per rank per step
+  C5  body25 + hand, 1920x1080, same scales, 40 hand boxes per frame (the multi-person stress shape, configs[4])
 Hand boxes are fixed per workload because random-init weights never produce a person for util.handDetect.
+The JSON line is the headline workload (C2 unless --workload says otherwise); the other workloads are measured in the
+same run with fewer steps and reported under "sub_results", each with its own value / e2e / roofline.
 
 value   frames/s with the frames already resident in HBM (device-timed, max over ranks)
 e2e     frames/s through the public host API (numpy frames in, numpy results out; H2D from pinned memory and the
@@ -38,7 +43,8 @@ WEIGHT_INIT = "torch"   # nn.Conv2d's default init distribution (SURVEY.md secti
 WORKLOADS = {
     # name: (model_type, H, W, hand boxes [x, y, w, is_left], default batch per rank)
     "C2": ("coco", 480, 640, [[400, 250, 109, True], [22, 246, 90, False]], 16),
-    "C3": ("body25", 720, 1280, [[800, 300, 128, True], [300, 300, 128, False]], 16),
+    "C3": ("body25", 720, 1280, [[800, 300, 128, True], [300, 300, 128, False]], 32),
+    "C4": ("body25", 720, 1280, [[800, 300, 128, True], [300, 300, 128, False]], 30),
     # C5 (BASELINE.json configs[4]): 1080p, "20+ people" = 40 hand crops per frame on a fixed 8 x 5 lattice, 96..127 px
     "C5": ("body25", 1080, 1920, [[40 + 230 * (i % 8), 60 + 200 * (i // 8), 96 + (7 * i) % 32, i % 2 == 0] for i in range(40)], 4),
 }
@@ -59,9 +65,29 @@ def peaks():
     return 1400.0, 1590.0, 6500.0, "fallback"
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant conv kernel from the committed
-# `ncu --set full` capture (profiles/): filled in by hand from the capture, None until one exists for this round
-CONV_DRAM_TRAFFIC = 39.79e6   # v5, 7x7 128->128, 92x164x8: 36.10 MB read + 3.69 MB written (profiles/r1_ncu_full_conv7x7_v5.txt)
+def conv_dram_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant conv kernel, read from the committed
+    `ncu --set full` capture of this round (profiles/r2_ncu_conv_dram.csv: `ncu -i ... --page raw --csv` of the v5 kernel
+    on the 7x7 128->128 layer). None when no capture is committed."""
+    import csv
+
+    path = os.path.join(ROOT, "profiles", "r2_ncu_conv_dram.csv")
+    if not os.path.isfile(path):
+        return None, None
+    try:
+        rows = list(csv.reader(l for l in open(path) if not l.startswith("==")))
+        hdr = rows[0]
+        units = rows[1]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        total = 0.0
+        for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(name)
+            vals = [float(r[i].replace(",", "")) * scale[units[i]] for r in rows[2:] if len(r) > i and r[i]]
+            total += sum(vals) / len(vals)
+        return total, os.path.relpath(path, ROOT)
+    except Exception:
+        return None, None
+
 
 
 class ClockSampler(threading.Thread):
@@ -148,56 +174,51 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": len(times),
             "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(wl, 1), "timing": "host wall clock around each step (CPU only, no device work)"},
+            "config": {"workload": workload_name(wl, WORKLOADS[wl][4]),
+                       "timing": "host wall clock around each step (CPU only, no device work); a step here is ONE frame of the "
+                                 "workload (the GPU arm's step is the whole batch): frames/s is per-frame work either way"},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=0, help="frames per step per rank (0 = workload default)")
-    ap.add_argument("--chunk", type=int, default=0, help="split a step into pipeline stages of this many frames (0 = one stage per step)")
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--weights", default="torch", choices=["torch", "he"], help="random-init distribution (he = noisy-map stress)")
-    args = ap.parse_args()
-    global WEIGHT_INIT
-    WEIGHT_INIT = args.weights
-    if args.impl == "reference":
-        return run_reference(args)
-    args.warmup = max(args.warmup, 3)
+class ShardView(object):
+    """The frames of one step's clips as a sequence indexed by GLOBAL frame index, holding only this rank's shard."""
 
+    def __init__(self, n_items, owned):
+        self.n, self.owned = n_items, owned
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        return self.owned[i]
+
+
+def measure(ctx, wl, B, steps, warmup, chunk=None, headline=False):
+    """All legs of one workload on this rank; returns the dict rank 0 turns into a JSON line / sub_result."""
     import torch
     import torch.distributed as dist
 
     import isl_b200
-    from isl_b200 import _lib, synth
-    from isl_b200.extract import KeypointExtractor
+    from isl_b200 import _lib, features, synth
+    from isl_b200.extract import KeypointExtractor, merge_shards, shard_indices
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    mt, H, W, boxes, default_batch = WORKLOADS[args.workload]
-    B = args.batch or default_batch
+    rank, world, local = ctx["rank"], ctx["world"], ctx["local"]
+    mt, H, W, boxes, _ = WORKLOADS[wl]
+    clips = wl == "C4"
     body = isl_b200.Body(synth.make_flat_weights(mt, seed=0, init=WEIGHT_INIT), mt, scale_search=SCALES)
     hand = isl_b200.Hand(synth.make_flat_weights("hand", seed=0, init=WEIGHT_INIT))
-    ex = KeypointExtractor(body, hand, chunk=args.chunk or None)
+    ex = KeypointExtractor(body, hand, chunk=chunk)
     hand_boxes = [boxes] * B
+    flush = ctx["flush"]
+    L = _lib.lib()
 
     def frames_for(step):
+        if clips:   # SURVEY.md section 8d: clip c, frame t -> seed 1000*c + t; this rank's frames of `world` clips
+            return [synth.synth_frame(H, W, 1000 * ((step * world * B + i) // B) + i % B) for i in shard_indices(world * B, rank, world)]
         return [synth.synth_frame(H, W, (rank * 100003 + step * B + i) % (2 ** 31)) for i in range(B)]
-
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB of L2
 
     def barrier():
         torch.cuda.synchronize()
@@ -205,56 +226,116 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    L = _lib.lib()
-
-    # ---- leg 1: device-resident inputs (value) ---------------------------------------------------------------
-    total_steps = args.warmup + args.steps
-    dev_frames = [torch.from_numpy(np.stack(frames_for(s))).cuda() for s in range(min(total_steps, 4))]
-
     def run_steps(batches_of, n_steps):
         """K steps through the two-lane pipeline; returns (device ms between the brackets, results of the last step)."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        last = None
+        if clips:
+            # the reference's extraction loop (extract_features.py:143-173) per step: this rank's shard of the clips'
+            # frames in batches, one feature row per frame, host gather to rank 0, merge in frame order
+            barrier()
+            e0.record()
+            for s in range(n_steps):
+                flush.zero_()
+                owned = dict(zip(shard_indices(world * B, rank, world), batches_of(s)))
+                res = ex.run_sharded(ShardView(world * B, owned), rank, world, batch_size=chunk or B,
+                                     hand_boxes=[boxes] * (world * B))
+                rows = [features.feature_record(c, sb, hp, frame_no=i, model_type=mt) for i, (c, sb, hp) in
+                        zip(shard_indices(world * B, rank, world), res)]
+                if world > 1:
+                    shards = [None] * world if rank == 0 else None
+                    dist.gather_object(rows, shards, dst=0)
+                else:
+                    shards = [rows]
+                if rank == 0:
+                    last = merge_shards(shards, world * B)
+            e1.record()
+            barrier()
+            return e0.elapsed_time(e1), last
+
         def feed():
             for s in range(n_steps):
                 flush.zero_()   # evicts L2 between steps (the per-step working set is far larger than L2 anyway)
                 yield batches_of(s), hand_boxes
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
-        last = None
         for res in ex.pipeline(feed()):
             last = res
         e1.record()
         barrier()
         return e0.elapsed_time(e1), last
 
-    run_steps(lambda s: dev_frames[s % len(dev_frames)], args.warmup)   # W untimed steps (both lanes get their buffers)
+    out = {"workload": workload_name(wl, B), "frames_per_step_per_rank": B}
+    # ---- leg 1: device-resident inputs (value) ---------------------------------------------------------------
+    n_distinct = min(warmup + steps, 4 if B * H * W < 40e6 else 2)
+    host_sets = [frames_for(s) for s in range(n_distinct)]
+    if clips:
+        dev_sets = [[torch.from_numpy(f).cuda() for f in hs] for hs in host_sets]   # run_sharded indexes single frames
+        dev_sets = [[torch.stack(ds[a:a + (chunk or B)]) for a in range(0, len(ds), chunk or B)] for ds in dev_sets]
+    else:
+        dev_sets = [torch.from_numpy(np.stack(hs)).cuda() for hs in host_sets]
+
+    if clips:
+        # device-resident variant of the clip loop: the same sharded batches, already in HBM
+        def run_steps_dev(n_steps, first):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            e0.record()
+            last = None
+            for s in range(n_steps):
+                flush.zero_()
+                parts = dev_sets[(first + s) % len(dev_sets)]
+                res = [r for rs in ex.pipeline((p, [boxes] * int(p.shape[0])) for p in parts) for r in rs]
+                rows = [features.feature_record(c, sb, hp, frame_no=i, model_type=mt) for i, (c, sb, hp) in
+                        zip(shard_indices(world * B, rank, world), res)]
+                if world > 1:
+                    shards = [None] * world if rank == 0 else None
+                    dist.gather_object(rows, shards, dst=0)
+                else:
+                    shards = [rows]
+                if rank == 0:
+                    last = merge_shards(shards, world * B)
+            e1.record()
+            barrier()
+            return e0.elapsed_time(e1), last
+        run_steps_dev(warmup, 0)
+    else:
+        run_steps(lambda s: dev_sets[s % len(dev_sets)], warmup)   # W untimed steps (both lanes get their buffers)
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = L.islpose_launch_count()
-    dev_ms, _ = run_steps(lambda s: dev_frames[(args.warmup + s) % len(dev_frames)], args.steps)
-    gpu_launches = L.islpose_launch_count() - launches0
+    if clips:
+        dev_ms, _ = run_steps_dev(steps, warmup)
+    else:
+        dev_ms, _ = run_steps(lambda s: dev_sets[(warmup + s) % len(dev_sets)], steps)
+    out["gpu_launches"] = int(L.islpose_launch_count() - launches0)
     sampler.stop_flag = True
+    out["clocks"] = sampler.summary()
 
     # ---- leg 2: host API end to end (e2e) ------------------------------------------------------------------
-    host_frames = [frames_for(1000 + s) for s in range(min(args.steps, 4))]
-    run_steps(lambda s: host_frames[s % len(host_frames)], 2)
-    e2e_ms, res = run_steps(lambda s: host_frames[s % len(host_frames)], args.steps)
-    d2h = sum(c.nbytes + sb.nbytes + sum(p.nbytes for p in hp) for c, sb, hp in res)
-    h2d = B * H * W * 3   # hand crops are cut from the device copy of the frame
+    run_steps(lambda s: host_sets[s % len(host_sets)], 2)
+    e2e_ms, res = run_steps(lambda s: host_sets[s % len(host_sets)], steps)
+    if clips:
+        import pickle
+        out["d2h"] = len(pickle.dumps(res)) if res is not None else 0   # the merged feature rows (rank 0)
+    else:
+        out["d2h"] = int(sum(c.nbytes + sb.nbytes + sum(p.nbytes for p in hp) for c, sb, hp in res))
+    out["h2d"] = B * H * W * 3   # hand crops are cut from the device copy of the frame
 
     # ---- leg 3: the convolution plans of one step on their own (roofline of the tcgen05 kernels) -------------
-    # exactly the network replays a step performs (same chunks, lanes and streams; resize, im2col and max-pool
-    # launches included), without the post-processing, so the events time tensor-bound work only
-    chunk = ex.chunk or B
+    # exactly the network replays a step performs (same chunks, lanes and streams; resize and first-layer launches
+    # included), without the post-processing, so the events time tensor-bound work only
+    ck = ex.chunk or B
     lanes = ex._lane_streams(torch)
     main = torch.cuda.current_stream()
+    flat_dev = torch.cat(dev_sets[0]) if clips else dev_sets[0]
 
     def networks_only(frames_dev):
         flops = 0
         ready = torch.cuda.Event()
         ready.record(main)
-        for ci, a in enumerate(range(0, B, chunk)):
-            sub = frames_dev[a:a + chunk]
+        for ci, a in enumerate(range(0, B, ck)):
+            sub = frames_dev[a:a + ck]
             with torch.cuda.stream(lanes[ci % 2]):
                 lanes[ci % 2].wait_event(ready)
                 body.model.timing = []
@@ -272,24 +353,28 @@ def main():
         body.model.timing = hand.model.timing = None
         return flops
 
-    networks_only(dev_frames[0])
+    networks_only(flat_dev)
     barrier()
     conv_events, conv_flops = [], 0
-    for s in range(args.steps):
+    conv_sampler = ClockSampler(local)
+    conv_sampler.start()
+    for s in range(steps):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        conv_flops += networks_only(dev_frames[s % len(dev_frames)])
+        conv_flops += networks_only(flat_dev)
         e1.record()
         conv_events.append((e0, e1))
     barrier()
+    conv_sampler.stop_flag = True
     conv_ms = sum(a.elapsed_time(b) for a, b in conv_events)
+    out["conv_clocks"] = conv_sampler.summary()
 
     # ---- leg 4: the body map post-processing on its own (HBM roofline of subsystem 2) -------------------------
     # maps accumulation + gaussian/NMS/peak lists for one chunk, from the network outputs left by leg 3
-    nb = min(chunk, B)
+    nb = min(ck, B)
     ws = body._workspace(nb, H, W, 0)
-    maps = body.network_outputs(dev_frames[0][:nb], H, W, lane=0)
+    maps = body.network_outputs(flat_dev[:nb], H, W, lane=0)
     parts = body.njoint - 1
     heat_scales = body._scales_struct(maps, 1)
     need = L.islpose_maps_workspace_floats(heat_scales, len(maps), nb, parts)
@@ -306,7 +391,7 @@ def main():
     post_maps()
     barrier()
     post_events = []
-    for s in range(args.steps):
+    for s in range(steps):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -314,72 +399,156 @@ def main():
         e1.record()
         post_events.append((e0, e1))
     barrier()
-    post_ms = sum(a.elapsed_time(b) for a, b in post_events) / args.steps
+    post_ms = sum(a.elapsed_time(b) for a, b in post_events) / steps
     ws["overflow"].zero_()
     # SURVEY.md section 8d convention for the bytes of the reference dataflow, heat maps only (the PAF maps are never
     # materialised here; their share of B_post is reported separately as what the lazy sampler avoids)
     S = len(SCALES)
     grid_bytes = sum(4 * (m[2][2] // 8) * (m[2][3] // 8) for m in maps)
-    post_bytes_heat = nb * (4 * H * W * ((2 * S - 1) * body.njoint + 2 * parts) + grid_bytes * body.njoint)
-    post_bytes_all = nb * (4 * H * W * ((2 * S - 1) * (body.njoint + body.npaf) + 2 * parts) + grid_bytes * (body.njoint + body.npaf))
+    out["post_bytes_heat"] = nb * (4 * H * W * ((2 * S - 1) * body.njoint + 2 * parts) + grid_bytes * body.njoint)
+    out["post_bytes_all"] = nb * (4 * H * W * ((2 * S - 1) * (body.njoint + body.npaf) + 2 * parts) + grid_bytes * (body.njoint + body.npaf))
+    out["post_frames"] = nb
 
     # ---- single-frame latency through the same public API (BASELINE.json's C2 is literally one frame) -------
-    one = [host_frames[0][0]]
-    for _ in range(2):
-        ex.batch(one, hand_boxes[:1])
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(3):
-        ex.batch(one, hand_boxes[:1])
-    torch.cuda.synchronize()
-    single_ms = (time.perf_counter() - t0) / 3 * 1e3
+    single_ms = None
+    if headline:
+        one = [host_sets[0][0]]
+        for _ in range(2):
+            ex.batch(one, hand_boxes[:1])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            ex.batch(one, hand_boxes[:1])
+        torch.cuda.synchronize()
+        single_ms = (time.perf_counter() - t0) / 5 * 1e3
+    out["single_ms"] = single_ms
 
     times = torch.tensor([dev_ms, e2e_ms, conv_ms, post_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, conv_ms, post_ms = [float(x) for x in times.cpu()]
+    out["dev_ms"], out["e2e_ms"], out["conv_ms"], out["post_ms"] = [float(x) for x in times.cpu()]
+    out["conv_flops"] = conv_flops
+    out["steps"], out["warmup"] = steps, warmup
+    del body, hand, ex, dev_sets, flat_dev, ws, maps
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    return out
+
+
+def summarise(m, world, n_sm):
+    """Measurement dict of one workload -> the keys of a JSON line (also the shape of a sub_result)."""
+    sustained, burst, hbm_peak, src = peaks()
+    B, steps = m["frames_per_step_per_rank"], m["steps"]
+    frames_total = world * B * steps
+    achieved = m["conv_flops"] / (m["conv_ms"] * 1e-3) / 1e12 if m["conv_ms"] > 0 else 0.0
+    traffic, traffic_src = conv_dram_traffic()
+    mhz = (m["conv_clocks"] or {}).get("sm_mhz")
+    # the chip's own ceiling at the clock the leg actually ran at: 8192 dense bf16 FLOP per clock per SM
+    # (build/mma_rate: one M=128 x N=256 x K=16 tcgen05.mma per 128 cycles, profiles/r1_mma_rate.txt)
+    at_clock = n_sm * 8192 * mhz * 1e6 / 1e12 if mhz else None
+    nb = m["post_frames"]
+    post_gbs = m["post_bytes_heat"] / (m["post_ms"] * 1e-3) / 1e9
+    return {
+        "value": frames_total / (m["dev_ms"] * 1e-3), "unit": "frames/s", "ms_per_step": m["dev_ms"] / steps, "steps": steps,
+        "warmup": m["warmup"],
+        "e2e": {"value": frames_total / (m["e2e_ms"] * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": m["h2d"],
+                "d2h_bytes_per_step": m["d2h"]},
+        "gpu_launches": m["gpu_launches"], "clocks": m["clocks"],
+        "roofline": {"bound": "tensor", "kernel": "conv_umma_* (tcgen05 implicit-GEMM variants): the network replays of a step run "
+                                                  "on their own, same chunks / lanes / streams as the step; the resize and first-"
+                                                  "layer launches are inside the same events",
+                     "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
+                     "peak_source": "%s bf16_tflops_sustained (burst %.1f)" % (src, burst),
+                     "frac_at_clock": achieved / at_clock if at_clock else None,
+                     "peak_at_clock": at_clock, "sm_mhz_during_leg": mhz,
+                     "traffic": traffic, "traffic_source": traffic_src,
+                     "conv_share_of_step": m["conv_ms"] / max(m["dev_ms"], 1e-9)},
+        "post_roofline": {"bound": "hbm", "kernel": "upsample8 + resize_accumulate + gauss_nms + sort_peaks "
+                                                    "(body maps of one %d-frame chunk, run on their own)" % nb,
+                          "achieved": post_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": post_gbs / hbm_peak,
+                          "limiter": "instruction issue and the FP64 pipe, not HBM: the reference's float32 (no FMA, fixed order) "
+                                     "cubic stages and float64 accumulation / gaussian are reproduced bit for bit (DESIGN.md section 7)",
+                          "ms_per_frame": m["post_ms"] / nb, "algorithmic_bytes_per_frame": m["post_bytes_heat"] // nb,
+                          "reference_dataflow_bytes_per_frame_incl_paf": m["post_bytes_all"] // nb},
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="frames per step per rank (0 = workload default)")
+    ap.add_argument("--chunk", type=int, default=0, help="split a step into pipeline stages of this many frames (0 = one stage per step)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sub", action="store_true", help="headline workload only (no sub_results)")
+    ap.add_argument("--sub-steps", type=int, default=4, help="timed steps of every sub_result workload")
+    ap.add_argument("--weights", default="torch", choices=["torch", "he"], help="random-init distribution (he = noisy-map stress)")
+    args = ap.parse_args()
+    global WEIGHT_INIT
+    WEIGHT_INIT = args.weights
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+
+    import isl_b200
+    isl_b200.configure()   # 32 hardware queues for the pipeline's streams; must precede the CUDA context
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = {"rank": rank, "world": world, "local": local,
+           "flush": torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")}  # > 126 MB of L2
+    n_sm = torch.cuda.get_device_properties(local).multi_processor_count
+
+    def chunk_of(wl, B):
+        return args.chunk or (15 if wl == "C4" else None)
+
+    wl = args.workload
+    B = args.batch or WORKLOADS[wl][4]
+    head = measure(ctx, wl, B, args.steps, args.warmup, chunk=chunk_of(wl, B), headline=True)
+    subs = []
+    if not args.no_sub:
+        for other in ("C2", "C3", "C4", "C5"):
+            if other == wl:
+                continue
+            Bo = WORKLOADS[other][4]
+            subs.append((other, measure(ctx, other, Bo, args.sub_steps, 3, chunk=chunk_of(other, Bo))))
 
     if rank == 0:
-        sustained, burst, hbm_peak, src = peaks()
-        achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
-        frames_total = world * B * args.steps
-        line = {
-            "metric": METRIC, "value": frames_total / (dev_ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload_name(args.workload, B), "weights": "seeded random init, %s (no trained weights ship with the reference)" % (
-                           "nn.Conv2d default distribution" if WEIGHT_INIT == "torch" else "He-uniform (noisy maps: thousands of peaks)"),
-                       "l2": "flushed with a 256 MiB write before every timed step",
-                       "timing": "CUDA events on the launching stream around the K steps; max over ranks",
-                       "pipeline": "steps run through KeypointExtractor.pipeline(): two lanes, the post-processing and copies of "
-                                   "one step overlap the convolutions of the next; all K steps start and end inside the timed region",
-                       "single_frame_latency_ms": round(single_ms, 2)},
-            "clocks": sampler.summary(),
-            "e2e": {"value": frames_total / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h)},
-            "gpu_launches": int(gpu_launches),
-            "roofline": {"bound": "tensor", "kernel": "conv_umma_* (tcgen05 implicit-GEMM variants): the network replays of "
-                                                      "a step run on their own, same chunks / lanes / streams as the step; the "
-                                                      "resize, first-layer and max-pool launches are inside the same events",
-                         "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
-                         "peak_source": "%s bf16_tflops_sustained (burst %.1f)" % (src, burst),
-                         "traffic": CONV_DRAM_TRAFFIC, "conv_share_of_step": conv_ms / max(dev_ms, 1e-9)},
-            "post_roofline": {"bound": "hbm", "kernel": "upsample8 + resize_accumulate + gauss_window + sort_peaks "
-                                                        "(body maps of one %d-frame chunk, run on their own)" % nb,
-                              "achieved": post_bytes_heat / (post_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                              "frac": post_bytes_heat / (post_ms * 1e-3) / 1e9 / hbm_peak,
-                              "limiter": "instruction issue and the FP64 pipe, not HBM: the reference's float32 (no FMA, fixed order) "
-                                         "cubic stages and float64 accumulation / gaussian are reproduced bit for bit "
-                                         "(profiles/r1_ncu_full_post.txt, DESIGN.md section 7)",
-                              "ms_per_frame": post_ms / nb, "algorithmic_bytes_per_frame": post_bytes_heat // nb,
-                              "reference_dataflow_bytes_per_frame_incl_paf": post_bytes_all // nb},
-        }
+        mt, H, W, boxes, _ = WORKLOADS[wl]
+        line = {"metric": METRIC, "n_gpus": world, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic"}
+        line.update(summarise(head, world, n_sm))
+        line["config"] = {"workload": head["workload"],
+                          "weights": "seeded random init, %s (no trained weights ship with the reference)" % (
+                              "nn.Conv2d default distribution" if WEIGHT_INIT == "torch" else "He-uniform (noisy maps: thousands of peaks)"),
+                          "l2": "flushed with a 256 MiB write before every timed step",
+                          "timing": "CUDA events on the launching stream around the K steps; max over ranks",
+                          "pipeline": "steps run through KeypointExtractor.pipeline(): two lanes, the post-processing and copies of "
+                                      "one step overlap the convolutions of the next; all K steps start and end inside the timed region",
+                          "single_frame_latency_ms": round(head["single_ms"], 2) if head["single_ms"] else None}
+        line["sub_results"] = []
+        for name, m in subs:
+            sr = {"config": {"workload": m["workload"]}, "n_gpus": world}
+            sr.update(summarise(m, world, n_sm))
+            line["sub_results"].append(sr)
         if world == 1 and not args.no_cpu_baseline:
             # bounded sample of the same workload on the host cores: one untimed frame (weights, thread pools), then
             # frames until about 12 s of CPU work have been timed (at least 2, at most 4)
-            _, nets = cpu_reference_frame(args.workload, 0)
+            _, nets = cpu_reference_frame(wl, 0)
             ts = []
             while len(ts) < 2 or (sum(ts) < 12.0 and len(ts) < 4):
-                t, nets = cpu_reference_frame(args.workload, 1 + len(ts), nets)
+                t, nets = cpu_reference_frame(wl, 1 + len(ts), nets)
                 ts.append(t)
             line["cpu_baseline"] = {"value": len(ts) / sum(ts), "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "port",
                                     "sample": "%d frames of the workload (body 4 scales + %d hands each) after one untimed frame, "

@@ -209,10 +209,16 @@ class KeypointExtractor(object):
         return rows
 
     def run_sharded(self, frames, rank, world_size, batch_size=8, hand_boxes=None):
-        """Processes this rank's shard of `frames` in batches; returns results in shard order."""
+        """Processes this rank's shard of `frames` (any sequence indexable by global frame index) in batches through
+        pipeline(); returns results in shard order (merge_shards() of all ranks' lists restores frame order)."""
         idx = shard_indices(len(frames), rank, world_size)
+        sels = [idx[b:b + batch_size] for b in range(0, len(idx), batch_size)]
+        gen = (([frames[i] for i in sel], None if hand_boxes is None else [hand_boxes[i] for i in sel]) for sel in sels)
         out = []
-        for b in range(0, len(idx), batch_size):
-            sel = idx[b:b + batch_size]
-            out.extend(self.batch([frames[i] for i in sel], None if hand_boxes is None else [hand_boxes[i] for i in sel]))
+        if hasattr(self.body, "enqueue"):
+            for res in self.pipeline(gen):
+                out.extend(res)
+        else:
+            for fr, hb in gen:
+                out.extend(self.batch(fr, hb))
         return out

@@ -18,6 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 import isl_b200  # noqa: E402
+isl_b200.configure()
 from isl_b200 import _lib, synth  # noqa: E402
 from isl_b200.body import scale_geometry  # noqa: E402
 
@@ -49,7 +50,7 @@ def main():
     frames = torch.from_numpy(np.stack([synth.synth_frame(H, W, i) for i in range(nb)])).cuda()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
     sustained, burst, hbm, _ = bench.peaks()
-    print("== %s, %d frames, gauss variant %s" % (wl, nb, os.environ.get("ISLPOSE_GAUSS", "2")))
+    print("== %s, %d frames" % (wl, nb))
 
     # ---- body networks
     geoms = scale_geometry(H, W, bench.SCALES, 368)
@@ -129,11 +130,13 @@ def main():
                                                                                  100 * flops / ms / 1e9 / sustained, sustained))
     per_crop = hand.network_outputs(crops, 0)
 
+    kp = torch.zeros((len(crops), 21, 2), dtype=torch.int32, device="cuda")
+
     def hand_post():
-        for i, c in enumerate(crops):
-            hand.postprocess(per_crop[i], c.shape[0], c.shape[1])
+        for a in range(0, len(crops), 32):
+            hand.keypoints(per_crop[a:a + 32], [(c.shape[0], c.shape[1]) for c in crops[a:a + 32]], kp[a:a + 32])
     ms = timed(hand_post, reps, flush)
-    print("hand key points, %2d crops, one stream %7.3f ms" % (len(crops), ms))
+    print("hand key points, %2d crops, batched %7.3f ms" % (len(crops), ms))
     ms = timed(lambda: hand.finish(hand.enqueue(crops, 0)), reps, flush)
     print("hand enqueue+finish (nets + post)     %7.3f ms" % ms)
 
