@@ -8,8 +8,8 @@ no collective on the data path; scaling is weak). Workloads (BASELINE.json confi
   C2  coco body + hand, 640x480, scale_search [0.5,1,1.5,2], two fixed hand boxes per frame      (default)
   C3  body25 + hand, 1280x720, same scales, two 128-px hand boxes per frame, batch 32 (configs[2])
   C4  the frame loop of the reference's extract_features*.py on C3-shaped frames: 30-frame clips of host frames, sharded
-      by frame index over the ranks (KeypointExtractor.run_sharded), per-frame feature rows, results gathered on rank 0
-      and merged in frame order inside the timed region (configs[3]); one clip per rank per step
+      by frame index over the ranks, run through one pipeline like a video, per-frame feature rows, results gathered on
+      rank 0 and merged in frame order inside the timed region (configs[3]); one clip per rank per step
   C5  body25 + hand, 1920x1080, same scales, 40 hand boxes per frame (the multi-person stress shape, configs[4])
 Hand boxes are fixed per workload because random-init weights never produce a person for util.handDetect.
 The JSON line is the headline workload (C2 unless --workload says otherwise); the other workloads are measured in the
@@ -183,17 +183,23 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-class ShardView(object):
-    """The frames of one step's clips as a sequence indexed by GLOBAL frame index, holding only this rank's shard."""
+class ChunkList(object):
+    """A step's frames held as device chunks [k,H,W,3]; slicing at chunk boundaries hands the chunks back."""
 
-    def __init__(self, n_items, owned):
-        self.n, self.owned = n_items, owned
+    def __init__(self, chunks):
+        self.chunks = chunks
+        self.n = sum(int(c.shape[0]) for c in chunks)
 
     def __len__(self):
         return self.n
 
-    def __getitem__(self, i):
-        return self.owned[i]
+    def __getitem__(self, sl):
+        pos = 0
+        for c in self.chunks:
+            if pos == sl.start:
+                return c
+            pos += int(c.shape[0])
+        raise IndexError(sl)
 
 
 def measure(ctx, wl, B, steps, warmup, chunk=None, headline=False):
@@ -203,7 +209,7 @@ def measure(ctx, wl, B, steps, warmup, chunk=None, headline=False):
 
     import isl_b200
     from isl_b200 import _lib, features, synth
-    from isl_b200.extract import KeypointExtractor, merge_shards, shard_indices
+    from isl_b200.extract import KeypointExtractor, shard_indices
 
     rank, world, local = ctx["rank"], ctx["world"], ctx["local"]
     mt, H, W, boxes, _ = WORKLOADS[wl]
@@ -231,24 +237,32 @@ def measure(ctx, wl, B, steps, warmup, chunk=None, headline=False):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         last = None
         if clips:
-            # the reference's extraction loop (extract_features.py:143-173) per step: this rank's shard of the clips'
-            # frames in batches, one feature row per frame, host gather to rank 0, merge in frame order
+            # the reference's extraction loop (extract_features.py:143-173): this rank's frames of the K steps' clips in
+            # batches through ONE pipeline (as a video is processed), one feature row per frame, then the host gather to
+            # rank 0 and the merge in frame order - all inside the timed region
+            def all_batches():
+                ck_ = chunk or B
+                for s in range(n_steps):
+                    fr = batches_of(s)
+                    for a in range(0, len(fr), ck_):
+                        flush.zero_()
+                        yield fr[a:a + ck_], [boxes] * len(fr[a:a + ck_])
             barrier()
             e0.record()
-            for s in range(n_steps):
-                flush.zero_()
-                owned = dict(zip(shard_indices(world * B, rank, world), batches_of(s)))
-                res = ex.run_sharded(ShardView(world * B, owned), rank, world, batch_size=chunk or B,
-                                     hand_boxes=[boxes] * (world * B))
-                rows = [features.feature_record(c, sb, hp, frame_no=i, model_type=mt) for i, (c, sb, hp) in
-                        zip(shard_indices(world * B, rank, world), res)]
-                if world > 1:
-                    shards = [None] * world if rank == 0 else None
-                    dist.gather_object(rows, shards, dst=0)
-                else:
-                    shards = [rows]
-                if rank == 0:
-                    last = merge_shards(shards, world * B)
+            res = [r for rs in ex.pipeline(all_batches()) for r in rs]
+            own = [s * world * B + i for s in range(n_steps) for i in shard_indices(world * B, rank, world)]
+            rows = [features.feature_record(c, sb, hp, frame_no=i, model_type=mt) for i, (c, sb, hp) in zip(own, res)]
+            if world > 1:
+                gathered = [None] * world if rank == 0 else None
+                dist.gather_object((own, rows), gathered, dst=0)
+            else:
+                gathered = [(own, rows)]
+            if rank == 0:
+                last = [None] * (n_steps * world * B)
+                for idxs, rws in gathered:
+                    for i, r in zip(idxs, rws):
+                        last[i] = r
+                assert all(r is not None for r in last)
             e1.record()
             barrier()
             return e0.elapsed_time(e1), last
@@ -276,28 +290,9 @@ def measure(ctx, wl, B, steps, warmup, chunk=None, headline=False):
         dev_sets = [torch.from_numpy(np.stack(hs)).cuda() for hs in host_sets]
 
     if clips:
-        # device-resident variant of the clip loop: the same sharded batches, already in HBM
+        # device-resident variant: the same sharded batches, already in HBM
         def run_steps_dev(n_steps, first):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            barrier()
-            e0.record()
-            last = None
-            for s in range(n_steps):
-                flush.zero_()
-                parts = dev_sets[(first + s) % len(dev_sets)]
-                res = [r for rs in ex.pipeline((p, [boxes] * int(p.shape[0])) for p in parts) for r in rs]
-                rows = [features.feature_record(c, sb, hp, frame_no=i, model_type=mt) for i, (c, sb, hp) in
-                        zip(shard_indices(world * B, rank, world), res)]
-                if world > 1:
-                    shards = [None] * world if rank == 0 else None
-                    dist.gather_object(rows, shards, dst=0)
-                else:
-                    shards = [rows]
-                if rank == 0:
-                    last = merge_shards(shards, world * B)
-            e1.record()
-            barrier()
-            return e0.elapsed_time(e1), last
+            return run_steps(lambda s: ChunkList(dev_sets[(first + s) % len(dev_sets)]), n_steps)
         run_steps_dev(warmup, 0)
     else:
         run_steps(lambda s: dev_sets[s % len(dev_sets)], warmup)   # W untimed steps (both lanes get their buffers)

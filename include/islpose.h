@@ -73,7 +73,12 @@ int islpose_plan_add_conv(islpose_plan* plan, const islpose_conv_desc* desc);
  * out bf16 NHWC with out_cstride (>= 64) channels per pixel. */
 int islpose_plan_add_first_conv(islpose_plan* plan, const float* in_nchw, const void* weights, const float* bias,
                                 const float* slope, void* out, int32_t out_cstride, int32_t n, int32_t h, int32_t w);
-int islpose_plan_run(const islpose_plan* plan, void* stream);
+/* Replays the plan on `stream`. The first run records the launches into a CUDA graph (programmatic dependent launch edges
+ * included); later runs are one graph launch. islpose_plan_set_graph(plan, 0) keeps kernel-by-kernel launches;
+ * islpose_plan_graph_state: 0 = not recorded yet, 1 = graph in use, -1 = recording was not possible (direct launches). */
+int islpose_plan_run(islpose_plan* plan, void* stream);
+int islpose_plan_set_graph(islpose_plan* plan, int32_t enable);
+int32_t islpose_plan_graph_state(const islpose_plan* plan);
 /* Measurement aid: runs the plan launch by launch, each one `reps` times back to back between two CUDA events (after
  * one untimed run), and blocks until done. h_ms / h_flops / h_variant (HOST arrays of num_launches entries; the last
  * two may be NULL) receive the average milliseconds, the algorithmic FLOPs (0 for non-conv launches) and the conv
@@ -148,6 +153,18 @@ typedef struct islpose_group_buffers {
 
 int islpose_body_group(const islpose_scale* paf_scales, int32_t n_scales, int32_t model_kind, int32_t n, int32_t H,
                        int32_t W, double thre2, int32_t mid_num, const islpose_group_buffers* buffers, void* stream);
+
+/* The classifier's input row per frame, float64 [n][156] (src/util.py:99-151,187-219 get_bodypose / get_handpose,
+ * src/ISL_Model_parameter.py:376-410 populate_features): [0,15) x and [15,30) y of the first 15 body joints found (joint-major,
+ * person-minor), then per hand (the frame's first two): 21 x, 21 y, 21 key-point numbers.
+ * islpose_body_features writes the body part of every row and zero-fills the rest; candidate / subset / n_person are the
+ * outputs of islpose_body_group. islpose_hand_features then fills the hand parts: table int32 [n_hands][4] = (frame, slot 0|1,
+ * crop x, crop y) on the DEVICE, hand_xy = islpose_hand_keypoints' out_xy of those hands (crop coordinates; non-zero
+ * coordinates are shifted by the crop origin as demo.py:36-37 does). */
+int islpose_body_features(const double* candidate, const double* subset, const int32_t* n_person, int32_t n, int32_t max_cand,
+                          int32_t max_person, int32_t model_kind, double* features, void* stream);
+int islpose_hand_features(const int32_t* table, const int32_t* hand_xy, int32_t n_hands, int32_t n_frames, double* features,
+                          void* stream);
 
 /* Hand key points (src/hand.py:51-74), batched over crops of any sizes: per crop and scale both cubic stages and the
  * float64 mean over the scales (hand.py:51-56), gaussian sigma=3, threshold, 8-connected labelling, the component with the

@@ -77,6 +77,8 @@ SYMBOLS = {
     "islpose_plan_add_first_conv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                             C.c_int32, C.c_int32, C.c_int32]),
     "islpose_plan_run": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "islpose_plan_set_graph": (C.c_int, [C.c_void_p, C.c_int32]),
+    "islpose_plan_graph_state": (C.c_int32, [C.c_void_p]),
     "islpose_plan_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "islpose_plan_num_launches": (C.c_int32, [C.c_void_p]),
     "islpose_plan_conv_flops": (C.c_double, [C.c_void_p]),
@@ -89,6 +91,9 @@ SYMBOLS = {
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "islpose_body_group": (C.c_int, [C.POINTER(Scale), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double,
                                      C.c_int32, C.POINTER(GroupBuffers), C.c_void_p]),
+    "islpose_body_features": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                        C.c_void_p]),
+    "islpose_hand_features": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "islpose_hand_workspace_bytes": (C.c_int64, [C.POINTER(HandCrop), C.c_int32]),
     "islpose_hand_keypoints": (C.c_int, [C.POINTER(HandCrop), C.c_int32, C.c_int32, C.POINTER(C.c_double), C.c_double,
                                          C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),

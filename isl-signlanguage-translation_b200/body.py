@@ -148,6 +148,12 @@ class Body(object):
             setattr(gb, f, ws[f].data_ptr())
         _lib.check(L.islpose_body_group(paf_scales, len(maps), 1 if self._kind == 'body25' else 0, n, H, W, self.thre2,
                                         self.mid_num, C.byref(gb), _lib.stream_ptr()), "islpose_body_group")
+        # body half of the classifier's feature rows (util.get_bodypose circles), straight from the grouping outputs. A
+        # fresh tensor per call: the hand stage of this batch fills its half while later batches run on this workspace
+        ws["features"] = torch.empty((n, 156), dtype=torch.float64, device=self.device)
+        _lib.check(L.islpose_body_features(_lib.ptr(ws["candidate"]), _lib.ptr(ws["subset"]), _lib.ptr(ws["n_person"]), n,
+                                           parts * PEAK_CAP, ws["max_person"], 1 if self._kind == 'body25' else 0,
+                                           _lib.ptr(ws["features"]), _lib.stream_ptr()), "islpose_body_features")
         # the three small result tables travel together, asynchronously, into pinned memory, and with them the leading
         # rows of candidate / subset (as many as recent calls needed, with head room): one synchronisation per call
         ws["tail_dev"][:n].copy_(ws["n_cand"])
@@ -187,7 +193,7 @@ class Body(object):
         self._group(maps, n, H, W, ws)
         done = torch.cuda.Event()
         done.record()
-        return dict(maps=maps, n=n, H=H, W=W, ws=ws, done=done, stream=torch.cuda.current_stream())
+        return dict(maps=maps, n=n, H=H, W=W, ws=ws, done=done, stream=torch.cuda.current_stream(), features=ws["features"])
 
     def post_finish(self, ticket):
         """Waits for a post_enqueue() ticket and returns the list of (candidate, subset)."""
@@ -246,6 +252,19 @@ class Body(object):
     def upload(self, frames, lane=0, after=None):
         """Host frames -> this call's device staging buffer [n,H,W,3] (through pinned memory; one buffer per lane).
         `after`: an event the copy must wait for - the last reader of the lane's previous contents."""
+        if torch.is_tensor(frames):
+            # a (pinned) host tensor [n,H,W,3], e.g. a FrameFeeder batch: one asynchronous DMA, no host-side copy
+            if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[3] != 3 or not frames.is_contiguous():
+                raise ValueError("Body.upload needs a contiguous uint8 [n,H,W,3] tensor, got %s %s" % (tuple(frames.shape), frames.dtype))
+            key = (frames.shape[0], frames.shape[1], frames.shape[2], lane)
+            stage = self._staging.get(key)
+            if stage is None:
+                stage = (None, torch.empty(tuple(frames.shape), dtype=torch.uint8, device=self.device))
+                self._staging[key] = stage
+            if after is not None:
+                torch.cuda.current_stream().wait_event(after)
+            stage[1].copy_(frames, non_blocking=True)
+            return stage[1]
         frames = [np.asarray(f) for f in frames]
         H, W = frames[0].shape[:2]
         for f in frames:
@@ -253,9 +272,9 @@ class Body(object):
                 raise ValueError("Body.batch needs uint8 [H,W,3] frames of one size, got %s %s" % (f.shape, f.dtype))
         key = (len(frames), H, W, lane)
         stage = self._staging.get(key)
-        if stage is None:
+        if stage is None or stage[0] is None:
             stage = (torch.empty((len(frames), H, W, 3), dtype=torch.uint8).pin_memory(),
-                     torch.empty((len(frames), H, W, 3), dtype=torch.uint8, device=self.device))
+                     stage[1] if stage is not None else torch.empty((len(frames), H, W, 3), dtype=torch.uint8, device=self.device))
             self._staging[key] = stage
         host = stage[0].numpy()
         for i, f in enumerate(frames):

@@ -103,6 +103,19 @@ int fill_scales(const islpose_scale* scales, int n_scales, int channels, int H, 
 struct islpose_plan {
   std::vector<Op> ops;
   double flops = 0;
+  // The launches of a plan never change (buffers, tensor maps and shapes are fixed when it is built), so the first
+  // islpose_plan_run captures them into a CUDA graph and every later run is ONE graph launch: a 93..117-kernel network
+  // costs the host ~0.4 ms to launch kernel by kernel, which is the critical path of a single-frame call where eight
+  // such networks (4 body + 4 hand scales) are queued one after the other. Programmatic dependent launch edges survive
+  // the capture. graph_state: 0 = not tried, 1 = ready, -1 = capture not possible here (direct launches from then on).
+  int use_graph = 1;
+  int graph_state = 0;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  ~islpose_plan() {
+    if (graph_exec != nullptr) cudaGraphExecDestroy(graph_exec);
+    if (graph != nullptr) cudaGraphDestroy(graph);
+  }
 };
 
 extern "C" {
@@ -187,9 +200,51 @@ static int run_op(const Op& op, cudaStream_t st) {
   return launch_conv_first(static_cast<const float*>(op.in), op.n, op.h, op.w, op.weights, op.bias, op.slope, op.out, op.c, st);
 }
 
-int islpose_plan_run(const islpose_plan* plan, void* stream) {
+int islpose_plan_set_graph(islpose_plan* plan, int32_t enable) {
+  if (plan == nullptr) return set_err("plan_set_graph: null plan");
+  plan->use_graph = enable ? 1 : 0;
+  return 0;
+}
+
+static int plan_capture(islpose_plan* plan, cudaStream_t st) {
+  // thread-local mode: other host threads (allocators, other lanes) keep making CUDA calls while this one records
+  if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    return 1;
+  }
+  int rc = 0;
+  for (size_t i = 0; i < plan->ops.size() && rc == 0; ++i) rc = run_op(plan->ops[i], st);
+  cudaGraph_t g = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(st, &g);
+  if (rc != 0 || e != cudaSuccess || g == nullptr) {
+    if (g != nullptr) cudaGraphDestroy(g);
+    cudaGetLastError();
+    return 1;
+  }
+  cudaGraphExec_t ge = nullptr;
+  if (cudaGraphInstantiate(&ge, g, 0) != cudaSuccess) {
+    cudaGraphDestroy(g);
+    cudaGetLastError();
+    return 1;
+  }
+  plan->graph = g;
+  plan->graph_exec = ge;
+  return 0;
+}
+
+int islpose_plan_run(islpose_plan* plan, void* stream) {
   if (plan == nullptr) return set_err("plan_run: null plan");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (plan->use_graph && plan->graph_state == 0 && plan->ops.size() > 1) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone)
+      plan->graph_state = plan_capture(plan, st) == 0 ? 1 : -1;
+  }
+  if (plan->use_graph && plan->graph_state == 1) {
+    if (cudaGraphLaunch(plan->graph_exec, st) != cudaSuccess) return check_cuda("plan_run/graph") ? 1 : set_err("plan_run: graph launch failed");
+    g_launches.fetch_add(static_cast<long long>(plan->ops.size()), std::memory_order_relaxed);
+    return 0;
+  }
   for (size_t i = 0; i < plan->ops.size(); ++i) {
     const Op& op = plan->ops[i];
     const int rc = run_op(op, st);
@@ -232,6 +287,7 @@ int islpose_plan_profile(const islpose_plan* plan, void* stream, int32_t reps, f
   return 0;
 }
 
+int32_t islpose_plan_graph_state(const islpose_plan* plan) { return plan ? plan->graph_state : 0; }
 int32_t islpose_plan_num_launches(const islpose_plan* plan) { return plan ? static_cast<int32_t>(plan->ops.size()) : 0; }
 double islpose_plan_conv_flops(const islpose_plan* plan) { return plan ? plan->flops : 0.0; }
 
@@ -326,6 +382,29 @@ int islpose_body_group(const islpose_scale* paf_scales, int32_t n_scales, int32_
     return check_cuda("body_group/paf_score") ? 1 : set_err("body_group: peak capacity out of range (cap %d)", gb.cap);
   if (launch_group(lt, n, W, gb, st) != 0) return check_cuda("body_group/group") ? 1 : set_err("body_group: launch failed");
   g_launches.fetch_add(4, std::memory_order_relaxed);
+  return 0;
+}
+
+int islpose_body_features(const double* candidate, const double* subset, const int32_t* n_person, int32_t n, int32_t max_cand,
+                          int32_t max_person, int32_t model_kind, double* features, void* stream) {
+  if (candidate == nullptr || subset == nullptr || n_person == nullptr || features == nullptr) return set_err("body_features: null pointer");
+  if (model_kind != 0 && model_kind != 1) return set_err("body_features: model_kind must be 0 (coco) or 1 (body25)");
+  if (n <= 0 || max_cand <= 0 || max_person <= 0) return set_err("body_features: bad sizes");
+  if (launch_body_features(candidate, subset, n_person, n, max_cand, max_person, model_kind == 1 ? 26 : 19, features,
+                           static_cast<cudaStream_t>(stream)) != 0)
+    return check_cuda("body_features") ? 1 : set_err("body_features: launch failed");
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+int islpose_hand_features(const int32_t* table, const int32_t* hand_xy, int32_t n_hands, int32_t n_frames, double* features,
+                          void* stream) {
+  if (n_hands == 0) return 0;
+  if (table == nullptr || hand_xy == nullptr || features == nullptr || n_hands < 0 || n_frames <= 0)
+    return set_err("hand_features: bad argument");
+  if (launch_hand_features(table, hand_xy, n_hands, n_frames, features, static_cast<cudaStream_t>(stream)) != 0)
+    return check_cuda("hand_features") ? 1 : set_err("hand_features: launch failed");
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }
 

@@ -64,6 +64,11 @@ int launch_paf_score(const ScaleSet& paf, const LimbTable& lt, int N, int H, int
                      const GroupBuffers& gb, cudaStream_t st);
 int launch_group(const LimbTable& lt, int N, int W, const GroupBuffers& gb, cudaStream_t st);
 
+// features.cu: the classifier's 156-number row per frame, float64 [n][156]
+int launch_body_features(const double* candidate, const double* subset, const int* n_person, int n, int max_cand, int max_person,
+                         int njoint, double* out, cudaStream_t st);
+int launch_hand_features(const int* table, const int* xy, int n_hands, int n_frames, double* out, cudaStream_t st);
+
 // hand.cu: key points of up to kHandMaxCrops crops (of any sizes) per launch chain
 constexpr int kHandMaxCrops = 32;
 constexpr int kHandMaxScales = 4;  // hand.py:25 fixes the list at four scales

@@ -88,11 +88,14 @@ class KeypointExtractor(object):
             out.extend(res)
         return out
 
-    def pipeline(self, batches):
+    def pipeline(self, batches, with_features=False):
         """Software pipeline over a sequence of batches: yields the result list of every batch, in order.
+        with_features: every frame's result is (candidate, subset, hand_peaks, row) with `row` the classifier's float64
+        [156] feature vector, formed on the device (csrc/features.cu) instead of (candidate, subset, hand_peaks).
 
-        batches: iterable of (frames, hand_boxes); frames is a uint8 cuda tensor [n,H,W,3] or a list of numpy frames
-        (uploaded through pinned memory), hand_boxes a per-frame list of boxes or None (= util.handDetect).
+        batches: iterable of (frames, hand_boxes); frames is a uint8 cuda tensor [n,H,W,3], a list of numpy frames
+        (uploaded through pinned memory) or a pinned host tensor [n,H,W,3] (frames.FrameFeeder batches: copied as they
+        are); hand_boxes a per-frame list of boxes or None (= util.handDetect).
 
         Two lanes (independent buffers and streams) alternate: while the host waits for the body results of batch i
         (it needs them for util.handDetect), the body networks of batch i+1 are already queued, and the hand networks
@@ -112,7 +115,7 @@ class KeypointExtractor(object):
                 frames, boxes = next(it)
             except StopIteration:
                 return None
-            if not torch.is_tensor(frames):
+            if not (torch.is_tensor(frames) and frames.is_cuda):
                 # the lane's staging buffer is about to be overwritten: its last readers are the body kernels of batch
                 # idx - 2 (finished: their results were collected) and the crop copies of that batch on the hand stream
                 frames = self.body.upload(frames, lane=idx % 2, after=crops_cut[idx % 2])
@@ -127,8 +130,14 @@ class KeypointExtractor(object):
         def finish_hand(pending):
             bodies, owner, ticket = pending
             if self.hand is None:
-                return [(c, s, []) for c, s in bodies]
-            return self._assemble(bodies, owner, self.hand.finish(ticket))
+                res = [(c, s, []) for c, s in bodies]
+            else:
+                res = self._assemble(bodies, owner, self.hand.finish(ticket))
+            if with_features:
+                ticket["done"].synchronize()
+                rows = ticket["features"].numpy()
+                res = [(c, s, hp, rows[i].copy()) for i, (c, s, hp) in enumerate(res)]
+            return res
 
         idx = 0
         pending = None
@@ -138,6 +147,9 @@ class KeypointExtractor(object):
             nxt = start_body(idx + 1)
             bodies = self.body.finish(ticket)
             owner, hticket = [], None
+            if self.hand is None and with_features:
+                with torch.cuda.stream(lanes[2 + idx % 2]):
+                    hticket = self._rows_to_host(torch, ticket["features"])
             if self.hand is not None:
                 crops = []
                 st = lanes[2 + idx % 2]
@@ -151,7 +163,8 @@ class KeypointExtractor(object):
                     cut = torch.cuda.Event()
                     cut.record(st)
                     crops_cut[idx % 2] = cut
-                    hticket = self.hand.enqueue(crops, lane=idx % 2) if crops else None
+                    feats = (ticket["features"], owner) if with_features else None
+                    hticket = self.hand.enqueue(crops, lane=idx % 2, features=feats) if (crops or feats) else None
             if pending is not None:
                 yield finish_hand(pending)
             pending = (bodies, owner, hticket)
@@ -160,6 +173,14 @@ class KeypointExtractor(object):
             yield finish_hand(pending)
         for st in lanes:
             main.wait_stream(st)
+
+    @staticmethod
+    def _rows_to_host(torch, rows):
+        host = torch.empty(rows.shape, dtype=rows.dtype).pin_memory()
+        host.copy_(rows, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream())
+        return dict(done=done, features=host, keep=rows)
 
     def _lane_streams(self, torch):
         if self._lanes is None:
@@ -183,16 +204,17 @@ class KeypointExtractor(object):
         return self._assemble(bodies, owner, peaks)
 
     def features(self, frames, batch_size=8):
-        """Clip -> float64 [T,156]: the per-frame feature vectors of demo_isl_translate.py's loop (features.py),
-        frames processed in batches through pipeline()."""
-        from . import features as F
-
+        """Clip -> float64 [T,156]: the per-frame feature vectors of demo_isl_translate.py's loop, frames processed in
+        batches through pipeline(); the rows are formed on the device and arrive with the key points."""
         frames = list(frames)
-        mt = getattr(self.body, "model_type", "coco")
         batches = [(frames[a:a + batch_size], None) for a in range(0, len(frames), batch_size)]
-        runner = self.pipeline(batches) if hasattr(self.body, "enqueue") else (self.batch(b) for b, _ in batches)
-        rows = [F.frame_features(c, s, hp, mt) for res in runner for (c, s, hp) in res]
-        return np.stack(rows) if rows else np.zeros((0, F.N_FEATURES))
+        if not hasattr(self.body, "enqueue"):   # stand-in estimators without a device path (tests)
+            from . import features as F
+            mt = getattr(self.body, "model_type", "coco")
+            rows = [F.frame_features(c, s, hp, mt) for b, _ in batches for (c, s, hp) in self.batch(b)]
+        else:
+            rows = [r for res in self.pipeline(batches, with_features=True) for (_, _, _, r) in res]
+        return np.stack(rows) if rows else np.zeros((0, 156))
 
     def records(self, frames, batch_size=8, first_frame_no=0, **meta):
         """Clip -> list of per-frame feature rows (features.feature_record = extract_features.py's saveFeature dict)."""

@@ -110,13 +110,14 @@ class Hand(object):
                 sc.lowres = t.data_ptr() + 4 * off
                 sc.gh, sc.gw, sc.hc, sc.wc = hp // 8, wp // 8, rh, rw
         need = L.islpose_hand_workspace_bytes(crops, n)
-        ws = self._work.get(lane)
+        key = (lane, torch.cuda.current_stream().cuda_stream)   # launches on one stream are ordered: one scratch per stream
+        ws = self._work.get(key)
         if ws is None or ws.numel() < need:
             # the previous (smaller) buffer may still be in use by launches in flight on this lane: let the caching
             # allocator keep it alive for them (record_stream) instead of synchronising
             if ws is not None:
                 ws.record_stream(torch.cuda.current_stream())
-            ws = self._work[lane] = torch.empty((int(need * 1.25) + 256,), dtype=torch.uint8, device=self.device)
+            ws = self._work[key] = torch.empty((int(need * 1.25) + 256,), dtype=torch.uint8, device=self.device)
         _lib.check(L.islpose_hand_keypoints(crops, n, len(self.scale_search), self._gauss, self.thre, _lib.ptr(ws), ws.numel(),
                                             _lib.ptr(out), _lib.stream_ptr()), "islpose_hand_keypoints")
 
@@ -136,11 +137,17 @@ class Hand(object):
         with torch.cuda.device(self.device):
             return self.batch_device([torch.from_numpy(c).to(self.device, non_blocking=True) for c in crops])
 
-    def enqueue(self, dev_crops, lane=0):
+    def enqueue(self, dev_crops, lane=0, features=None):
         """Launches the four network scales and the key-point selection of every crop (list of contiguous uint8
-        cuda tensors [h,w,3]) without waiting; finish(ticket) returns the list of int64 [21,2] arrays."""
+        cuda tensors [h,w,3]) without waiting; finish(ticket) returns the list of int64 [21,2] arrays.
+        features = (rows, owner): `rows` is the float64 cuda tensor [frames,156] whose body part Body wrote, owner[i] =
+        (frame, crop x, crop y) of crop i in util.handDetect order; the hand parts of the rows are filled on the device
+        and the finished rows travel to the host with the key points (ticket["features"])."""
         if not dev_crops:
-            return None
+            if features is None:
+                return None
+            with torch.cuda.device(self.device):
+                return self._features_only(features[0])
         with torch.cuda.device(self.device):
             main = torch.cuda.current_stream()
             out = torch.zeros((len(dev_crops), 21, 2), dtype=torch.int32, device=self.device)
@@ -152,14 +159,38 @@ class Hand(object):
                 self.keypoints(per_crop, [(c.shape[0], c.shape[1]) for c in part], out[a:a + len(part)], lane)
             host = torch.empty(out.shape, dtype=out.dtype).pin_memory()
             host.copy_(out, non_blocking=True)
+            feat_host = None
+            if features is not None:
+                rows, owner = features
+                seen, table = {}, []
+                for (fi, x, y) in owner:
+                    slot = seen.get(fi, 0)
+                    seen[fi] = slot + 1
+                    table.append((fi, slot if slot < 2 else -1, x, y))   # util.get_handpose keeps two hands (util.py:198)
+                tab = torch.tensor(table, dtype=torch.int32).pin_memory().to(self.device, non_blocking=True)
+                _lib.check(_lib.lib().islpose_hand_features(_lib.ptr(tab), _lib.ptr(out), len(table), rows.shape[0],
+                                                            _lib.ptr(rows), _lib.stream_ptr()), "islpose_hand_features")
+                feat_host = torch.empty(rows.shape, dtype=rows.dtype).pin_memory()
+                feat_host.copy_(rows, non_blocking=True)
+                out = (out, tab)
             done = torch.cuda.Event()
             done.record(main)
-        return dict(host=host, done=done, n=len(dev_crops), keep=(out, dev_crops))
+        return dict(host=host, done=done, n=len(dev_crops), keep=(out, dev_crops), features=feat_host)
+
+    def _features_only(self, rows):
+        """A batch without hand crops: the rows (body part only) still travel to the host."""
+        feat_host = torch.empty(rows.shape, dtype=rows.dtype).pin_memory()
+        feat_host.copy_(rows, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream())
+        return dict(host=None, done=done, n=0, keep=(rows,), features=feat_host)
 
     def finish(self, ticket):
         if ticket is None:
             return []
         ticket["done"].synchronize()
+        if ticket["host"] is None:
+            return []
         stacked = ticket["host"].numpy()
         return [stacked[i].astype(np.int64) for i in range(ticket["n"])]
 

@@ -311,6 +311,8 @@ class _Instance:
             self.op_names.append(s["layer"] + ("+pool" if d.pool else ""))
         self.flops = L.islpose_plan_conv_flops(handle)
         self.launches = L.islpose_plan_num_launches(handle)
+        if not net.tuning.get("graph", True):
+            _lib.check(L.islpose_plan_set_graph(handle, 0), "islpose_plan_set_graph")
         # the zero-fills above ran on the current stream, but the plan may be replayed on any stream: make the
         # buffers (in particular their never-written zero pad channels) globally visible before first use
         if share is None:

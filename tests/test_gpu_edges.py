@@ -125,7 +125,10 @@ def test_abi_error_paths_on_device(dev):
     d.in_ = buf.data_ptr()
     d.ksize = 5
     assert L.islpose_plan_add_conv(handle, C.byref(d)) != 0 and b"kernel size" in L.islpose_last_error()
-    assert L.islpose_plan_add_maxpool2x2(handle, buf.data_ptr(), buf.data_ptr(), 1, 3, 4, 64) != 0
+    d.ksize, d.pool, d.h = 3, 1, 3   # fused 2x2 pooling needs even sizes
+    assert L.islpose_plan_add_conv(handle, C.byref(d)) != 0 and b"pool" in L.islpose_last_error()
+    assert L.islpose_pack_conv_weights(buf.data_ptr(), 64, 60, 3, None, 64, 64, 0, buf.data_ptr(), None) != 0
+    assert L.islpose_hand_keypoints(None, 1, 4, (C.c_double * 25)(), 0.05, buf.data_ptr(), 0, buf.data_ptr(), None) != 0
     assert L.islpose_body_peaks(buf.data_ptr(), 1, 8, 8, (C.c_double * 25)(), 0.1, 4096, buf.data_ptr(), buf.data_ptr(),
                                 buf.data_ptr(), buf.data_ptr(), None) != 0
     assert L.islpose_plan_destroy(handle) == 0
