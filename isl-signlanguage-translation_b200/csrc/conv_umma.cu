@@ -6,8 +6,8 @@
 //       output channels (~97 % of the FLOPs); bias / ReLU / PReLU / bf16 / slice write / 2x2 max-pool in the epilogue
 //   v1  one pixel tile per CTA, two CTAs per SM: 1x1 layers and the float32 network heads
 //   v2  persistent, double-buffered TMEM, two pixel sub-tiles per weight stage: narrow 1x1 heads on large grids
-//   v3, v4  earlier halo / swapped-operand kernels, selectable for A/B measurements (conv_test), not chosen automatically
-//           (v4 only with ISLPOSE_NO_V5)
+//   v3, v4  earlier halo / swapped-operand kernels: compiled only into build/conv_test (-DISLPOSE_BRINGUP_VARIANTS) for
+//           A/B measurements; libislpose.so holds v1, v2, v5 and has no environment switches
 // Warp roles in every variant:
 //   warp 0      : TMA producer - the whole warp runs the loop with warp-uniform state, one elected lane issues
 //   warp 1      : TMEM owner + MMA issuer - same pattern; tcgen05.commit releases ring slots and signals the epilogue
@@ -27,7 +27,9 @@ namespace islpose {
 
 namespace {
 
-constexpr int kThreads = 192;
+#ifdef ISLPOSE_BRINGUP_VARIANTS
+constexpr int kThreads = 192;  // v3 / v4
+#endif
 constexpr int kThreadsV1 = 320;  // v1: eight epilogue warps (two per TMEM lane quarter, alternating 32-column chunks)
 constexpr uint32_t kASlotBytes = 128 * 128;  // 128 pixel rows x 64 bf16
 constexpr int kMaxStages = 8;
@@ -530,6 +532,7 @@ conv_umma_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
 }
 
 
+#ifdef ISLPOSE_BRINGUP_VARIANTS  // v3 / v4: earlier kernels kept for A/B measurements in build/conv_test only
 // ------------------------------------------------------------------------------------------------ v3
 // Halo variant for k > 1: the CTA's 8 x 16 pixel tile needs, per 64-channel block, the (8+2p) x (16+2p) input
 // pixels around it. They are fetched ONCE as one TMA box of 16 x (16+2p) pixel rows (pitch 16 keeps every 8-row
@@ -919,6 +922,8 @@ conv_umma_swapped_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   }
 }
 
+#endif  // ISLPOSE_BRINGUP_VARIANTS
+
 // ------------------------------------------------------------------------------------------------ v5
 // Swapped operands + resident activation halo, persistent. With lean issue loops the v1 / v4 kernels are bound by
 // L2 -> SM operand delivery (~60 B/clk/SM: 32 KB per 128x128x64 K-block, 48 KB per 128x256x64), not by the tensor
@@ -1259,8 +1264,7 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   // 92x164x8 grid, 1245 against 938 on 69x92x8; 3x3 256->256: 1358 against 1047). 1x1 layers, the float32 network heads,
   // the 32-channel first layer stay on v1 / v2. A 64-output-channel layer (conv1_2) wastes half of the M=128 rows and still
   // beats the persistent v2 kernel, which is L2-bound on the re-fetched activations (617 against 495 TFLOP/s at 736x736x2).
-  static const int env_no_v5 = getenv("ISLPOSE_NO_V5") != nullptr;  // A/B measurement aid
-  const bool auto_v5 = d.variant <= 0 && !env_no_v5 && d.ksize >= 3 && d.in_c >= 64 && d.cout >= 48 && d.out_bf16 != nullptr &&
+  const bool auto_v5 = d.variant <= 0 && d.ksize >= 3 && d.in_c >= 64 && d.cout >= 48 && d.out_bf16 != nullptr &&
                        d.out_f32 == nullptr && d.force_n_tile <= 0 && d.force_bw <= 0;
   if (d.variant == 5 || auto_v5) {
     // swapped operands + resident halo, persistent (see the kernel): 8 x th pixel tiles, th even, <= 32
@@ -1279,7 +1283,7 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
         // N/2 plus shared-memory contention with the weight stream), never below ~100 (issue rate of one warp)
         const double fit = 76.0 + 2.8 * h;
         const double per_mma = fit > 100.0 ? fit : 100.0;
-        static const double tile_const = getenv("ISLPOSE_TILE_CONST") ? atof(getenv("ISLPOSE_TILE_CONST")) : 6000.0;  // per-tile overhead (cycles)
+        const double tile_const = 6000.0;  // per-tile overhead (cycles)
         const double cost = static_cast<double>((tiles + 147) / 148) * (kb5 * 4.0 * per_mma + tile_const);
         if (best < 0 || cost < best) {
           best = cost;
@@ -1384,20 +1388,12 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
     }
     return best;
   };
-  // Variant 4 (swapped operands: weights = M, up to 256 pixels = N) for 3x3 / 7x7 layers with 65..128 output
-  // channels, when the model predicts a win (measured, profiles/conv_test_v4_swapped_r1.log: 7x7 128->128 at
-  // 92x164x8: 909 -> 1307 TFLOP/s, 7x7 192->128 at 60x80x8: 610 -> 1034, 3x3 512->128 at 92x92x8: 936 -> 1186;
-  // equal on small grids, slower on 1x1 layers).
   int want_variant = d.variant;
   int bw = d.force_bw, bh = d.force_bh;
-  static const int env_no_v4 = getenv("ISLPOSE_NO_V4") != nullptr;  // debugging aid
-  if (want_variant <= 0 && !env_no_v4 && d.ksize >= 3 && d.cout > 64 && d.cout <= 128 && d.force_n_tile <= 0 && bw <= 0) {
-    int w1 = 0, h1 = 0, w4 = 0, h4 = 0;
-    const double tiles1 = best_box(128, false, &w1, &h1);
-    const double t1 = estimate(static_cast<long long>(tiles1), 128, 3000.0);
-    const double t4 = best_box(256, true, &w4, &h4);
-    if (t4 < 0.9 * t1) want_variant = 4;
-  }
+#ifndef ISLPOSE_BRINGUP_VARIANTS
+  if (want_variant == 3 || want_variant == 4)
+    return fail(err, errlen, "conv: variant %lld is a bring-up kernel, built into build/conv_test only", want_variant);
+#endif
   if (want_variant == 3) {
     if (d.ksize == 1) return fail(err, errlen, "conv: the halo variant needs k > 1");
     bw = 8;  // one 8-row operand group = 8 neighbouring pixels of one image row
@@ -1534,7 +1530,7 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   }
 
   // v1: the staging blocks (16 KB per 64 channels) must fit into the operand ring
-  const bool v1_store = variant == 1 && d.out_bf16 != nullptr && getenv("ISLPOSE_NO_V1_TMA_STORE") == nullptr &&
+  const bool v1_store = variant == 1 && d.out_bf16 != nullptr &&
                         static_cast<uint32_t>((n_tile + 63) / 64) * kASlotBytes <= stages * per_stage;
   if ((variant == 4 && d.out_bf16 != nullptr && stages >= 2) || v1_store) {
     cuuint64_t gdim[4] = {static_cast<cuuint64_t>(a.cout_store), static_cast<cuuint64_t>(d.W),
@@ -1571,10 +1567,12 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
     cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv_umma_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+#ifdef ISLPOSE_BRINGUP_VARIANTS
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv_umma_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv_umma_swapped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+#endif
     if (e != cudaSuccess) return fail(err, errlen, "conv: cannot raise dynamic shared memory limit (%lld)", e);
     attr_set = true;
   }
@@ -1586,7 +1584,7 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
 // griddepcontrol.wait before its first access to the previous layer's output.
 template <typename... KArgs, typename... Args>
 static int launch_pdl(void (*kernel)(KArgs...), dim3 grid, int threads, uint32_t smem, cudaStream_t stream, Args&&... args) {
-  static const bool no_pdl = getenv("ISLPOSE_NO_PDL") != nullptr;  // A/B measurement aid
+  const bool no_pdl = false;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(threads);
@@ -1603,14 +1601,17 @@ static int launch_pdl(void (*kernel)(KArgs...), dim3 grid, int threads, uint32_t
 int conv_run(const ConvLaunch& l, cudaStream_t stream) {
   if (l.variant == 2) return launch_pdl(conv_umma_persistent_kernel, l.grid, kThreadsV1, l.smem_bytes, stream, l.tmA, l.tmB, l.args);
   if (l.variant == 5) return launch_pdl(conv_umma_halo_swapped_kernel, l.grid, kThreadsV1, l.smem_bytes, stream, l.tmA, l.tmB, l.args);
+#ifdef ISLPOSE_BRINGUP_VARIANTS
   if (l.variant == 3) {
     conv_umma_halo_kernel<<<l.grid, kThreads, l.smem_bytes, stream>>>(l.tmA, l.tmB, l.args);
-  } else if (l.variant == 4) {
-    conv_umma_swapped_kernel<<<l.grid, kThreads, l.smem_bytes, stream>>>(l.tmA, l.tmB, l.tmC, l.args);
-  } else {
-    return launch_pdl(conv_umma_kernel, l.grid, kThreadsV1, l.smem_bytes, stream, l.tmA, l.tmB, l.tmC, l.args);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
   }
-  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+  if (l.variant == 4) {
+    conv_umma_swapped_kernel<<<l.grid, kThreads, l.smem_bytes, stream>>>(l.tmA, l.tmB, l.tmC, l.args);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+  }
+#endif
+  return launch_pdl(conv_umma_kernel, l.grid, kThreadsV1, l.smem_bytes, stream, l.tmA, l.tmB, l.tmC, l.args);
 }
 
 }  // namespace islpose
