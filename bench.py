@@ -249,9 +249,11 @@ def measure(ctx, wl, B, steps, warmup, chunk=None, headline=False):
                         yield fr[a:a + ck_], [boxes] * len(fr[a:a + ck_])
             barrier()
             e0.record()
-            res = [r for rs in ex.pipeline(all_batches()) for r in rs]
             own = [s * world * B + i for s in range(n_steps) for i in shard_indices(world * B, rank, world)]
-            rows = [features.feature_record(c, sb, hp, frame_no=i, model_type=mt) for i, (c, sb, hp) in zip(own, res)]
+            rows = []
+            for rs in ex.pipeline(all_batches()):   # the rows of a batch are built while the GPU works on the next one
+                for (c, sb, hp) in rs:
+                    rows.append(features.feature_record(c, sb, hp, frame_no=own[len(rows)], model_type=mt))
             if world > 1:
                 gathered = [None] * world if rank == 0 else None
                 dist.gather_object((own, rows), gathered, dst=0)
@@ -379,7 +381,7 @@ def measure(ctx, wl, B, steps, warmup, chunk=None, headline=False):
     def post_maps():
         _lib.check(L.islpose_maps_accumulate(heat_scales, len(maps), body.njoint, nb, H, W, parts, 1, _lib.ptr(ws["heat"]),
                                              _lib.ptr(ws["mid"]), ws["mid"].numel(), _lib.stream_ptr()), "maps_accumulate")
-        _lib.check(L.islpose_body_peaks(_lib.ptr(ws["heat"]), nb * parts, H, W, body._gauss, body.thre1, 1024,
+        _lib.check(L.islpose_body_peaks(_lib.ptr(ws["heat"]), nb * parts, H, W, body._gauss, body.thre1, ws["cap"],
                                         _lib.ptr(ws["counts"]), _lib.ptr(ws["keys"]), _lib.ptr(ws["scores"]),
                                         _lib.ptr(ws["overflow"]), _lib.stream_ptr()), "body_peaks")
 

@@ -79,6 +79,7 @@ int islpose_plan_add_first_conv(islpose_plan* plan, const float* in_nchw, const 
 int islpose_plan_run(islpose_plan* plan, void* stream);
 int islpose_plan_set_graph(islpose_plan* plan, int32_t enable);
 int32_t islpose_plan_graph_state(const islpose_plan* plan);
+const char* islpose_plan_graph_note(const islpose_plan* plan); /* why recording was not possible ("" otherwise) */
 /* Measurement aid: runs the plan launch by launch, each one `reps` times back to back between two CUDA events (after
  * one untimed run), and blocks until done. h_ms / h_flops / h_variant (HOST arrays of num_launches entries; the last
  * two may be NULL) receive the average milliseconds, the algorithmic FLOPs (0 for non-conv launches) and the conv
@@ -117,7 +118,8 @@ int islpose_maps_accumulate(const islpose_scale* scales, int32_t n_scales, int32
 
 /* Peak detection (src/body.py:86-107): scipy gaussian_filter(sigma=3) in float64 with reflect borders, 4-neighbour
  * NMS against zero-filled shifts, threshold; peaks of every (frame, part) plane sorted in row-major order.
- * h_gauss: the 25 float64 filter weights, a HOST pointer. cap <= 1024 peaks per plane.
+ * h_gauss: the 25 float64 filter weights, a HOST pointer. cap <= 1024 peaks per plane, or 2048 / 4096 (the caller grows it
+ * when ISLPOSE_OVERFLOW_PEAKS comes back).
  * counts int32 [planes]; keys uint32 [planes][cap] = y*W+x; scores float64 [planes][cap] = unsmoothed value. */
 int islpose_body_peaks(const double* heat, int32_t planes, int32_t H, int32_t W, const double* h_gauss, double thre1,
                        int32_t cap, int32_t* counts, uint32_t* keys, double* scores, int32_t* overflow, void* stream);

@@ -79,6 +79,7 @@ SYMBOLS = {
     "islpose_plan_run": (C.c_int, [C.c_void_p, C.c_void_p]),
     "islpose_plan_set_graph": (C.c_int, [C.c_void_p, C.c_int32]),
     "islpose_plan_graph_state": (C.c_int32, [C.c_void_p]),
+    "islpose_plan_graph_note": (C.c_char_p, [C.c_void_p]),
     "islpose_plan_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "islpose_plan_num_launches": (C.c_int32, [C.c_void_p]),
     "islpose_plan_conv_flops": (C.c_double, [C.c_void_p]),

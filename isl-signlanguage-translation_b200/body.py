@@ -18,7 +18,8 @@ from .tables import model_dims
 from .util import gaussian_weights
 from .weights import load_flat
 
-PEAK_CAP = 1024        # peaks per (frame, part): the kernels' hard limit
+PEAK_CAP = 1024        # initial peaks per (frame, part); grows (x2) up to MAX_PEAK_CAP when a frame needs more
+MAX_PEAK_CAP = 4096    # the sort / matching kernels' limit (csrc/prepost.cuh kMaxPeakCap)
 PAIR_CAP = 128 * 1024  # initial nA*nB capacity per (frame, limb); grows (x4) when a frame needs more
 MAX_PERSON = 4096      # initial row slots per frame (rows ever created); grows (x4) up to 65536
 
@@ -71,24 +72,36 @@ class Body(object):
             ws = dict(
                 heat=torch.empty((n, parts, H, W), **f64),
                 counts=torch.zeros((n * parts,), **i32),
-                keys=torch.zeros((n * parts, PEAK_CAP), dtype=torch.int32, device=dev),
-                scores=torch.zeros((n * parts, PEAK_CAP), **f64),
                 pair_cap=PAIR_CAP,
                 pair_score=torch.empty((n * nl, PAIR_CAP), **f64),
-                end_paf=torch.empty((n * nl, 2, PEAK_CAP, 2), **f64),
                 conn_count=torch.zeros((n * nl,), **i32),
-                conn_ij=torch.zeros((n * nl, PEAK_CAP, 2), **i32),
-                conn_score=torch.zeros((n * nl, PEAK_CAP), **f64),
-                owner=torch.zeros((n, parts * PEAK_CAP, 2), **i32),
                 max_person=MAX_PERSON,
-                candidate=torch.zeros((n, parts * PEAK_CAP, 4), **f64),
                 n_cand=torch.zeros((n,), **i32),
                 subset=torch.zeros((n, MAX_PERSON, self.njoint + 1), **f64),
                 n_person=torch.zeros((n,), **i32),
                 overflow=torch.zeros((1,), **i32),
             )
+            self._size_peak_buffers(ws, n, PEAK_CAP)
             self._work[key] = ws
         return ws
+
+    def _size_peak_buffers(self, ws, n, cap):
+        """(Re)allocates everything whose size follows the peak capacity per (frame, part)."""
+        dev = self.device
+        parts = self.njoint - 1
+        nl = 24 if self._kind == 'body25' else 19
+        i32 = dict(dtype=torch.int32, device=dev)
+        f64 = dict(dtype=torch.float64, device=dev)
+        ws.update(
+            cap=cap,
+            keys=torch.zeros((n * parts, cap), **i32),
+            scores=torch.zeros((n * parts, cap), **f64),
+            end_paf=torch.empty((n * nl, 2, cap, 2), **f64),
+            conn_ij=torch.zeros((n * nl, cap, 2), **i32),
+            conn_score=torch.zeros((n * nl, cap), **f64),
+            owner=torch.zeros((n, parts * cap, 2), **i32),
+            candidate=torch.zeros((n, parts * cap, 4), **f64),
+        )
 
     def network_outputs(self, frames_dev, H, W, lane=0):
         """Runs every scale; returns [(paf, heat, geometry)] with the plans' float32 NCHW output tensors.
@@ -137,12 +150,17 @@ class Body(object):
             arr[i].gh, arr[i].gw, arr[i].hc, arr[i].wc = hp // 8, wp // 8, rh, rw
         return arr
 
+    def _peaks(self, n, H, W, ws):
+        _lib.check(_lib.lib().islpose_body_peaks(_lib.ptr(ws["heat"]), n * (self.njoint - 1), H, W, self._gauss, self.thre1,
+                                                 ws["cap"], _lib.ptr(ws["counts"]), _lib.ptr(ws["keys"]), _lib.ptr(ws["scores"]),
+                                                 _lib.ptr(ws["overflow"]), _lib.stream_ptr()), "islpose_body_peaks")
+
     def _group(self, maps, n, H, W, ws):
         L = _lib.lib()
         parts = self.njoint - 1
         paf_scales = self._scales_struct(maps, 0)
         gb = _lib.GroupBuffers()
-        gb.cap, gb.pair_cap, gb.max_cand, gb.max_person = PEAK_CAP, ws["pair_cap"], parts * PEAK_CAP, ws["max_person"]
+        gb.cap, gb.pair_cap, gb.max_cand, gb.max_person = ws["cap"], ws["pair_cap"], parts * ws["cap"], ws["max_person"]
         for f in ("counts", "keys", "scores", "pair_score", "end_paf", "conn_count", "conn_ij", "conn_score", "owner", "candidate",
                   "n_cand", "subset", "n_person", "overflow"):
             setattr(gb, f, ws[f].data_ptr())
@@ -152,7 +170,7 @@ class Body(object):
         # fresh tensor per call: the hand stage of this batch fills its half while later batches run on this workspace
         ws["features"] = torch.empty((n, 156), dtype=torch.float64, device=self.device)
         _lib.check(L.islpose_body_features(_lib.ptr(ws["candidate"]), _lib.ptr(ws["subset"]), _lib.ptr(ws["n_person"]), n,
-                                           parts * PEAK_CAP, ws["max_person"], 1 if self._kind == 'body25' else 0,
+                                           parts * ws["cap"], ws["max_person"], 1 if self._kind == 'body25' else 0,
                                            _lib.ptr(ws["features"]), _lib.stream_ptr()), "islpose_body_features")
         # the three small result tables travel together, asynchronously, into pinned memory, and with them the leading
         # rows of candidate / subset (as many as recent calls needed, with head room): one synchronisation per call
@@ -187,9 +205,7 @@ class Body(object):
             ws["tail_host"] = torch.zeros((2 * n + 1,), dtype=torch.int32).pin_memory()
         _lib.check(L.islpose_maps_accumulate(heat_scales, len(maps), self.njoint, n, H, W, parts, 1, _lib.ptr(ws["heat"]),
                                              _lib.ptr(ws["mid"]), ws["mid"].numel(), st), "islpose_maps_accumulate")
-        _lib.check(L.islpose_body_peaks(_lib.ptr(ws["heat"]), n * parts, H, W, self._gauss, self.thre1, PEAK_CAP,
-                                        _lib.ptr(ws["counts"]), _lib.ptr(ws["keys"]), _lib.ptr(ws["scores"]),
-                                        _lib.ptr(ws["overflow"]), st), "islpose_body_peaks")
+        self._peaks(n, H, W, ws)
         self._group(maps, n, H, W, ws)
         done = torch.cuda.Event()
         done.record()
@@ -208,16 +224,23 @@ class Body(object):
                 redo = False
                 if flags:
                     ws["overflow"].zero_()
-                    # capacities that cannot grow are reported first: the peak lists were truncated (which peaks survive
-                    # depends on the order of the atomics), so nothing computed from them is returned
+                    # the peak lists were truncated (which peaks survive depends on the order of the atomics), so nothing
+                    # computed from them is returned: larger lists, then peaks and grouping again from the heat maps,
+                    # which are still in the workspace. The reference has no such limit; this one ends at MAX_PEAK_CAP.
                     if flags & (_lib.OVERFLOW_PEAKS | _lib.OVERFLOW_CANDIDATES):
-                        raise _lib.IslposeError("a body part has more than %d peaks in one frame (overflow flags %d): the "
-                                                "peak lists of this call are incomplete" % (PEAK_CAP, flags))
+                        if ws["cap"] >= MAX_PEAK_CAP:
+                            raise _lib.IslposeError("a body part has more than %d peaks in one frame (overflow flags %d)" % (
+                                MAX_PEAK_CAP, flags))
+                        newcap = 1024
+                        while newcap <= ws["cap"]:
+                            newcap *= 2
+                        self._size_peak_buffers(ws, n, min(newcap, MAX_PEAK_CAP))
+                        self._peaks(n, H, W, ws)
                     if flags & _lib.OVERFLOW_PAIRS:
-                        if ws["pair_cap"] >= PEAK_CAP * PEAK_CAP:
+                        if ws["pair_cap"] >= ws["cap"] * ws["cap"]:
                             raise _lib.IslposeError("pair matrix overflow at its maximum size")
                         # a limb has more candidate pairs than the scratch matrix holds: enlarge it and redo the grouping
-                        ws["pair_cap"] = min(ws["pair_cap"] * 4, PEAK_CAP * PEAK_CAP)
+                        ws["pair_cap"] = min(ws["pair_cap"] * 4, ws["cap"] * ws["cap"])
                         ws["pair_score"] = torch.empty((ws["conn_count"].numel(), ws["pair_cap"]), dtype=torch.float64,
                                                        device=self.device)
                     if flags & _lib.OVERFLOW_PERSONS:
@@ -235,6 +258,7 @@ class Body(object):
                 if not redo:
                     break
                 self._group(maps, n, H, W, ws)
+                ticket["features"] = ws["features"]   # the rows of the repeated grouping, not of the truncated one
                 ticket["done"] = torch.cuda.Event()
                 ticket["done"].record()
             cand, sub = ws["cand_host"].numpy(), ws["sub_host"].numpy()

@@ -112,6 +112,7 @@ struct islpose_plan {
   int graph_state = 0;
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t graph_exec = nullptr;
+  char graph_note[160] = "";   // why recording failed (islpose_plan_graph_note)
   ~islpose_plan() {
     if (graph_exec != nullptr) cudaGraphExecDestroy(graph_exec);
     if (graph != nullptr) cudaGraphDestroy(graph);
@@ -206,24 +207,28 @@ int islpose_plan_set_graph(islpose_plan* plan, int32_t enable) {
   return 0;
 }
 
-static int plan_capture(islpose_plan* plan, cudaStream_t st) {
-  // thread-local mode: other host threads (allocators, other lanes) keep making CUDA calls while this one records
-  if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
-    cudaGetLastError();
+static int plan_capture(islpose_plan* plan) {
+  // Recorded on a private stream (the caller's may be the legacy default stream, which cannot capture; nothing executes
+  // while recording, so no ordering with the caller's stream is needed). Thread-local mode: other host threads
+  // (allocators, other lanes) keep making CUDA calls while this one records.
+  cudaStream_t st = nullptr;
+  if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) {
+    snprintf(plan->graph_note, sizeof(plan->graph_note), "no capture stream: %s", cudaGetErrorString(cudaGetLastError()));
     return 1;
   }
+  cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
   int rc = 0;
-  for (size_t i = 0; i < plan->ops.size() && rc == 0; ++i) rc = run_op(plan->ops[i], st);
   cudaGraph_t g = nullptr;
-  const cudaError_t e = cudaStreamEndCapture(st, &g);
-  if (rc != 0 || e != cudaSuccess || g == nullptr) {
-    if (g != nullptr) cudaGraphDestroy(g);
-    cudaGetLastError();
-    return 1;
+  if (e == cudaSuccess) {
+    for (size_t i = 0; i < plan->ops.size() && rc == 0; ++i) rc = run_op(plan->ops[i], st);
+    e = cudaStreamEndCapture(st, &g);
   }
   cudaGraphExec_t ge = nullptr;
-  if (cudaGraphInstantiate(&ge, g, 0) != cudaSuccess) {
-    cudaGraphDestroy(g);
+  if (rc == 0 && e == cudaSuccess && g != nullptr) e = cudaGraphInstantiate(&ge, g, 0);
+  cudaStreamDestroy(st);
+  if (rc != 0 || e != cudaSuccess || ge == nullptr) {
+    snprintf(plan->graph_note, sizeof(plan->graph_note), "capture failed (launch rc %d): %s", rc, cudaGetErrorString(e));
+    if (g != nullptr) cudaGraphDestroy(g);
     cudaGetLastError();
     return 1;
   }
@@ -238,7 +243,9 @@ int islpose_plan_run(islpose_plan* plan, void* stream) {
   if (plan->use_graph && plan->graph_state == 0 && plan->ops.size() > 1) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone)
-      plan->graph_state = plan_capture(plan, st) == 0 ? 1 : -1;
+      plan->graph_state = plan_capture(plan) == 0 ? 1 : -1;
+    else
+      cudaGetLastError();
   }
   if (plan->use_graph && plan->graph_state == 1) {
     if (cudaGraphLaunch(plan->graph_exec, st) != cudaSuccess) return check_cuda("plan_run/graph") ? 1 : set_err("plan_run: graph launch failed");
@@ -288,6 +295,7 @@ int islpose_plan_profile(const islpose_plan* plan, void* stream, int32_t reps, f
 }
 
 int32_t islpose_plan_graph_state(const islpose_plan* plan) { return plan ? plan->graph_state : 0; }
+const char* islpose_plan_graph_note(const islpose_plan* plan) { return plan ? plan->graph_note : ""; }
 int32_t islpose_plan_num_launches(const islpose_plan* plan) { return plan ? static_cast<int32_t>(plan->ops.size()) : 0; }
 double islpose_plan_conv_flops(const islpose_plan* plan) { return plan ? plan->flops : 0.0; }
 
@@ -341,7 +349,8 @@ int islpose_body_peaks(const double* heat, int32_t planes, int32_t H, int32_t W,
                        int32_t cap, int32_t* counts, uint32_t* keys, double* scores, int32_t* overflow, void* stream) {
   if (heat == nullptr || h_gauss == nullptr || counts == nullptr || keys == nullptr || scores == nullptr || overflow == nullptr)
     return set_err("body_peaks: null pointer");
-  if (cap <= 0 || cap > 1024) return set_err("body_peaks: cap must be in 1..1024, got %d", cap);
+  if (cap <= 0 || cap > kMaxPeakCap || (cap > 1024 && (cap & (cap - 1)) != 0))
+    return set_err("body_peaks: cap must be in 1..1024 or a power of two up to %d, got %d", kMaxPeakCap, cap);
   GaussWeights gw;
   memcpy(gw.w, h_gauss, sizeof(gw.w));
   if (launch_gauss_nms(heat, planes, H, W, gw, thre1, cap, counts, keys, scores, overflow, static_cast<cudaStream_t>(stream)) != 0)

@@ -147,7 +147,6 @@ paf_score_kernel(const ScaleSet ss, const LimbTable lt, int H, int W, int parts,
   }
 }
 
-constexpr int kPeakCap = 1024;
 
 // Greedy matching in parallel rounds. With a strict total order on the candidate pairs (score descending, then
 // i*nB+j ascending = the reference's enumeration order, which Python's stable sort preserves for equal scores),
@@ -157,14 +156,30 @@ constexpr int kPeakCap = 1024;
 // accepting it blocks exactly the pairs the sequential walk would skip.) The walk stops at min(nA, nB) connections,
 // which is also when no free row or no free column is left. Accepted connections are finally sorted into the
 // order the walk would have produced them in, because the person assembly consumes them in that order.
+// Dynamic shared memory, sized by the peak capacity (match_smem_bytes): 32.25 bytes per peak slot.
+// Array lengths are the capacity rounded up to a power of two (the final bitonic sort pads to one).
+__host__ __device__ inline int pow2_at_least(int v) {
+  int p = 32;
+  while (p < v) p <<= 1;
+  return p;
+}
+__host__ __device__ inline size_t match_smem_bytes(int cap) {
+  const size_t c = static_cast<size_t>(pow2_at_least(cap));
+  return c * 32 + (c / 32 + 1) * 8;
+}
+
 __global__ void __launch_bounds__(256)
 match_kernel(const LimbTable lt, const GroupBuffers gb) {
-  __shared__ double s_rowv[kPeakCap];
-  __shared__ int s_rowj[kPeakCap];
-  __shared__ int s_coli[kPeakCap];
-  __shared__ uint32_t s_usedA[kPeakCap / 32], s_usedB[kPeakCap / 32];
-  __shared__ double s_cv[kPeakCap];   // accepted connections: score, i, j
-  __shared__ int s_ci[kPeakCap], s_cj[kPeakCap];
+  extern __shared__ double s_match[];
+  const int kcap = pow2_at_least(gb.cap);
+  double* const s_rowv = s_match;                 // [cap] best free partner's score per row
+  double* const s_cv = s_rowv + kcap;             // [cap] accepted connections: score, i, j
+  int* const s_rowj = reinterpret_cast<int*>(s_cv + kcap);
+  int* const s_coli = s_rowj + kcap;
+  int* const s_ci = s_coli + kcap;
+  int* const s_cj = s_ci + kcap;
+  uint32_t* const s_usedA = reinterpret_cast<uint32_t*>(s_cj + kcap);
+  uint32_t* const s_usedB = s_usedA + (kcap / 32 + 1);
   __shared__ int s_made, s_round;
   const int k = blockIdx.x, n = blockIdx.y;
   const int parts = lt.njoint - 1;
@@ -181,7 +196,7 @@ match_kernel(const LimbTable lt, const GroupBuffers gb) {
     return;
   }
   const double* sc = gb.pair_score + static_cast<long long>(slot) * gb.pair_cap;
-  for (int i = threadIdx.x; i < kPeakCap / 32; i += blockDim.x) {
+  for (int i = threadIdx.x; i < kcap / 32 + 1; i += blockDim.x) {
     s_usedA[i] = 0;
     s_usedB[i] = 0;
   }
@@ -459,7 +474,7 @@ assemble_kernel(const LimbTable lt, int W, const GroupBuffers gb) {
 
 int launch_paf_score(const ScaleSet& paf, const LimbTable& lt, int N, int H, int W, double thre2, int mid_num,
                      const GroupBuffers& gb, cudaStream_t st) {
-  if (mid_num != 10 || gb.cap > kPeakCap) return 1;
+  if (mid_num != 10 || gb.cap > kMaxPeakCap) return 1;
   if (gb.end_paf == nullptr) return 1;
   paf_endpoints_kernel<<<dim3(8, lt.nlimbs * 2, N), 128, 0, st>>>(paf, lt, W, lt.njoint - 1, gb);
   const dim3 grid(48, lt.nlimbs, N);
@@ -468,8 +483,19 @@ int launch_paf_score(const ScaleSet& paf, const LimbTable& lt, int N, int H, int
 }
 
 int launch_group(const LimbTable& lt, int N, int W, const GroupBuffers& gb, cudaStream_t st) {
-  if (gb.cap > kPeakCap || lt.njoint + 1 > 32) return 1;
-  match_kernel<<<dim3(lt.nlimbs, N), 256, 0, st>>>(lt, gb);
+  if (gb.cap > kMaxPeakCap || lt.njoint + 1 > 32) return 1;
+  const size_t smem = match_smem_bytes(gb.cap);
+  if (smem > 48 * 1024) {  // opt in to large dynamic shared memory once per device
+    static bool done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!done[dev & 63]) {
+      if (cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(match_smem_bytes(kMaxPeakCap))) != cudaSuccess)
+        return 1;
+      done[dev & 63] = true;
+    }
+  }
+  match_kernel<<<dim3(lt.nlimbs, N), 256, smem, st>>>(lt, gb);
   assemble_kernel<<<N, 256, 0, st>>>(lt, W, gb);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }

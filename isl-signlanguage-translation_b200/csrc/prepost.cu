@@ -320,13 +320,38 @@ gauss_nms_kernel(const double* __restrict__ heat, int H, int W, const GaussWeigh
                                  scores + static_cast<long long>(plane_id) * cap, nullptr);
 }
 
-// One CTA per (frame, part): bitonic sort of the appended peaks by y*W+x = np.nonzero order.
-constexpr int kSortCap = 1024;
+// One CTA per (frame, part): bitonic sort of the appended peaks by y*W+x = np.nonzero order. Lists of up to 1024
+// peaks are sorted in shared memory; longer ones (caps up to kMaxPeakCap, after the host grew the capacity) in place in
+// global memory, padded with sentinels up to the next power of two (cap itself is a power of two >= that).
+constexpr int kSortSmem = 1024;
+template <typename KeyPtr, typename ValPtr>
+__device__ __forceinline__ void bitonic_by_key(KeyPtr k, ValPtr v, int m) {
+  for (int size = 2; size <= m; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const int j = i ^ stride;
+        if (j > i) {
+          const bool up = (i & size) == 0;
+          const uint32_t a = k[i], b = k[j];
+          if ((a > b) == up) {
+            k[i] = b;
+            k[j] = a;
+            const double t = v[i];
+            v[i] = v[j];
+            v[j] = t;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
 __global__ void __launch_bounds__(512)
 sort_peaks_kernel(int cap, int* __restrict__ counts, uint32_t* __restrict__ keys, double* __restrict__ scores,
                   int* __restrict__ overflow) {
-  __shared__ uint32_t s_k[kSortCap];
-  __shared__ double s_s[kSortCap];
+  __shared__ uint32_t s_k[kSortSmem];
+  __shared__ double s_s[kSortSmem];
   const int id = blockIdx.x;
   int n = counts[id];
   if (n > cap) {
@@ -341,33 +366,24 @@ sort_peaks_kernel(int cap, int* __restrict__ counts, uint32_t* __restrict__ keys
   double* sc = scores + static_cast<long long>(id) * cap;
   int m = 2;
   while (m < n) m <<= 1;
-  for (int i = threadIdx.x; i < m; i += blockDim.x) {
-    s_k[i] = i < n ? k[i] : 0xffffffffu;
-    s_s[i] = i < n ? sc[i] : 0.0;
-  }
-  __syncthreads();
-  for (int size = 2; size <= m; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int i = threadIdx.x; i < m; i += blockDim.x) {
-        const int j = i ^ stride;
-        if (j > i) {
-          const bool up = (i & size) == 0;
-          const uint32_t a = s_k[i], b = s_k[j];
-          if ((a > b) == up) {
-            s_k[i] = b;
-            s_k[j] = a;
-            const double t = s_s[i];
-            s_s[i] = s_s[j];
-            s_s[j] = t;
-          }
-        }
-      }
-      __syncthreads();
+  if (m <= kSortSmem) {
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+      s_k[i] = i < n ? k[i] : 0xffffffffu;
+      s_s[i] = i < n ? sc[i] : 0.0;
     }
-  }
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    k[i] = s_k[i];
-    sc[i] = s_s[i];
+    __syncthreads();
+    bitonic_by_key(s_k, s_s, m);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      k[i] = s_k[i];
+      sc[i] = s_s[i];
+    }
+  } else {  // m <= cap: the sentinels sort to the end and are never read (counts stays n)
+    for (int i = n + threadIdx.x; i < m; i += blockDim.x) {
+      k[i] = 0xffffffffu;
+      sc[i] = 0.0;
+    }
+    __syncthreads();
+    bitonic_by_key(k, sc, m);
   }
 }
 
@@ -428,7 +444,7 @@ int launch_heat_accumulate(const ScaleSet& ss, int N, int H, int W, int parts, i
 
 int launch_gauss_nms(const double* heat, int planes_total, int H, int W, const GaussWeights& gw, double thre, int cap,
                      int* counts, uint32_t* keys, double* scores, int* overflow, cudaStream_t st) {
-  if (cap > kSortCap) return 1;
+  if (cap > kMaxPeakCap || (cap > kSortSmem && (cap & (cap - 1)) != 0)) return 1;
   if (cudaMemsetAsync(counts, 0, sizeof(int) * planes_total, st) != cudaSuccess) return 1;
   const dim3 grid((W + kG2W - 1) / kG2W, (H + kG2H - 1) / kG2H, planes_total);
   gauss_nms_kernel<<<grid, kG2Threads, 0, st>>>(heat, H, W, gw, thre, cap, counts, keys, scores);

@@ -32,13 +32,15 @@ int launch_gauss_nms(const double* heat, int planes_total, int H, int W, const G
 int launch_pack_conv_weights(const float* w, int cout, int cin, int ksize, const int* chan_map, int in_c, int w_cin, int first,
                              void* out, cudaStream_t st);
 
+constexpr int kMaxPeakCap = 4096;  // peaks per (frame, part) the sort / matching kernels can hold; powers of two above 1024
+
 // Capacity flags OR-ed into the `overflow` word (one bit each, so that one cannot mask another)
 enum { kOverflowPeaks = 1, kOverflowCandidates = 2, kOverflowPairs = 4, kOverflowPersons = 8 };
 
 // group.cu
 struct GroupBuffers {
   // inputs: sorted peak lists per (frame, part)
-  int cap;               // peak capacity per part (<= 1024)
+  int cap;               // peak capacity per part (<= kMaxPeakCap)
   const int* counts;     // [N*parts]
   const uint32_t* keys;  // [N*parts*cap]  y*W+x
   const double* scores;  // [N*parts*cap]  unsmoothed heat value

@@ -335,27 +335,68 @@ def test_overflow_flags_do_not_mask_each_other(dev):
     assert int(flags.item()) == _lib.OVERFLOW_PEAKS | _lib.OVERFLOW_PAIRS
 
 
-def test_body_raises_on_peak_overflow_and_recovers(dev, monkeypatch):
-    """Through the public API: more than PEAK_CAP peaks in one part is an IslposeError (never a silently truncated,
-    run-to-run varying result), and the same Body keeps working afterwards."""
-    from isl_b200 import body as body_mod
-    monkeypatch.setattr(body_mod, "PEAK_CAP", 8)
-    body = isl_b200.Body(O.make_flat_weights("coco", seed=1), "coco")
-    H, W = 96, 128
-    sk = synth.synth_skeletons("coco", 12, 3)
+def _injected(body, sk, H, W, dev):
     maps = []
     for (m, rh, rw, hp, wp) in scale_geometry(H, W, body.scale_search, body.boxsize):
         paf, heat = synth.render_maps("coco", sk, hp // 8, wp // 8)
         maps.append((torch.from_numpy(paf)[None].contiguous().to(dev), torch.from_numpy(heat)[None].contiguous().to(dev), (rh, rw, hp, wp)))
+    return maps
+
+
+def test_peak_capacity_grows_and_its_end_is_an_error(dev, monkeypatch):
+    """The reference has no limit on peaks per part. Here the lists start at PEAK_CAP and grow on overflow (peaks and
+    grouping are redone from the heat maps), with identical results; only beyond MAX_PEAK_CAP is there an IslposeError -
+    never a silently truncated, run-to-run varying result - and the same Body keeps working afterwards."""
+    from isl_b200 import body as body_mod
+    H, W = 96, 128
+    flat = O.make_flat_weights("coco", seed=1)
+    sk = synth.synth_skeletons("coco", 12, 3)
+    want = isl_b200.Body(flat, "coco")
+    (wc, wsub), = want.postprocess(_injected(want, sk, H, W, dev), 1, H, W, want._workspace(1, H, W))
+    monkeypatch.setattr(body_mod, "PEAK_CAP", 8)      # 12 people: every part overflows 8 slots
+    body = isl_b200.Body(flat, "coco")
+    ws = body._workspace(1, H, W)
+    assert ws["cap"] == 8
+    (c, s), = body.postprocess(_injected(body, sk, H, W, dev), 1, H, W, ws)
+    assert ws["cap"] == 1024 and np.array_equal(c, wc) and np.array_equal(s, wsub)
+    monkeypatch.setattr(body_mod, "MAX_PEAK_CAP", 8)
+    small = isl_b200.Body(flat, "coco")
     with pytest.raises(_lib.IslposeError):
-        body.postprocess(maps, 1, H, W, body._workspace(1, H, W))
-    sk2 = synth.synth_skeletons("coco", 2, 3)
-    maps2 = []
-    for (m, rh, rw, hp, wp) in scale_geometry(H, W, body.scale_search, body.boxsize):
-        paf, heat = synth.render_maps("coco", sk2, hp // 8, wp // 8)
-        maps2.append((torch.from_numpy(paf)[None].contiguous().to(dev), torch.from_numpy(heat)[None].contiguous().to(dev), (rh, rw, hp, wp)))
-    (cand, sub), = body.postprocess(maps2, 1, H, W, body._workspace(1, H, W))
+        small.postprocess(_injected(small, sk, H, W, dev), 1, H, W, small._workspace(1, H, W))
+    (cand, sub), = small.postprocess(_injected(small, synth.synth_skeletons("coco", 2, 3), H, W, dev), 1, H, W,
+                                     small._workspace(1, H, W))
     assert len(cand) >= 30
+
+
+def test_more_than_1024_peaks_in_one_part(dev):
+    """A plane with ~1500 peaks: the lists grow to 2048 (global-memory sort, matching with 64 KB of shared memory) and
+    the peak table equals the oracle's."""
+    H, W = 240, 320
+    body = isl_b200.Body(O.make_flat_weights("coco", seed=1), "coco")
+    yy, xx = np.mgrid[0:H // 8, 0:W // 8]
+    heat = np.zeros((19, H // 8, W // 8), np.float32)
+    heat[3] = 0.5 + 0.4 * ((yy + xx) % 2)          # a checkerboard at stride 8: a maximum every 16 px in both diagonals
+    heat[3] += 0.01 * np.random.RandomState(0).rand(H // 8, W // 8).astype(np.float32)
+    fine = np.zeros((19, H, W))
+    maps = [(torch.zeros((1, 38, H // 8, W // 8), device=dev), torch.from_numpy(heat)[None].contiguous().to(dev), (H, W, H, W))]
+    body.scale_search = [368.0 / H * 1.0]   # geometry only matters through `maps` here
+    ws = body._workspace(1, H, W)
+    # a denser field than any network gives: write the float64 plane directly, then run peaks + grouping
+    rng = np.random.RandomState(1)
+    plane = 0.3 + 0.2 * rng.rand(H, W)
+    ws["heat"].zero_()
+    ws["heat"][0, 3] = torch.from_numpy(plane).to(dev)
+    body._peaks(1, H, W, ws)
+    body._group(maps, 1, H, W, ws)
+    ticket = dict(maps=maps, n=1, H=H, W=W, ws=ws, done=torch.cuda.Event(), stream=torch.cuda.current_stream(), features=None)
+    ticket["done"].record()
+    (cand, sub), = body.post_finish(ticket)
+    heat_avg = np.zeros((H, W, 19))
+    heat_avg[:, :, 3] = plane
+    want = np.array([list(p) for part in O.body_peaks(heat_avg, 19, backend="lib") for p in part], dtype=np.float64).reshape(-1, 4)
+    assert len(want) > 1024 and ws["cap"] >= 2048
+    assert cand.shape == want.shape and np.array_equal(cand, want)
+    del fine
 
 
 def test_pipeline_with_host_frames_equals_batch(dev):
@@ -412,8 +453,9 @@ def test_device_feature_rows_through_the_abi(dev, fixture):
     peaks[0, 4] = 0
     peaks[1, 7, 0] = 0
     table = np.array([[0, 0, 11, 22], [0, 1, 300, 40], [0, -1, 5, 5], [2, 0, 64, 0]], dtype=np.int32)
-    _lib.check(L.islpose_hand_features(_lib.ptr(torch.from_numpy(table).to(dev)), _lib.ptr(torch.from_numpy(peaks).to(dev)), 4, n,
-                                       _lib.ptr(rows), _lib.stream_ptr()), "hand_features")
+    d_table, d_peaks = torch.from_numpy(table).to(dev), torch.from_numpy(peaks).to(dev)   # kept alive across the launch
+    _lib.check(L.islpose_hand_features(_lib.ptr(d_table), _lib.ptr(d_peaks), 4, n, _lib.ptr(rows), _lib.stream_ptr()),
+               "hand_features")
     got = rows.cpu().numpy()
 
     def shifted(k):
@@ -486,7 +528,8 @@ def test_plans_replay_as_cuda_graphs_with_identical_results(dev):
     for _ in range(3):
         got = net(x)
         assert all(torch.equal(a, b) for a, b in zip(got, want))
-    assert _lib.lib().islpose_plan_graph_state(net.instance(2, 64, 88).handle) == 1
+    h = net.instance(2, 64, 88).handle
+    assert _lib.lib().islpose_plan_graph_state(h) == 1, _lib.lib().islpose_plan_graph_note(h)
     # replays on another stream than the one the graph was recorded on
     with torch.cuda.stream(torch.cuda.Stream()):
         got = net(x)

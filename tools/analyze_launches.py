@@ -28,13 +28,13 @@ def main(path, body_kind, body_hw, hand_hw, n_body, n_hand):
         print("  %-52s n=%5d %9.3f ms %5.1f%%  avg %8.1f us" % (k[:52], v[0], v[1] / 1e6, 100 * v[1] / allt, v[1] / v[0] / 1e3))
     bystream = collections.defaultdict(list)
     for r in rows:
-        if any(t in r['Kernel Name'] for t in ('conv_umma', 'conv_first', 'maxpool', 'im2col')):
+        if any(t in r['Kernel Name'] for t in ('conv_umma', 'conv_first')):
             bystream[r['Stream']].append(r)
     last = {}
     for st, lst in bystream.items():
         cur = None
         for r in lst:
-            if 'im2col' in r['Kernel Name'] or 'conv_first' in r['Kernel Name']:
+            if 'conv_first' in r['Kernel Name']:
                 cur = []
                 last[(st, r['Grid Size'])] = cur
             elif cur is not None:
@@ -47,7 +47,7 @@ def main(path, body_kind, body_hw, hand_hw, n_body, n_hand):
         print("  stream %s: %3d launches %8.3f ms" % (st, len(p), t / 1e6))
     for kind, hw, n, length in ((body_kind, body_hw, n_body, None), ("hand", hand_hw, n_hand, 56)):
         prog = nets.build_program(kind)
-        steps = [s for s in prog.steps if s[0] != 'im2col']
+        steps = [s for s in prog.steps if s[0] == 'conv']   # the pools are fused into their producers
         cands = [p for p in plans if p[2] == len(steps)]
         if not cands:
             continue
@@ -78,5 +78,14 @@ def main(path, body_kind, body_hw, hand_hw, n_body, n_hand):
 
 
 if __name__ == "__main__":
-    a = sys.argv
-    main(a[1], a[2], (int(a[3]), int(a[4])), (int(a[5]), int(a[5])), int(a[6]), int(a[7]))
+    import argparse
+
+    ap = argparse.ArgumentParser(description=__doc__)
+    ap.add_argument("csv", help="ncu --metrics gpu__time_duration.sum --csv launch list")
+    ap.add_argument("--body", default="coco", choices=["coco", "body25"])
+    ap.add_argument("--body-hw", type=int, nargs=2, default=[736, 984], help="largest body network input (h w)")
+    ap.add_argument("--hand-hw", type=int, default=736, help="largest hand network input (square)")
+    ap.add_argument("--n-body", type=int, default=8, help="frames per body replay")
+    ap.add_argument("--n-hand", type=int, default=16, help="crops per hand replay")
+    a = ap.parse_args()
+    main(a.csv, a.body, tuple(a.body_hw), (a.hand_hw, a.hand_hw), a.n_body, a.n_hand)

@@ -91,7 +91,7 @@ def main():
                                              None, 0, _lib.stream_ptr()), "acc1")
 
     def peaks():
-        _lib.check(L.islpose_body_peaks(_lib.ptr(ws["heat"]), nb * parts, H, W, body._gauss, body.thre1, 1024,
+        _lib.check(L.islpose_body_peaks(_lib.ptr(ws["heat"]), nb * parts, H, W, body._gauss, body.thre1, ws["cap"],
                                         _lib.ptr(ws["counts"]), _lib.ptr(ws["keys"]), _lib.ptr(ws["scores"]),
                                         _lib.ptr(ws["overflow"]), _lib.stream_ptr()), "peaks")
 
