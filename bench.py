@@ -122,32 +122,48 @@ class ClockSampler(threading.Thread):
 
 
 def cpu_reference_frame(wl, seed, nets=None):
-    """One frame of the workload through the oracle port of the reference (backend 'lib': cv2 / scipy / torch CPU
-    exactly where the reference calls them). Returns (seconds, nets) so repeated calls reuse the weights."""
+    """One frame of the workload on the host cores. With the reference's own files at hand (oracle/_ref/, placed there by
+    __graft_entry__.build() in the build container; /root/reference itself there) this runs the UNMODIFIED reference:
+    its Body.__call__ / Hand.__call__ over its nn.Modules (kind "reference"). Otherwise the oracle port in `lib` mode:
+    cv2 / scipy / torch CPU exactly where the reference calls them (kind "port"). Returns (seconds, state)."""
     import torch
 
     from isl_b200 import synth
     from oracle import openpose_oracle as O
+    from oracle import ref_import
 
     mt, H, W, boxes, _ = WORKLOADS[wl]
     if nets is None:
         torch.set_num_threads(os.cpu_count() or 1)
-        nets = (O.make_net_fn(mt, synth.make_flat_weights(mt, seed=0, init=WEIGHT_INIT)),
-                O.make_net_fn("hand", synth.make_flat_weights("hand", seed=0, init=WEIGHT_INIT)))
+        flat_b = synth.make_flat_weights(mt, seed=0, init=WEIGHT_INIT)
+        flat_h = synth.make_flat_weights("hand", seed=0, init=WEIGHT_INIT)
+        if ref_import.available():
+            nets = ("reference", ref_import.make_body(mt, ref_import.reference_module(mt, flat_b), SCALES),
+                    ref_import.make_hand(ref_import.reference_module("hand", flat_h)))
+        else:
+            nets = ("port", O.make_net_fn(mt, flat_b), O.make_net_fn("hand", flat_h))
     frame = synth.synth_frame(H, W, seed)
     t0 = time.perf_counter()
-    try:
-        O.body_call(nets[0], frame, mt, tuple(SCALES), backend="lib", strict=False)
-    except IndexError:
-        pass
-    for (x, y, w, _) in boxes:
-        O.hand_call(nets[1], np.ascontiguousarray(frame[y:y + w, x:x + w, :]), backend="lib")
+    with torch.no_grad():
+        try:
+            if nets[0] == "reference":
+                nets[1](frame)
+            else:
+                O.body_call(nets[1], frame, mt, tuple(SCALES), backend="lib", strict=False)
+        except IndexError:
+            pass   # body.py:193-197 raises on a third matching row (noisy maps); the frame's time still counts
+        for (x, y, w, _) in boxes:
+            crop = np.ascontiguousarray(frame[y:y + w, x:x + w, :])
+            if nets[0] == "reference":
+                nets[2](crop)
+            else:
+                O.hand_call(nets[2], crop, backend="lib")
     return time.perf_counter() - t0, nets
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path (oracle port; the Python reference cannot
-    travel to the GPU box) on all host threads, one frame of the workload per step."""
+    """--impl reference: the reference's CPU implementation of the path on all host threads, one frame of the workload
+    per step: the unmodified reference when its files are at hand (cpu_reference_frame), else the oracle port."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -177,7 +193,7 @@ def run_reference(args):
             "config": {"workload": workload_name(wl, WORKLOADS[wl][4]),
                        "timing": "host wall clock around each step (CPU only, no device work); a step here is ONE frame of the "
                                  "workload (the GPU arm's step is the whole batch): frames/s is per-frame work either way"},
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": nets[0], "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -547,7 +563,7 @@ def main():
             while len(ts) < 2 or (sum(ts) < 12.0 and len(ts) < 4):
                 t, nets = cpu_reference_frame(wl, 1 + len(ts), nets)
                 ts.append(t)
-            line["cpu_baseline"] = {"value": len(ts) / sum(ts), "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "port",
+            line["cpu_baseline"] = {"value": len(ts) / sum(ts), "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": nets[0],
                                     "sample": "%d frames of the workload (body 4 scales + %d hands each) after one untimed frame, "
                                               "%.1f s of CPU work" % (len(ts), len(boxes), sum(ts))}
         print(json.dumps(line), flush=True)

@@ -17,7 +17,29 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("ISL_REFERENCE_ROOT", "/root/reference")
+# /root/reference in the build container; on the GPU box the copy of the four hot-path files that
+# __graft_entry__.build() places under oracle/_ref/ (git-ignored, travels with the gpurun snapshot like built .so files)
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CANDIDATES = [os.environ.get("ISL_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "_ref")]
+REFERENCE_ROOT = next((c for c in _CANDIDATES if c and os.path.isfile(os.path.join(c, "src", "body.py"))), "/root/reference")
+HOT_PATH_FILES = ("model.py", "body.py", "hand.py", "util.py")
+
+
+def vendor(dst=None):
+    """Copies the reference's four hot-path files, unmodified, from /root/reference into oracle/_ref/src/ so that
+    bench.py's reference arm can run the UNMODIFIED reference on the GPU box (where /root/reference does not exist).
+    oracle/_ref/ is git-ignored: the files never enter this repository's history."""
+    import shutil
+
+    src_root = "/root/reference"
+    if not os.path.isfile(os.path.join(src_root, "src", "body.py")):
+        return False
+    dst = dst or os.path.join(_HERE, "_ref")
+    os.makedirs(os.path.join(dst, "src"), exist_ok=True)
+    for f in HOT_PATH_FILES:
+        shutil.copyfile(os.path.join(src_root, "src", f), os.path.join(dst, "src", f))
+    open(os.path.join(dst, "src", "__init__.py"), "a").close()
+    return True
 
 
 def available():
@@ -99,3 +121,12 @@ def make_hand(net):
     h = hand.Hand.__new__(hand.Hand)
     h.model = net
     return h
+
+
+def reference_module(kind, flat):
+    """The reference nn.Module with flat Caffe-named weights loaded exactly like Body/Hand.__init__ do
+    (util.transfer + load_state_dict, body.py:35-36)."""
+    rmodel, _, _, rutil = load()
+    net = {"coco": rmodel.bodypose_model, "body25": rmodel.bodypose_25_model, "hand": rmodel.handpose_model}[kind]()
+    net.load_state_dict(rutil.transfer(net, flat))
+    return net.eval()

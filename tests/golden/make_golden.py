@@ -70,12 +70,7 @@ def hand_points(seed, missing):
     return pts
 
 
-def reference_module(kind, flat):
-    """Builds the reference nn.Module and loads flat Caffe-named weights exactly like Body/Hand.__init__."""
-    rmodel, _, _, rutil = ref_import.load()
-    net = {"coco": rmodel.bodypose_model, "body25": rmodel.bodypose_25_model, "hand": rmodel.handpose_model}[kind]()
-    net.load_state_dict(rutil.transfer(net, flat))
-    return net.eval()
+reference_module = ref_import.reference_module
 
 
 def main():

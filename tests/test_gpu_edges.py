@@ -129,7 +129,7 @@ def test_abi_error_paths_on_device(dev):
     assert L.islpose_plan_add_conv(handle, C.byref(d)) != 0 and b"pool" in L.islpose_last_error()
     assert L.islpose_pack_conv_weights(buf.data_ptr(), 64, 60, 3, None, 64, 64, 0, buf.data_ptr(), None) != 0
     assert L.islpose_hand_keypoints(None, 1, 4, (C.c_double * 25)(), 0.05, buf.data_ptr(), 0, buf.data_ptr(), None) != 0
-    assert L.islpose_body_peaks(buf.data_ptr(), 1, 8, 8, (C.c_double * 25)(), 0.1, 4096, buf.data_ptr(), buf.data_ptr(),
+    assert L.islpose_body_peaks(buf.data_ptr(), 1, 8, 8, (C.c_double * 25)(), 0.1, 5000, buf.data_ptr(), buf.data_ptr(),
                                 buf.data_ptr(), buf.data_ptr(), None) != 0
     assert L.islpose_plan_destroy(handle) == 0
 
