@@ -167,6 +167,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # the reference picks its device by torch.cuda.is_available() (body.py:31,59): hide the GPUs so that this arm is its
+    # CPU path on the box's host cores (must happen before torch is imported, which is why torch imports live in functions)
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""
     wl = args.workload
     budget_s = 240.0
     warm, nets = cpu_reference_frame(wl, 999)
@@ -556,16 +559,17 @@ def main():
             sr.update(summarise(m, world, n_sm))
             line["sub_results"].append(sr)
         if world == 1 and not args.no_cpu_baseline:
-            # bounded sample of the same workload on the host cores: one untimed frame (weights, thread pools), then
-            # frames until about 12 s of CPU work have been timed (at least 2, at most 4)
-            _, nets = cpu_reference_frame(wl, 0)
-            ts = []
-            while len(ts) < 2 or (sum(ts) < 12.0 and len(ts) < 4):
-                t, nets = cpu_reference_frame(wl, 1 + len(ts), nets)
-                ts.append(t)
-            line["cpu_baseline"] = {"value": len(ts) / sum(ts), "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": nets[0],
-                                    "sample": "%d frames of the workload (body 4 scales + %d hands each) after one untimed frame, "
-                                              "%.1f s of CPU work" % (len(ts), len(boxes), sum(ts))}
+            # bounded sample of the same workload on the host cores: the reference arm of this script in a child process
+            # without GPUs (one untimed frame for weights and thread pools, then two timed frames: ~10-30 s of CPU work)
+            child = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", wl,
+                                    "--steps", "2", "--warmup", "1", "--weights", WEIGHT_INIT],
+                                   capture_output=True, text=True, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+            rows = [l for l in child.stdout.splitlines() if l.startswith("{")]
+            if child.returncode == 0 and rows:
+                line["cpu_baseline"] = json.loads(rows[-1])["cpu_baseline"]
+            else:
+                line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                        "sample": "reference arm failed: " + child.stderr[-300:]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
