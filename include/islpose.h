@@ -55,6 +55,9 @@ typedef struct islpose_conv_desc {
   int32_t n_tile, stages, tile_w, tile_h; /* tuning overrides, 0 = automatic */
   int32_t pool;         /* 1: nn.MaxPool2d(2,2,0) fused behind the activation (src/model.py:30-32); out_bf16 is then the pooled
                            [n][h/2][w/2] buffer. Only for 3x3 / 7x7 layers with >= 64 input and >= 48 output channels */
+  int32_t sm_budget;    /* SMs the layer's persistent kernel may occupy, 0 = all. Plans that run side by side on several
+                           streams (the scales of one small batch) finish sooner when each keeps to a share of the device
+                           than when every layer of every plan asks for all of it */
 } islpose_conv_desc;
 
 /* Weight ingestion (src/body.py:35-36, src/util.py:35-44): one nn.Conv2d weight, float32 [cout][cin][k][k] on the device,

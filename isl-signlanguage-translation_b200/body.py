@@ -111,7 +111,8 @@ class Body(object):
         L = _lib.lib()
         n = frames_dev.shape[0]
         geoms = scale_geometry(H, W, self.scale_search, self.boxsize)
-        insts = [self.model.instance(n, hp, wp, lane) for (_, _, _, hp, wp) in geoms]
+        budgets = self.model.share_sms([(n, hp, wp) for (_, _, _, hp, wp) in geoms])
+        insts = [self.model.instance(n, hp, wp, lane, sm_budget=b) for (_, _, _, hp, wp), b in zip(geoms, budgets)]
         main = torch.cuda.current_stream()
         streams = self._streams.setdefault(lane, [])
         while len(streams) < len(geoms):

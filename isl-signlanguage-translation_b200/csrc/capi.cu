@@ -162,6 +162,7 @@ int islpose_plan_add_conv(islpose_plan* plan, const islpose_conv_desc* d) {
   c.force_bw = d->tile_w;
   c.force_bh = d->tile_h;
   c.pool = d->pool;
+  c.sm_budget = d->sm_budget;
   Op op;
   memset(&op, 0, sizeof(op));
   op.kind = kConv;

@@ -1233,6 +1233,27 @@ int fail(char* err, int errlen, const char* fmt, long long a = 0, long long b = 
   return 1;
 }
 
+// SM count and opt-in shared memory per block of the current device (queried once per device ordinal): grids, wave models
+// and ring depths follow the part the library runs on (a MIG slice or a part with fewer enabled SMs included).
+struct DeviceLimits {
+  int sms;
+  uint32_t smem_optin;
+};
+DeviceLimits device_limits() {
+  static DeviceLimits cache[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  DeviceLimits& l = cache[dev & 63];
+  if (l.sms == 0) {
+    int sms = 0, smem = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    if (cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || smem <= 0) smem = 227 * 1024;
+    l.sms = sms;
+    l.smem_optin = static_cast<uint32_t>(smem);
+  }
+  return l;
+}
+
 }  // namespace
 
 int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
@@ -1253,6 +1274,9 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
 
   ConvArgs& a = out->args;
   memset(out, 0, sizeof(*out));
+  const DeviceLimits lim = device_limits();
+  // SMs this layer may occupy: all of them, or the caller's share when several plans run side by side (latency mode)
+  const int nsm = (d.sm_budget > 0 && d.sm_budget < lim.sms) ? d.sm_budget : lim.sms;
   a.ksize = d.ksize;
   a.pad = (d.ksize - 1) / 2;
   a.cin_k16 = (d.in_c + 15) / 16;
@@ -1284,7 +1308,7 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
         const double fit = 76.0 + 2.8 * h;
         const double per_mma = fit > 100.0 ? fit : 100.0;
         const double tile_const = 6000.0;  // per-tile overhead (cycles)
-        const double cost = static_cast<double>((tiles + 147) / 148) * (kb5 * 4.0 * per_mma + tile_const);
+        const double cost = static_cast<double>((tiles + nsm - 1) / nsm) * (kb5 * 4.0 * per_mma + tile_const);
         if (best < 0 || cost < best) {
           best = cost;
           th = h;
@@ -1308,7 +1332,7 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
     a.tmem_cols = 512;
     a.b_stage_bytes = 128 * 128;
     const uint32_t fixed = 2u * 2048u * a.halo_h + 1024u + 512u;
-    int stages = (d.force_stages > 0 && d.variant == 5) ? d.force_stages : static_cast<int>((227u * 1024u - fixed) / (128u * 128u));
+    int stages = (d.force_stages > 0 && d.variant == 5) ? d.force_stages : static_cast<int>((lim.smem_optin - fixed) / (128u * 128u));
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) return fail(err, errlen, "conv: v5 does not fit shared memory (halo %lld rows)", a.halo_h);
     a.stages = stages;
@@ -1347,7 +1371,7 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return fail(err, errlen, "conv: weight tensor map rejected (CUresult %lld)", r);
     }
-    out->grid = dim3(static_cast<unsigned>(a.work_items < 148 ? a.work_items : 148), 1, 1);
+    out->grid = dim3(static_cast<unsigned>(a.work_items < nsm ? a.work_items : nsm), 1, 1);
     out->flops = 2.0 * d.in_c * d.cout * d.ksize * d.ksize * static_cast<double>(d.H) * d.W * d.N;
     // the opt-in to large dynamic shared memory is per device: one flag per device ordinal
     static bool attr5_dev[64] = {};
@@ -1355,7 +1379,7 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
     cudaGetDevice(&dev5);
     bool& attr5 = attr5_dev[dev5 & 63];
     if (!attr5) {
-      if (cudaFuncSetAttribute(conv_umma_halo_swapped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
+      if (cudaFuncSetAttribute(conv_umma_halo_swapped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(lim.smem_optin)) !=
           cudaSuccess)
         return fail(err, errlen, "conv: cannot raise dynamic shared memory limit");
       attr5 = true;
@@ -1368,7 +1392,7 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   // issue loops, where an MMA cost about 207 + N/2 cycles alone and 192 + N with two CTAs per SM; `epi` is the epilogue.
   const int kblocks = d.ksize * d.ksize * ((d.in_c + 63) / 64);
   auto estimate = [&](long long tiles, int n, double epi) {
-    const double per_mma = tiles <= 148 ? 207.0 + n / 2.0 : 192.0 + n;
+    const double per_mma = tiles <= lim.sms ? 207.0 + n / 2.0 : 192.0 + n;
     return static_cast<double>((tiles + 295) / 296) * (kblocks * 4.0 * per_mma + epi);
   };
   auto best_box = [&](int cap, bool wave_model, int* obw, int* obh) {
@@ -1417,7 +1441,7 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
     // as much): measured ~900 TFLOP/s. N=256 halves the activation traffic per FLOP: measured 1243 TFLOP/s on
     // 3x3 512->512 with a 2-deep ring and two CTAs per SM. Use it whenever the grid still fills the machine.
     if (cout16 <= 128) n_tile = cout16;
-    else n_tile = (cout16 % 256 == 0 && m_tiles * (cout16 / 256) >= 148) ? 256 : 128;
+    else n_tile = (cout16 % 256 == 0 && m_tiles * (cout16 / 256) >= lim.sms) ? 256 : 128;
   }
   if (n_tile % 16 != 0 || n_tile > 256 || n_tile < 16) return fail(err, errlen, "conv: bad channel tile %lld", n_tile);
   const int n_tiles = (cout16 + n_tile - 1) / n_tile;
@@ -1485,7 +1509,7 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   a.stages = stages;
   out->smem_bytes = stages * per_stage + kCtrlBytes + 1024;
   if (variant == 3) out->smem_bytes += (128u * a.halo_w * a.halo_h + 1023u) & ~1023u;
-  if (out->smem_bytes > 227u * 1024u) return fail(err, errlen, "conv: shared memory budget exceeded (%lld B)", out->smem_bytes);
+  if (out->smem_bytes > lim.smem_optin) return fail(err, errlen, "conv: shared memory budget exceeded (%lld B)", out->smem_bytes);
 
   a.out_bf16 = d.out_bf16;
   a.out_pix_stride = d.out_cstride;
@@ -1547,11 +1571,11 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   }
 
   if (variant == 2) {
-    int per_sm = static_cast<int>((226u * 1024u) / out->smem_bytes);  // persistent CTAs that fit on one SM
+    int per_sm = static_cast<int>((lim.smem_optin - 1024u) / out->smem_bytes);  // persistent CTAs that fit on one SM
     if (per_sm * a.tmem_cols > 512) per_sm = 512 / a.tmem_cols;
     if (per_sm > 2) per_sm = 2;  // 320 threads x ~100 registers: two CTAs per SM
     if (per_sm < 1) per_sm = 1;
-    const int slots = 148 * per_sm;
+    const int slots = nsm * per_sm;
     const int ctas = a.work_items < slots ? a.work_items : slots;
     out->grid = dim3(static_cast<unsigned>(ctas), 1, 1);
   } else {
@@ -1564,14 +1588,14 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   cudaGetDevice(&dev);
   bool& attr_set = attr_set_dev[dev & 63];
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(lim.smem_optin));
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv_umma_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      e = cudaFuncSetAttribute(conv_umma_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(lim.smem_optin));
 #ifdef ISLPOSE_BRINGUP_VARIANTS
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv_umma_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      e = cudaFuncSetAttribute(conv_umma_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(lim.smem_optin));
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv_umma_swapped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      e = cudaFuncSetAttribute(conv_umma_swapped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(lim.smem_optin));
 #endif
     if (e != cudaSuccess) return fail(err, errlen, "conv: cannot raise dynamic shared memory limit (%lld)", e);
     attr_set = true;

@@ -57,6 +57,7 @@ struct ConvDesc {
   int msub;     // v2: pixel sub-tiles per work item sharing one weight stage (0 = automatic, 1 or 2)
   int acc_bufs; // v2: TMEM accumulator buffers (0 = automatic, 1 or 2)
   int pool;     // 1: nn.MaxPool2d(2,2) fused behind the activation (v5 only): out_bf16 is the [N,H/2,W/2] pooled buffer
+  int sm_budget;  // SMs the persistent variants may occupy (0 = all): plans that run side by side each get a share
 };
 
 // A fully resolved launch (tensor maps built once, reusable for every replay).

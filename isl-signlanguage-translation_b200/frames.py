@@ -186,7 +186,7 @@ class VideoExtractor(object):
     (extract_features.py:97-101), i.e. outside test mode it never resumes."""
 
     def __init__(self, extractor, transforms_path_parent, dataset_base_path="", model_type=None, batch_size=8, rank=0,
-                 world_size=1, limit=None):
+                 world_size=1, limit=None, hand_boxes=None):
         self.extractor = extractor
         self.transforms_path_parent = transforms_path_parent
         self.dataset_base_path = dataset_base_path
@@ -194,6 +194,7 @@ class VideoExtractor(object):
         self.batch_size = batch_size
         self.rank, self.world_size = rank, world_size
         self.limit = limit
+        self.hand_boxes = hand_boxes   # benchmarks only: fixed [x, y, w, is_left] boxes per frame instead of util.handDetect
         self.stats = {}
 
     def directory(self, filename, transform, label_type, label_expression):
@@ -241,10 +242,10 @@ class VideoExtractor(object):
         def batches():
             for idxs, frames in feeder:
                 order.append(idxs)
-                yield frames, None
+                yield frames, ([self.hand_boxes] * len(idxs) if self.hand_boxes is not None else None)
         rows = []
         ex = self.extractor
-        runner = ex.pipeline(batches()) if hasattr(ex.body, "enqueue") else (ex.batch(list(fr.numpy())) for fr, _ in batches())
+        runner = ex.pipeline(batches()) if hasattr(ex.body, "enqueue") else (ex.batch(list(fr.numpy()), hb) for fr, hb in batches())
         for bi, res in enumerate(runner):
             for idx, (cand, sub, peaks) in zip(order[bi], res):
                 rows.append(self.saveFeature(filename, idx, transform, (cand, sub, peaks), label_type, label_expression, writer))

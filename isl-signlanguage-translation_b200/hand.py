@@ -54,8 +54,13 @@ class Hand(object):
             for ci, g in enumerate(geoms):
                 groups.setdefault((g[si][3], g[si][4]), []).append(ci)
             groups_of.append(groups)
-            for (hp, wp), members in groups.items():
-                self.model.instance(len(members), hp, wp, lane, exact_of=_pow2_at_least(len(members)))
+        # all (scale, shape) groups run side by side on their own streams: a few crops do not fill the device, so every
+        # group keeps to a share of the SMs (PoseNet.share_sms)
+        flat_groups = [(si, hw, members) for si in range(len(self.scale_search)) for hw, members in groups_of[si].items()]
+        shares = self.model.share_sms([(len(m), hw[0], hw[1]) for (_, hw, m) in flat_groups])
+        budget = {(si, hw): b for (si, hw, _), b in zip(flat_groups, shares)}
+        for (si, hw, members) in flat_groups:
+            self.model.instance(len(members), hw[0], hw[1], lane, exact_of=_pow2_at_least(len(members)), sm_budget=budget[(si, hw)])
         streams = self._streams.setdefault(lane, [])
         main = torch.cuda.current_stream()
         timing = self.model.timing
@@ -73,7 +78,8 @@ class Hand(object):
                     streams.append(torch.cuda.Stream(device=self.device))
                 side = streams[used]
                 used += 1
-                inst = self.model.instance(len(members), hp, wp, lane, exact_of=_pow2_at_least(len(members)))
+                inst = self.model.instance(len(members), hp, wp, lane, exact_of=_pow2_at_least(len(members)),
+                                           sm_budget=budget[(si, (hp, wp))])
                 with torch.cuda.stream(side):
                     side.wait_event(fork)
                     for slot, ci in enumerate(members):

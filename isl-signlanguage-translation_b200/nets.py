@@ -209,7 +209,7 @@ class _Instance:
     images of that instance's buffers (NHWC / NCHW batch prefixes are contiguous) and owns no memory of its own - an
     exact-size replay for the cost of a few hundred tensor-map encodings."""
 
-    def __init__(self, net, n, h, w, share=None):
+    def __init__(self, net, n, h, w, share=None, sm_budget=0):
         L = _lib.lib()
         dev = net.device
         self.net = net
@@ -307,6 +307,7 @@ class _Instance:
                 d.out_f32_channels = o.shape[1]
             cfg = net.tuning
             d.n_tile, d.stages = cfg.get("n_tile", 0), cfg.get("stages", 0)
+            d.sm_budget = sm_budget
             _lib.check(L.islpose_plan_add_conv(handle, C.byref(d)), "islpose_plan_add_conv(%s)" % s["layer"])
             self.op_names.append(s["layer"] + ("+pool" if d.pool else ""))
         self.flops = L.islpose_plan_conv_flops(handle)
@@ -468,19 +469,21 @@ class PoseNet(torch.nn.Module):
             self._pack()
         return out
 
-    def instance(self, n, h, w, lane=0, exact_of=None):
+    def instance(self, n, h, w, lane=0, exact_of=None, sm_budget=0):
         """The plan (and its activation buffers) for one input shape. `lane` selects an independent copy, so that
         two batches of the same shape can be in flight at once. exact_of = a batch capacity >= n: the plan for n
-        images runs inside the buffers of the (capacity, h, w, lane) instance instead of allocating its own."""
+        images runs inside the buffers of the (capacity, h, w, lane) instance instead of allocating its own.
+        sm_budget > 0: the plan's persistent kernels keep to that many SMs (share_sms)."""
         if h % 8 or w % 8:
             raise ValueError("network input must be a multiple of 8 in both dimensions, got %dx%d" % (h, w))
-        if exact_of is not None and exact_of != n:
-            key = (n, h, w, lane, exact_of)
+        cap = exact_of if exact_of is not None else n
+        if cap != n or sm_budget:
+            key = (n, h, w, lane, cap, sm_budget)
             inst = self._instances.get(key)
             if inst is None:
-                parent = self.instance(exact_of, h, w, lane)
+                parent = self.instance(cap, h, w, lane)
                 with torch.cuda.device(self.device):
-                    inst = _Instance(self, n, h, w, share=parent)
+                    inst = _Instance(self, n, h, w, share=parent, sm_budget=sm_budget)
                 self._instances[key] = inst
             return inst
         key = (n, h, w, lane)
@@ -490,6 +493,24 @@ class PoseNet(torch.nn.Module):
                 inst = _Instance(self, n, h, w)
             self._instances[key] = inst
         return inst
+
+    def share_sms(self, shapes):
+        """SM budgets for plans that will run side by side, one per (n, h, w) in `shapes` - or all zeros (no limit) when
+        at least one of them fills the device on its own. A layer of a small batch has fewer tiles than the device has
+        SMs, so a plan tuned for itself spreads every layer thinly over all of them (short, narrow MMAs); four such
+        plans on four streams then queue behind each other. With a share each - proportional to its work, at least 4 -
+        they run truly concurrently on fuller tiles (measured on a single C2 frame: 5.0 ms -> see DESIGN.md)."""
+        sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        if len(shapes) < 2:
+            return [0] * len(shapes)
+        tiles = [n * -(-(h // 8) * (w // 8) // 256) for (n, h, w) in shapes]   # 256-pixel tiles on the stride-8 grid
+        if max(tiles) >= sms:
+            return [0] * len(shapes)
+        work = [n * h * w for (n, h, w) in shapes]
+        left = sms - 4 * len(shapes)
+        budgets = [4 + int(left * wk / sum(work)) for wk in work]
+        budgets[work.index(max(work))] += sms - sum(budgets)
+        return budgets
 
     def forward_into(self, data):
         """Runs the plan for `data`'s shape; returns the plan's own float32 output tensors (overwritten by the

@@ -28,6 +28,8 @@ def main():
     ap.add_argument("--model", default="body25", choices=["coco", "body25"])
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--raw", action="store_true", help="a raw .npy dump instead of MJPEG (no decode cost)")
+    ap.add_argument("--hands", type=int, default=2, help="fixed 128-px hand boxes per frame (random-init maps hold no persons "
+                                                         "for util.handDetect); 0 = use handDetect")
     args = ap.parse_args()
     W, H = [int(v) for v in args.size.split("x")]
 
@@ -73,7 +75,8 @@ def main():
     rates = []
     for rep in range(2):   # the first pass builds plans and buffers
         out = os.path.join(work, "out_%d_%d" % (rep, rank))
-        vx = FR.VideoExtractor(ex, out, batch_size=args.batch, rank=rank, world_size=world)
+        boxes = [[(W // (args.hands + 1)) * (k + 1) - 64, H // 2 - 64, 128, k % 2 == 0] for k in range(args.hands)] or None
+        vx = FR.VideoExtractor(ex, out, batch_size=args.batch, rank=rank, world_size=world, hand_boxes=boxes)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -97,8 +100,8 @@ def main():
                 "frames_per_s": fps, "decode_alone_frames_per_s": decode_alone,
                 "decode_share_of_wall_rank0": stats["decode_seconds"] / stats["seconds"],
                 "limiter": "decode" if decode_alone < 1.15 * fps else "GPU (conv)",
-                "note": "one reader thread per rank into pinned buffers; JSON per frame written by a writer thread; "
-                        "handDetect finds no persons on random-init maps, so the hand networks do not run here"}
+                "hand_boxes_per_frame": args.hands,
+                "note": "one reader thread per rank into pinned buffers; JSON per frame written by a writer thread"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
