@@ -246,13 +246,22 @@ class VideoExtractor(object):
         rows = []
         ex = self.extractor
         runner = ex.pipeline(batches()) if hasattr(ex.body, "enqueue") else (ex.batch(list(fr.numpy()), hb) for fr, hb in batches())
+        rows_s = 0.0
         for bi, res in enumerate(runner):
+            t1 = time.perf_counter()
             for idx, (cand, sub, peaks) in zip(order[bi], res):
                 rows.append(self.saveFeature(filename, idx, transform, (cand, sub, peaks), label_type, label_expression, writer))
+            rows_s += time.perf_counter() - t1
+        t1 = time.perf_counter()
         writer.put(None)
         wt.join()
         wall = time.perf_counter() - t0
+        # where the wall time went: the reader thread's decode time (overlaps everything else), the consumer's time
+        # forming rows (feature_record: Python lists of every candidate), the tail spent waiting for the JSON writer, and
+        # the rest = waiting for the GPU pipeline
         self.stats = {"frames": len(rows), "seconds": wall, "frames_per_s": len(rows) / wall if wall > 0 else 0.0,
                       "decode_seconds": feeder.decode_s, "decode_frames_per_s": feeder.frames_decoded / feeder.decode_s
-                      if feeder.decode_s > 0 else None, "block": (feeder.start, feeder.stop)}
+                      if feeder.decode_s > 0 else None, "rows_seconds": rows_s, "writer_tail_seconds": time.perf_counter() - t1,
+                      "pipeline_wait_seconds": max(wall - rows_s - (time.perf_counter() - t1), 0.0),
+                      "block": (feeder.start, feeder.stop)}
         return rows

@@ -26,7 +26,7 @@ def main():
     ap.add_argument("--frames", type=int, default=240)
     ap.add_argument("--size", default="1280x720")
     ap.add_argument("--model", default="body25", choices=["coco", "body25"])
-    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--raw", action="store_true", help="a raw .npy dump instead of MJPEG (no decode cost)")
     ap.add_argument("--hands", type=int, default=2, help="fixed 128-px hand boxes per frame (random-init maps hold no persons "
                                                          "for util.handDetect); 0 = use handDetect")
@@ -98,8 +98,12 @@ def main():
         line = {"tool": "video_loop", "n_gpus": world, "frames": int(n), "size": args.size, "model": args.model,
                 "source": "raw npy" if args.raw else "MJPEG avi via cv2.VideoCapture (%s)" % cv2.__version__,
                 "frames_per_s": fps, "decode_alone_frames_per_s": decode_alone,
-                "decode_share_of_wall_rank0": stats["decode_seconds"] / stats["seconds"],
-                "limiter": "decode" if decode_alone < 1.15 * fps else "GPU (conv)",
+                "rank0_seconds": {k: round(stats[k], 3) for k in ("seconds", "decode_seconds", "rows_seconds",
+                                                                      "writer_tail_seconds", "pipeline_wait_seconds")},
+                "limiter": max((("decode (reader thread)", stats["decode_seconds"]),
+                                ("host rows + JSON (Python; ~%d candidates per frame on random-init maps)" % (
+                                    len(rows[0]["candidate"]) if rows else 0), stats["rows_seconds"] + stats["writer_tail_seconds"]),
+                                ("GPU pipeline", stats["pipeline_wait_seconds"])), key=lambda kv: kv[1])[0],
                 "hand_boxes_per_frame": args.hands,
                 "note": "one reader thread per rank into pinned buffers; JSON per frame written by a writer thread"}
         print(json.dumps(line), flush=True)
