@@ -8,8 +8,9 @@ no collective on the data path; scaling is weak). Workloads (BASELINE.json confi
   C2  coco body + hand, 640x480, scale_search [0.5,1,1.5,2], two fixed hand boxes per frame      (default)
   C3  body25 + hand, 1280x720, same scales, two 128-px hand boxes per frame, batch 32 (configs[2])
   C4  the frame loop of the reference's extract_features*.py on C3-shaped frames: 30-frame clips of host frames, sharded
-      by frame index over the ranks, run through one pipeline like a video, per-frame feature rows, results gathered on
-      rank 0 and merged in frame order inside the timed region (configs[3]); one clip per rank per step
+      by frame index over the ranks, run through one pipeline like a video, per-frame feature rows formed by every rank
+      (as the reference's workers keep their own CSV rows), the per-frame results gathered on rank 0 and merged in frame
+      order inside the timed region (configs[3]); one clip per rank per step
   C5  body25 + hand, 1920x1080, same scales, 40 hand boxes per frame (the multi-person stress shape, configs[4])
 Hand boxes are fixed per workload because random-init weights never produce a person for util.handDetect.
 The JSON line is the headline workload (C2 unless --workload says otherwise); the other workloads are measured in the
@@ -269,15 +270,18 @@ def measure(ctx, wl, B, steps, warmup, chunk=None, headline=False):
             barrier()
             e0.record()
             own = [s * world * B + i for s in range(n_steps) for i in shard_indices(world * B, rank, world)]
-            rows = []
+            rows, results = [], []
             for rs in ex.pipeline(all_batches()):   # the rows of a batch are built while the GPU works on the next one
                 for (c, sb, hp) in rs:
+                    # every worker keeps its own rows, as the reference's workers do (extract_features_mp.py:142-147
+                    # saveFeaturesDict per process); what travels to rank 0 is the extractor's result per frame
                     rows.append(features.feature_record(c, sb, hp, frame_no=own[len(rows)], model_type=mt))
+                    results.append((c, sb, hp))
             if world > 1:
                 gathered = [None] * world if rank == 0 else None
-                dist.gather_object((own, rows), gathered, dst=0)
+                dist.gather_object((own, results), gathered, dst=0)
             else:
-                gathered = [(own, rows)]
+                gathered = [(own, results)]
             if rank == 0:
                 last = [None] * (n_steps * world * B)
                 for idxs, rws in gathered:
@@ -332,8 +336,7 @@ def measure(ctx, wl, B, steps, warmup, chunk=None, headline=False):
     run_steps(lambda s: host_sets[s % len(host_sets)], 2)
     e2e_ms, res = run_steps(lambda s: host_sets[s % len(host_sets)], steps)
     if clips:
-        import pickle
-        out["d2h"] = len(pickle.dumps(res)) if res is not None else 0   # the merged feature rows (rank 0)
+        out["d2h"] = int(sum(c.nbytes + sb.nbytes + sum(p.nbytes for p in hp) for c, sb, hp in res)) // max(steps, 1) if res else 0
     else:
         out["d2h"] = int(sum(c.nbytes + sb.nbytes + sum(p.nbytes for p in hp) for c, sb, hp in res))
     out["h2d"] = B * H * W * 3   # hand crops are cut from the device copy of the frame
@@ -510,6 +513,12 @@ def main():
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
 
+    # exactly ONE line goes to stdout: libraries that print there (NCCL's version banner under torchrun) are sent to
+    # stderr while the measurement runs; the JSON line is written to the real stdout at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
 
@@ -570,7 +579,8 @@ def main():
             else:
                 line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "port",
                                         "sample": "reference arm failed: " + child.stderr[-300:]}
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

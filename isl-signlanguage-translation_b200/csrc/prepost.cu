@@ -5,8 +5,11 @@
 //   sort_peaks        np.nonzero row-major order for the atomically appended peak lists
 #include "prepost.cuh"
 
+#include <cuda.h>
+
 
 #include "cubic.cuh"
+#include "ptx.cuh"
 
 namespace islpose {
 
@@ -307,6 +310,164 @@ resize_accumulate_kernel(const ScaleSet ss, const MidSet ms, int N, int H, int W
   }
 }
 
+// ------------------------------------------------------------------------------------------------ accumulate, TMA-fed
+// The same second stage (bit-identical arithmetic), with the source rows of every (scale, channel) brought into shared
+// memory by TMA instead of per-thread loads. ncu on the kernel above (profiles/r2_ncu_full_other_kernels.txt):
+// `long_scoreboard` is the top stall, 124 registers hold 20 loads in flight per thread, occupancy 25 %, issue-active 52 %,
+// DRAM 11 % - memory latency that a CTA serialised by one barrier per iteration cannot hide. Here one thread issues, two
+// iterations ahead, a cp.async.bulk.tensor of the (rows_cap x cols_cap) window of the up-sampled map that the tile's
+// 32 x 32 outputs can touch (replicate borders = clamped indices, which stay inside the window; what TMA zero-fills beyond
+// the map is never read); the horizontal pass reads its four taps from that window, everything else is as above.
+constexpr int kTmaRing = 3;
+struct ResizeMaps {
+  CUtensorMap m[kMaxScales];  // per scale: (pitch, hc, N * parts) float32, box (cols_cap, rows_cap, 1)
+};
+struct TileWindow {
+  int r_lo, c_lo, nrows;
+};
+
+__global__ void __launch_bounds__(256, 2)
+resize_accumulate_tma_kernel(const __grid_constant__ ResizeMaps tms, const ScaleSet ss, int N, int H, int W, int parts, int q1,
+                             int rows_cap, int cols_cap, double* __restrict__ out) {
+  extern __shared__ __align__(128) uint8_t s_dyn_raw[];
+  __shared__ TileWindow s_win[kMaxScales];
+  __shared__ __align__(8) unsigned long long s_bars[kTmaRing];
+  const uint32_t buf_bytes = (static_cast<uint32_t>(rows_cap) * cols_cap * 4u + 127u) & ~127u;
+  const uint32_t box_bytes = static_cast<uint32_t>(rows_cap) * cols_cap * 4u;
+  // TMA destinations must be 128-byte aligned: align by hand (the launcher adds 128 bytes), as the conv kernels do
+  uint8_t* const s_dyn = s_dyn_raw + ((128u - (ptx::smem_u32(s_dyn_raw) & 127u)) & 127u);
+  const float* const s_src = reinterpret_cast<const float*>(s_dyn);
+  float (*s_t0)[kRT + 1] = reinterpret_cast<float (*)[kRT + 1]>(s_dyn + kTmaRing * buf_bytes);
+  float (*s_t1)[kRT + 1] = s_t0 + rows_cap;
+  const uint32_t src0 = ptx::smem_u32(s_dyn);
+  const uint32_t bar0 = ptx::smem_u32(s_bars);
+
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int x0 = blockIdx.x * kRT;
+  const int x = x0 + tx;
+  const int xc = x < W ? x : W - 1;  // threads beyond the frame compute a valid column and store nothing
+  const int y0 = blockIdx.y * kRT;
+  const int chunks = (parts + kRChunk - 1) / kRChunk;
+  const int n = blockIdx.z / chunks;
+  const int c0 = (blockIdx.z - n * chunks) * kRChunk;
+  const int nch = parts - c0 < kRChunk ? parts - c0 : kRChunk;
+  const int total = ss.count * nch;
+
+  if (threadIdx.x < ss.count) {
+    // the window of this tile in scale s: first tap of the first row / column .. last tap of the last (clamped, monotonic)
+    const ScaleGeom& g = ss.g[threadIdx.x];
+    int a, b;
+    float fdummy;
+    const int y_last = y0 + kRT - 1 < H ? y0 + kRT - 1 : H - 1;
+    cubic_src(y0, g.sy, a, fdummy);
+    cubic_src(y_last, g.sy, b, fdummy);
+    TileWindow w;
+    w.r_lo = clampi(a - 1, 0, g.hc - 1);
+    w.nrows = clampi(b + 2, 0, g.hc - 1) - w.r_lo + 1;
+    cubic_src(x0, g.sx, a, fdummy);
+    w.c_lo = clampi(a - 1, 0, g.wc - 1);
+    s_win[threadIdx.x] = w;
+  }
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < kTmaRing; ++b) ptx::mbar_init(bar0 + 8 * b, 1);
+    ptx::mbar_fence_init();
+  }
+  __syncthreads();
+  auto issue = [&](int itn) {  // thread 0: the window of iteration itn into ring slot itn % kTmaRing
+    const int s2 = itn / nch, i2 = itn - s2 * nch;
+    const uint32_t b = static_cast<uint32_t>(itn % kTmaRing);
+    ptx::mbar_arrive_expect_tx(bar0 + 8 * b, box_bytes);
+    ptx::tma_load_3d(src0 + b * buf_bytes, &tms.m[s2], bar0 + 8 * b, s_win[s2].c_lo, s_win[s2].r_lo, n * parts + c0 + i2);
+  };
+  if (threadIdx.x == 0) {
+    issue(0);
+    if (total > 1) issue(1);
+  }
+
+  double acc[4][kRChunk];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+#pragma unroll
+    for (int i = 0; i < kRChunk; ++i) acc[k][i] = 0.0;
+  }
+  const int C = ss.channels;
+  const long long tail_start = (static_cast<long long>(W) * C) / 4 * 4;
+  const float fS = static_cast<float>(ss.count);
+  const bool pow2 = (ss.count & (ss.count - 1)) == 0;  // v / S in float32 (body.py:80-81): for a power of two v * (1/S) is identical
+  const float rS = 1.0f / fS;
+  int buf = 0;
+  int it = 0;
+  for (int s = 0; s < ss.count; ++s) {
+    const ScaleGeom& g = ss.g[s];
+    const TileWindow win = s_win[s];
+    // this thread's column: stage-2 taps (as offsets into the window) and weights (once per scale)
+    int sx;
+    float fx, wx[4];
+    cubic_src(xc, g.sx, sx, fx);
+    cubic_coeffs(fx, wx);
+    int xo[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) xo[k] = clampi(sx - 1 + k, 0, g.wc - 1) - win.c_lo;
+    // this thread's four rows: weights and offsets into the shared rows
+    float wy[4][4];
+    unsigned ro4[4];  // shared-row index of each of the four taps of this thread's four rows, one byte each (< kRMaxRows)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int y = y0 + ty + 8 * k;
+      const int yc = y < H ? y : H - 1;
+      int sy;
+      float fy;
+      cubic_src(yc, g.sy, sy, fy);
+      cubic_coeffs(fy, wy[k]);
+      ro4[k] = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ro4[k] |= static_cast<unsigned>(clampi(sy - 1 + j, 0, g.hc - 1) - win.r_lo) << (8 * j);
+    }
+    for (int i = 0; i < nch; ++i, ++it) {
+      const int c = c0 + i;
+      const uint32_t slot = static_cast<uint32_t>(it % kTmaRing);
+      ptx::mbar_wait(bar0 + 8 * slot, static_cast<uint32_t>(it / kTmaRing) & 1u);
+      const float* src = s_src + slot * (buf_bytes / 4);
+      float (*s_t)[kRT + 1] = buf ? s_t1 : s_t0;
+      // horizontal pass: one dot product per (source row, column); rows strided over the 8 warps
+      for (int rb = ty; rb < win.nrows; rb += 8) {
+        const float* row = src + rb * cols_cap;
+        s_t[rb][tx] = dot4_lr(row[xo[0]], row[xo[1]], row[xo[2]], row[xo[3]], wx);
+      }
+      __syncthreads();
+      // every thread is past its reads of the slot iteration it - 1 used: refill it with the window of iteration it + 2
+      if (threadIdx.x == 0 && it + 2 < total) issue(it + 2);
+      const bool tail = static_cast<long long>(xc) * C + c >= tail_start;
+      const float* col = &s_t[0][tx];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float t0 = col[(ro4[k] & 0xffu) * (kRT + 1)], t1 = col[((ro4[k] >> 8) & 0xffu) * (kRT + 1)],
+                    t2 = col[((ro4[k] >> 16) & 0xffu) * (kRT + 1)], t3 = col[(ro4[k] >> 24) * (kRT + 1)];
+        const float v = tail ? dot4_lr(t0, t1, t2, t3, wy[k]) : dot4_rl(t0, t1, t2, t3, wy[k]);
+        const double t = static_cast<double>(pow2 ? __fmul_rn(v, rS) : __fdiv_rn(v, fS));
+        // acc is indexed by a loop variable that is not unrolled: select the accumulator without dynamic indexing
+#pragma unroll
+        for (int q = 0; q < kRChunk; ++q) {
+          if (q == i) acc[k][q] = q1 ? __dadd_rn(acc[k][q], __dadd_rn(acc[k][q], t)) : __dadd_rn(acc[k][q], t);
+        }
+      }
+      buf ^= 1;  // the next horizontal pass writes the other buffer: one barrier per (scale, channel)
+    }
+  }
+  if (x < W) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int y = y0 + ty + 8 * k;
+      if (y < H) {
+#pragma unroll
+        for (int i = 0; i < kRChunk; ++i) {
+          if (i < nch) out[((static_cast<long long>(n) * parts + c0 + i) * H + y) * W + x] = acc[k][i];
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ gaussian + NMS
 // body.py:88-107 on every (frame, part) plane: gauss.cuh's sliding-window filter, then the 4-neighbour NMS against
 // zero-filled borders and the threshold; peaks are appended to the plane's list (sorted afterwards).
@@ -390,6 +551,21 @@ sort_peaks_kernel(int cap, int* __restrict__ counts, uint32_t* __restrict__ keys
 // ------------------------------------------------------------------------------------------------ launchers
 #define ISL_LAUNCH_OK() (cudaGetLastError() == cudaSuccess ? 0 : 1)
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
 int launch_resize_pad_norm(const uint8_t* frames, int N, int H, int W, double scale, int rh, int rw, int hp, int wp,
                            float* out_nchw, uint8_t* out_u8, cudaStream_t st) {
   const dim3 block(32, 8);
@@ -438,6 +614,41 @@ int launch_heat_accumulate(const ScaleSet& ss, int N, int H, int W, int parts, i
   const int rchunks = (parts + kRChunk - 1) / kRChunk;
   const dim3 g2((W + kRT - 1) / kRT, (H + kRT - 1) / kRT, N * rchunks);
   const size_t smem = sizeof(float) * 2 * rows_cap * (kRT + 1);
+  // TMA-fed second stage when the windows fit a TMA box (<= 256 per dimension) and the driver entry point is there
+  int cols_cap = 8;
+  for (int s = 0; s < ss.count; ++s) {
+    const int need = (static_cast<int>(32.0 * ss.g[s].wc / W) + 6 + 3) / 4 * 4;  // multiple of 4 floats = 16 bytes
+    if (need > cols_cap) cols_cap = need;
+  }
+  EncodeTiledFn encode = get_encode_tiled();
+  const size_t ring = kTmaRing * ((static_cast<size_t>(rows_cap) * cols_cap * 4 + 127) & ~static_cast<size_t>(127));
+  if (encode != nullptr && cols_cap <= 256 && rows_cap <= 255 && ring + smem <= 160 * 1024) {
+    ResizeMaps tms;
+    bool ok = true;
+    for (int s = 0; s < ss.count && ok; ++s) {
+      const ScaleGeom& g = ss.g[s];
+      cuuint64_t gdim[3] = {static_cast<cuuint64_t>(ms.pitch[s]), static_cast<cuuint64_t>(g.hc), static_cast<cuuint64_t>(N) * parts};
+      cuuint64_t gstr[2] = {static_cast<cuuint64_t>(ms.pitch[s]) * 4, static_cast<cuuint64_t>(ms.pitch[s]) * 4 * g.hc};
+      cuuint32_t box[3] = {static_cast<cuuint32_t>(cols_cap), static_cast<cuuint32_t>(rows_cap), 1};
+      cuuint32_t estr[3] = {1, 1, 1};
+      ok = encode(&tms.m[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ms.mid[s]), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
+    if (ok) {
+      static bool attr_dev[64] = {};
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (!attr_dev[dev & 63]) {
+        ok = cudaFuncSetAttribute(resize_accumulate_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) == cudaSuccess;
+        attr_dev[dev & 63] = ok;
+      }
+    }
+    if (ok) {
+      resize_accumulate_tma_kernel<<<g2, 256, ring + smem + 128, st>>>(tms, ss, N, H, W, parts, q1, rows_cap, cols_cap, out);
+      return ISL_LAUNCH_OK();
+    }
+  }
   resize_accumulate_kernel<<<g2, 256, smem, st>>>(ss, ms, N, H, W, parts, q1, rows_cap, out);
   return ISL_LAUNCH_OK();
 }
