@@ -622,7 +622,10 @@ int launch_heat_accumulate(const ScaleSet& ss, int N, int H, int W, int parts, i
   }
   EncodeTiledFn encode = get_encode_tiled();
   const size_t ring = kTmaRing * ((static_cast<size_t>(rows_cap) * cols_cap * 4 + 127) & ~static_cast<size_t>(127));
-  if (encode != nullptr && cols_cap <= 256 && rows_cap <= 255 && ring + smem <= 160 * 1024) {
+#ifndef ISLPOSE_ACC_TMA
+  encode = nullptr;  // bring-up: the TMA-fed kernel faults on the device (gpurun_out/r2g_acc_plain.txt); the plain-load kernel is the product path
+#endif
+  if (encode != nullptr && cols_cap <= 256 && rows_cap <= 255 && ring + smem + 128 <= 160 * 1024) {
     ResizeMaps tms;
     bool ok = true;
     for (int s = 0; s < ss.count && ok; ++s) {
