@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define ISLPOSE_ABI_VERSION 2
+#define ISLPOSE_ABI_VERSION 3
 #define ISLPOSE_MAX_SCALES 8
 
 int islpose_abi_version(void);
@@ -170,6 +170,18 @@ int islpose_body_features(const double* candidate, const double* subset, const i
                           int32_t max_person, int32_t model_kind, double* features, void* stream);
 int islpose_hand_features(const int32_t* table, const int32_t* hand_xy, int32_t n_hands, int32_t n_frames, double* features,
                           void* stream);
+
+/* The sign classifier applied to windows of feature rows: the Keras Sequential of demo_isl_translate.py:72-99
+ * (Masking(0) -> BatchNorm -> BiLSTM(32, sequences) -> BiLSTM(32) -> ELU -> Dense(32) -> BN -> ELU -> Dense(32) -> BN -> ELU ->
+ * Dense(classes, softmax)) as ISLSignPosTranslator.call applies it (src/ISL_Model_parameter.py:353), inference, float32.
+ * windows: float64 [n][T][156] (rows as islpose_body_features / islpose_hand_features leave them; all-zero rows are masked
+ * steps), T <= 32. weights: `translation_model.get_weights()` concatenated in that order as float32 - BatchNorm (gamma, beta,
+ * moving_mean, moving_variance), per LSTM layer forward then backward (kernel [in][128], recurrent_kernel [32][128], bias [128];
+ * gate order i, f, c, o), Dense kernels [in][out], the last Dense's bias - islpose_translate_weight_floats(classes) floats.
+ * probs: float32 [n][classes]. One launch. */
+int64_t islpose_translate_weight_floats(int32_t classes);
+int islpose_translate(const double* windows, int32_t n, int32_t T, int32_t n_features, const float* weights, int64_t n_weights,
+                      int32_t classes, float* probs, void* stream);
 
 /* Hand key points (src/hand.py:51-74), batched over crops of any sizes: per crop and scale both cubic stages and the
  * float64 mean over the scales (hand.py:51-56), gaussian sigma=3, threshold, 8-connected labelling, the component with the

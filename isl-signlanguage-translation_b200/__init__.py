@@ -14,3 +14,4 @@ from ._lib import IslposeError, configure  # noqa: F401
 from .body import Body  # noqa: F401
 from .hand import Hand  # noqa: F401
 from .nets import PoseNet  # noqa: F401
+from .translate import RollingTranslator, Translator  # noqa: F401

@@ -34,7 +34,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libislpose.so")
 
 MAX_SCALES = 8
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class ConvDesc(C.Structure):
@@ -95,6 +95,9 @@ SYMBOLS = {
     "islpose_body_features": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                         C.c_void_p]),
     "islpose_hand_features": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "islpose_translate_weight_floats": (C.c_int64, [C.c_int32]),
+    "islpose_translate": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
+                                    C.c_void_p]),
     "islpose_hand_workspace_bytes": (C.c_int64, [C.POINTER(HandCrop), C.c_int32]),
     "islpose_hand_keypoints": (C.c_int, [C.POINTER(HandCrop), C.c_int32, C.c_int32, C.POINTER(C.c_double), C.c_double,
                                          C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),

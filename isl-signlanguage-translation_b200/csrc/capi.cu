@@ -418,6 +418,23 @@ int islpose_hand_features(const int32_t* table, const int32_t* hand_xy, int32_t 
   return 0;
 }
 
+int64_t islpose_translate_weight_floats(int32_t classes) { return classes > 0 ? translate_weight_floats(classes) : 0; }
+
+int islpose_translate(const double* windows, int32_t n, int32_t T, int32_t n_features, const float* weights, int64_t n_weights,
+                      int32_t classes, float* probs, void* stream) {
+  if (n == 0) return 0;
+  if (windows == nullptr || weights == nullptr || probs == nullptr || n < 0) return set_err("translate: bad argument");
+  if (n_features != 156) return set_err("translate: rows have 156 features (ISL_Model_parameter.py:376-410), got %d", n_features);
+  if (T <= 0 || T > 32) return set_err("translate: window length must be in 1..32, got %d", T);
+  if (classes <= 0 || classes > 4096) return set_err("translate: classes must be in 1..4096, got %d", classes);
+  if (n_weights != translate_weight_floats(classes))
+    return set_err("translate: %d classes need %lld weight floats", classes, static_cast<long long>(translate_weight_floats(classes)));
+  if (launch_translate(windows, n, T, weights, n_weights, classes, probs, static_cast<cudaStream_t>(stream)) != 0)
+    return check_cuda("translate") ? 1 : set_err("translate: launch failed");
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
 static int fill_gauss(const double* h_gauss, GaussWeights* gw) {
   if (h_gauss == nullptr) return set_err("hand: null gaussian weights");
   memcpy(gw->w, h_gauss, sizeof(gw->w));

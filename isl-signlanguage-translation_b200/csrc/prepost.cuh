@@ -71,6 +71,12 @@ int launch_body_features(const double* candidate, const double* subset, const in
                          int njoint, double* out, cudaStream_t st);
 int launch_hand_features(const int* table, const int* xy, int n_hands, int n_frames, double* out, cudaStream_t st);
 
+// translate.cu: the sign classifier (demo_isl_translate.py:72-99) on n windows of T x 156 float64 feature rows; weights = the
+// Keras model's get_weights() arrays concatenated, float32; probs float32 [n][classes]
+long long translate_weight_floats(int classes);
+int launch_translate(const double* windows, int n, int T, const float* weights, long long n_weights, int classes, float* probs,
+                     cudaStream_t st);
+
 // hand.cu: key points of up to kHandMaxCrops crops (of any sizes) per launch chain
 constexpr int kHandMaxCrops = 32;
 constexpr int kHandMaxScales = 4;  // hand.py:25 fixes the list at four scales

@@ -28,7 +28,7 @@ def test_header_symbols_are_exported_and_bound():
     for n in names:
         assert hasattr(handle, n), "libislpose.so does not export %s" % n
     assert sorted(_lib.SYMBOLS) == names, "ctypes table and header disagree"
-    assert _lib.lib().islpose_abi_version() == _lib.ABI_VERSION == 2
+    assert _lib.lib().islpose_abi_version() == _lib.ABI_VERSION == 3
 
 
 def test_struct_sizes_match_the_header_layout():
