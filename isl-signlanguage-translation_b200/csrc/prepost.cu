@@ -365,7 +365,9 @@ resize_accumulate_tma_kernel(const __grid_constant__ ResizeMaps tms, const Scale
     w.r_lo = clampi(a - 1, 0, g.hc - 1);
     w.nrows = clampi(b + 2, 0, g.hc - 1) - w.r_lo + 1;
     cubic_src(x0, g.sx, a, fdummy);
-    w.c_lo = clampi(a - 1, 0, g.wc - 1);
+    // the innermost TMA coordinate must be 16-byte aligned: an unaligned one is an illegal-instruction fault on sm_100a
+    // (measured with build/tma_probe, profiles/r2_tma_probe.txt), so the window starts at a multiple of four floats
+    w.c_lo = clampi(a - 1, 0, g.wc - 1) & ~3;
     s_win[threadIdx.x] = w;
   }
   if (threadIdx.x == 0) {
@@ -617,14 +619,12 @@ int launch_heat_accumulate(const ScaleSet& ss, int N, int H, int W, int parts, i
   // TMA-fed second stage when the windows fit a TMA box (<= 256 per dimension) and the driver entry point is there
   int cols_cap = 8;
   for (int s = 0; s < ss.count; ++s) {
-    const int need = (static_cast<int>(32.0 * ss.g[s].wc / W) + 6 + 3) / 4 * 4;  // multiple of 4 floats = 16 bytes
+    // 32 * wc / W + 4 taps (+ rounding), + 3 for the window start rounded down to 16 bytes, as a multiple of 4 floats
+    const int need = (static_cast<int>(32.0 * ss.g[s].wc / W) + 6 + 3 + 3) / 4 * 4;
     if (need > cols_cap) cols_cap = need;
   }
   EncodeTiledFn encode = get_encode_tiled();
   const size_t ring = kTmaRing * ((static_cast<size_t>(rows_cap) * cols_cap * 4 + 127) & ~static_cast<size_t>(127));
-#ifndef ISLPOSE_ACC_TMA
-  encode = nullptr;  // bring-up: the TMA-fed kernel faults on the device (gpurun_out/r2g_acc_plain.txt); the plain-load kernel is the product path
-#endif
   if (encode != nullptr && cols_cap <= 256 && rows_cap <= 255 && ring + smem + 128 <= 160 * 1024) {
     ResizeMaps tms;
     bool ok = true;

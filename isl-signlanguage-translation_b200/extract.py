@@ -216,6 +216,13 @@ class KeypointExtractor(object):
             rows = [r for res in self.pipeline(batches, with_features=True) for (_, _, _, r) in res]
         return np.stack(rows) if rows else np.zeros((0, 156))
 
+    def translate(self, frames, translator, batch_size=8):
+        """Clip -> (class index, probability) per frame from the 21st on: the whole of demo_isl_translate.py's loop
+        (:176-197), with every frame's key points extracted once instead of once per window it appears in."""
+        p = translator.sliding(self.features(frames, batch_size)).cpu().numpy()
+        idx = p.argmax(axis=1) if len(p) else np.zeros((0,), np.int64)
+        return [(int(i), float(p[k, i])) for k, i in enumerate(idx)]
+
     def records(self, frames, batch_size=8, first_frame_no=0, **meta):
         """Clip -> list of per-frame feature rows (features.feature_record = extract_features.py's saveFeature dict)."""
         from . import features as F

@@ -94,6 +94,21 @@ class Translator(object):
                                                     self.n_classes, _lib.ptr(probs), _lib.stream_ptr()), "islpose_translate")
         return probs
 
+    def sliding(self, rows, length=WINDOW):
+        """rows: [T,156] feature rows of a clip (numpy or device tensor). Classifies every window of `length` consecutive
+        rows the demo loop would form (demo_isl_translate.py:183-192: rows i-19..i for i >= 20) in one launch; returns the
+        float32 device tensor [max(T - length, 0), classes]."""
+        import torch
+
+        if not torch.is_tensor(rows):
+            rows = torch.from_numpy(np.ascontiguousarray(np.asarray(rows, dtype=np.float64)))
+        r = rows.to(self.device, dtype=torch.float64)
+        n = int(r.shape[0]) - length
+        if n <= 0:
+            return torch.empty((0, self.n_classes), dtype=torch.float32, device=self.device)
+        wins = r.unfold(0, length, 1)[1:].permute(0, 2, 1).contiguous()   # window k = rows k+1 .. k+length
+        return self(wins)
+
     def top(self, window):
         """(class index, probability) per window: demo_isl_translate.py:192-194."""
         p = self(window).cpu().numpy()

@@ -127,6 +127,11 @@ def test_rolling_translator_follows_the_demo_loop():
     for i in range(20, 25):
         ref = O.translate(rows[i - 19:i + 1], w)
         assert got[i][0] == int(ref.argmax()) and abs(got[i][1] - float(ref.max())) < 2e-5
+    # the same windows in one launch
+    p = tr.sliding(rows).cpu().numpy()
+    assert p.shape == (5, N_CLASSES)
+    assert [int(i) for i in p.argmax(1)] == [g[0] for g in got[20:]]
+    assert tr.sliding(rows[:20]).shape[0] == 0
 
 
 @pytest.mark.gpu

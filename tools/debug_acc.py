@@ -1,5 +1,5 @@
 """Bring-up check of the two-pass map accumulation (TMA-fed second stage) against the single-pass kernel.
-usage: python tools/debug_acc.py [H W n]"""
+usage: python tools/debug_acc.py [H W n [library]]"""
 import os
 import sys
 
@@ -15,6 +15,8 @@ def main():
     H, W, n = (int(a) for a in sys.argv[1:4]) if len(sys.argv) >= 4 else (240, 320, 2)
     C, parts = 19, 18
     dev = torch.device("cuda:0")
+    if len(sys.argv) >= 5:
+        _lib.LIB_PATH = os.path.abspath(sys.argv[4])   # a bring-up build of the library
     L = _lib.lib()
     scales = scale_geometry(H, W, [0.5, 1.0, 1.5, 2.0], 368)
     arr = (_lib.Scale * len(scales))()
