@@ -496,6 +496,33 @@ def summarise(m, world, n_sm):
     }
 
 
+def measure_classifier(torch, n_windows=1024, reps=20):
+    """The sign classifier behind the key points (demo_isl_translate.py:72-99): windows of 20 x 156 feature rows
+    per second through isl_b200.Translator, one launch per batch of windows, device-timed; and one window end to end."""
+    from isl_b200 import translate as TR
+    tr = TR.Translator(TR.random_weights(167, seed=0))
+    rng = np.random.RandomState(0)
+    win = torch.from_numpy(rng.uniform(0, 720, (n_windows, 20, 156))).cuda()
+    for _ in range(3):
+        tr(win)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        p = tr(win)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    one = win[:1].cpu().numpy()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        tr.top(one)
+    single_ms = (time.perf_counter() - t0) / 20 * 1e3
+    return {"windows_per_s": n_windows / ms * 1e3, "ms_per_launch": ms, "windows_per_launch": n_windows, "classes": 167,
+            "single_window_host_to_host_ms": single_ms, "weights": "seeded random (the trained model does not ship with the reference)",
+            "probability_sum_check": float(p[0].sum())}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -552,6 +579,8 @@ def main():
             Bo = WORKLOADS[other][4]
             subs.append((other, measure(ctx, other, Bo, args.sub_steps, 3, chunk=chunk_of(other, Bo))))
 
+    classifier = measure_classifier(torch) if rank == 0 else None
+
     if rank == 0:
         mt, H, W, boxes, _ = WORKLOADS[wl]
         line = {"metric": METRIC, "n_gpus": world, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -565,6 +594,7 @@ def main():
                           "pipeline": "steps run through KeypointExtractor.pipeline(): two lanes, the post-processing and copies of "
                                       "one step overlap the convolutions of the next; all K steps start and end inside the timed region",
                           "single_frame_latency_ms": round(head["single_ms"], 2) if head["single_ms"] else None}
+        line["classifier"] = classifier
         line["sub_results"] = []
         for name, m in subs:
             sr = {"config": {"workload": m["workload"]}, "n_gpus": world}

@@ -73,9 +73,13 @@ int islpose_plan_destroy(islpose_plan* plan);
 int islpose_plan_add_conv(islpose_plan* plan, const islpose_conv_desc* desc);
 /* conv1_1 (3 -> 64 channels, 3x3, src/model.py 'conv1_1' of all three networks) in one launch straight from the fp32 NCHW
  * network input: weights bf16 [64][32] with K index (ky*3+kx)*3+c (27 used, 5 zero), bias / slope as in islpose_conv_desc,
- * out bf16 NHWC with out_cstride (>= 64) channels per pixel. */
+ * out bf16 NHWC with out_cstride (>= 64) channels per pixel. relu != 0: the caller states that all 64 slopes are 0 (the
+ * layer is followed by nn.ReLU, as conv1_1 is in the coco and hand networks): the epilogue then converts with ReLU in one
+ * instruction per two channels instead of reading the slopes. The bias enters the GEMM as two bf16 K columns (hi + lo part,
+ * exact to 2^-17 of its value). */
 int islpose_plan_add_first_conv(islpose_plan* plan, const float* in_nchw, const void* weights, const float* bias,
-                                const float* slope, void* out, int32_t out_cstride, int32_t n, int32_t h, int32_t w);
+                                const float* slope, void* out, int32_t out_cstride, int32_t n, int32_t h, int32_t w,
+                                int32_t relu);
 /* Replays the plan on `stream`. The first run records the launches into a CUDA graph (programmatic dependent launch edges
  * included); later runs are one graph launch. islpose_plan_set_graph(plan, 0) keeps kernel-by-kernel launches;
  * islpose_plan_graph_state: 0 = not recorded yet, 1 = graph in use, -1 = recording was not possible (direct launches). */

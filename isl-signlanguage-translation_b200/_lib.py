@@ -75,7 +75,7 @@ SYMBOLS = {
     "islpose_plan_destroy": (C.c_int, [C.c_void_p]),
     "islpose_plan_add_conv": (C.c_int, [C.c_void_p, C.POINTER(ConvDesc)]),
     "islpose_plan_add_first_conv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
-                                            C.c_int32, C.c_int32, C.c_int32]),
+                                            C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "islpose_plan_run": (C.c_int, [C.c_void_p, C.c_void_p]),
     "islpose_plan_set_graph": (C.c_int, [C.c_void_p, C.c_int32]),
     "islpose_plan_graph_state": (C.c_int32, [C.c_void_p]),

@@ -42,6 +42,7 @@ struct Op {
   const void* weights;  // kFirst
   const float* bias;
   const float* slope;
+  bool relu;            // kFirst: every slope is 0
 };
 
 const int kCocoA[19] = {1, 1, 2, 3, 5, 6, 1, 8, 9, 1, 11, 12, 1, 0, 14, 0, 15, 2, 5};
@@ -174,7 +175,8 @@ int islpose_plan_add_conv(islpose_plan* plan, const islpose_conv_desc* d) {
 }
 
 int islpose_plan_add_first_conv(islpose_plan* plan, const float* in_nchw, const void* weights, const float* bias,
-                                const float* slope, void* out, int32_t out_cstride, int32_t n, int32_t h, int32_t w) {
+                                const float* slope, void* out, int32_t out_cstride, int32_t n, int32_t h, int32_t w,
+                                int32_t relu) {
   if (plan == nullptr || in_nchw == nullptr || weights == nullptr || bias == nullptr || slope == nullptr || out == nullptr)
     return set_err("plan_add_first_conv: null argument");
   if (out_cstride < 64 || out_cstride % 8 != 0 || (reinterpret_cast<uintptr_t>(out) & 15) != 0 ||
@@ -192,6 +194,7 @@ int islpose_plan_add_first_conv(islpose_plan* plan, const float* in_nchw, const 
   op.weights = weights;
   op.bias = bias;
   op.slope = slope;
+  op.relu = relu != 0;
   plan->ops.push_back(op);
   plan->flops += 2.0 * 32 * 64 * static_cast<double>(n) * h * w;
   return 0;
@@ -199,7 +202,7 @@ int islpose_plan_add_first_conv(islpose_plan* plan, const float* in_nchw, const 
 
 static int run_op(const Op& op, cudaStream_t st) {
   if (op.kind == kConv) return conv_run(op.conv, st);
-  return launch_conv_first(static_cast<const float*>(op.in), op.n, op.h, op.w, op.weights, op.bias, op.slope, op.out, op.c, st);
+  return launch_conv_first(static_cast<const float*>(op.in), op.n, op.h, op.w, op.weights, op.bias, op.slope, op.out, op.c, op.relu, st);
 }
 
 int islpose_plan_set_graph(islpose_plan* plan, int32_t enable) {

@@ -168,8 +168,10 @@ __host__ __device__ inline size_t match_smem_bytes(int cap) {
   return c * 32 + (c / 32 + 1) * 8;
 }
 
+// mat_pairs: pair scores that fit behind those arrays; a limb's nA x nB matrix that fits is copied there once, so that the
+// rounds (two scans of the whole matrix each) read shared memory instead of L2.
 __global__ void __launch_bounds__(256)
-match_kernel(const LimbTable lt, const GroupBuffers gb) {
+match_kernel(const LimbTable lt, const GroupBuffers gb, int mat_pairs) {
   extern __shared__ double s_match[];
   const int kcap = pow2_at_least(gb.cap);
   double* const s_rowv = s_match;                 // [cap] best free partner's score per row
@@ -196,6 +198,11 @@ match_kernel(const LimbTable lt, const GroupBuffers gb) {
     return;
   }
   const double* sc = gb.pair_score + static_cast<long long>(slot) * gb.pair_cap;
+  if (nA * nB <= mat_pairs) {
+    double* s_mat = s_match + match_smem_bytes(gb.cap) / sizeof(double);
+    for (int i = threadIdx.x; i < nA * nB; i += blockDim.x) s_mat[i] = sc[i];
+    sc = s_mat;
+  }
   for (int i = threadIdx.x; i < kcap / 32 + 1; i += blockDim.x) {
     s_usedA[i] = 0;
     s_usedB[i] = 0;
@@ -485,17 +492,24 @@ int launch_paf_score(const ScaleSet& paf, const LimbTable& lt, int N, int H, int
 int launch_group(const LimbTable& lt, int N, int W, const GroupBuffers& gb, cudaStream_t st) {
   if (gb.cap > kMaxPeakCap || lt.njoint + 1 > 32) return 1;
   const size_t smem = match_smem_bytes(gb.cap);
-  if (smem > 48 * 1024) {  // opt in to large dynamic shared memory once per device
+  // behind the per-peak arrays: room for a limb's pair-score matrix, at most 96 KB and what the 227 KB of an SM leave
+  const size_t limit = 220 * 1024;
+  if (smem > limit) return 1;
+  long long mat_ll = static_cast<long long>((limit - smem) / 8);
+  if (mat_ll > 12288) mat_ll = 12288;
+  if (mat_ll > gb.pair_cap) mat_ll = gb.pair_cap;
+  const int mat_pairs = static_cast<int>(mat_ll);
+  {  // opt in to large dynamic shared memory once per device
     static bool done[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (!done[dev & 63]) {
-      if (cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(match_smem_bytes(kMaxPeakCap))) != cudaSuccess)
+      if (cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(limit)) != cudaSuccess)
         return 1;
       done[dev & 63] = true;
     }
   }
-  match_kernel<<<dim3(lt.nlimbs, N), 256, smem, st>>>(lt, gb);
+  match_kernel<<<dim3(lt.nlimbs, N), 256, smem + static_cast<size_t>(mat_pairs) * 8, st>>>(lt, gb, mat_pairs);
   assemble_kernel<<<N, 256, 0, st>>>(lt, W, gb);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }

@@ -20,8 +20,9 @@ int launch_resize_pad_norm(const uint8_t* frames, int N, int H, int W, double sc
                            float* out_nchw, uint8_t* out_u8, cudaStream_t st);
 // conv_first.cu: conv1_1 (3 -> 64, 3x3) straight from the float32 NCHW network input; weights bf16 [64][32] with K index
 // (ky*3+kx)*3+c (27 used), out bf16 NHWC with out_cstride channels per pixel
+// relu: every slope is 0 (the caller has looked): the epilogue is then one convert-with-ReLU per two channels
 int launch_conv_first(const float* in, int N, int h, int w, const void* weights, const float* bias, const float* slope,
-                      void* out, int out_cstride, cudaStream_t st);
+                      void* out, int out_cstride, bool relu, cudaStream_t st);
 long long heat_accumulate_workspace_floats(const ScaleSet& ss, int N, int parts);
 int launch_heat_accumulate(const ScaleSet& ss, int N, int H, int W, int parts, int q1, double* out, float* workspace,
                            long long workspace_floats, cudaStream_t st);

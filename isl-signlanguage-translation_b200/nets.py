@@ -274,7 +274,8 @@ class _Instance:
                 db = self.bufs[s["dst"][0]]
                 _lib.check(L.islpose_plan_add_first_conv(handle, _lib.ptr(self.input), _lib.ptr(wt), _lib.ptr(bias),
                                                          _lib.ptr(slope), C.c_void_p(db.data_ptr() + 2 * s["dst"][1]),
-                                                         db.shape[3], n, h, w), "islpose_plan_add_first_conv")
+                                                         db.shape[3], n, h, w, 1 if s["act"] == RELU else 0),
+                           "islpose_plan_add_first_conv")
                 self.op_names.append(s["layer"])
                 continue
             sb = self.bufs[s["src"][0]]

@@ -31,6 +31,25 @@ def weight_shapes(n_classes, n_features=N_FEATURES, units=UNITS, hidden=32):
     return s
 
 
+def random_weights(n_classes, seed=0):
+    """Seeded stand-in for `translation_model.get_weights()` (the trained model does not ship with the reference): uniform
+    kernels, BatchNorm statistics in the range of pixel coordinates. For benchmarks and smoke runs."""
+    rng = np.random.RandomState(seed)
+    out = []
+    for i, shp in enumerate(weight_shapes(n_classes)):
+        if len(shp) == 2:
+            lim = np.sqrt(6.0 / (shp[0] + shp[1]))
+            w = rng.uniform(-lim, lim, shp)
+        elif i == 2:
+            w = rng.uniform(0.0, 300.0, shp)        # moving_mean of the input normalisation
+        elif i == 3:
+            w = rng.uniform(2000.0, 20000.0, shp)   # moving_variance of the input normalisation
+        else:
+            w = rng.uniform(0.2, 1.2, shp)
+        out.append(w.astype(np.float32))
+    return out
+
+
 def load_weights(source):
     """list of arrays | .npz written by np.savez(path, *get_weights()) | .npy of the concatenation -> list of float32 arrays
     or one flat float32 array."""
