@@ -58,6 +58,20 @@ typedef struct islpose_conv_desc {
   int32_t sm_budget;    /* SMs the layer's persistent kernel may occupy, 0 = all. Plans that run side by side on several
                            streams (the scales of one small batch) finish sooner when each keeps to a share of the device
                            than when every layer of every plan asks for all of it */
+  /* A second 1x1 layer chained behind this 1x1 layer in the same launch (Mconv6 -> Mconv7, conv5_4 -> conv5_5, conv6_1 ->
+   * conv6_2: src/model.py:57-62 builds them as consecutive nn.Conv2d(k=1)). weights2 != NULL selects it: this layer's cout
+   * (64..512, a multiple of 64) activations of a pixel tile stay in shared memory, rounded to bf16 as the stored
+   * activation would be, and out_bf16 / out_f32 must be NULL; the fields below are the second layer's. */
+  const void* weights2; /* bf16 [1][cout2][cout] */
+  int32_t cout2;        /* 1..64 */
+  const float* bias2;   /* fp32, at least 64 entries, zero padded */
+  const float* slope2;
+  void* out2_bf16;      /* bf16 NHWC slice (may be NULL): cout2 rounded up to 8 channels, pad = 0 */
+  int32_t out2_cstride;
+  void* out2b_bf16;     /* the same slice once more in another buffer (may be NULL) */
+  int32_t out2b_cstride;
+  float* out2_f32;      /* fp32 planar NCHW (may be NULL) */
+  int32_t out2_f32_channels;
 } islpose_conv_desc;
 
 /* Weight ingestion (src/body.py:35-36, src/util.py:35-44): one nn.Conv2d weight, float32 [cout][cin][k][k] on the device,

@@ -43,7 +43,10 @@ class ConvDesc(C.Structure):
                 ("w", C.c_int32), ("weights", C.c_void_p), ("cout", C.c_int32), ("ksize", C.c_int32),
                 ("bias", C.c_void_p), ("slope", C.c_void_p), ("out_bf16", C.c_void_p), ("out_cstride", C.c_int32),
                 ("out_f32", C.c_void_p), ("out_f32_channels", C.c_int32), ("n_tile", C.c_int32), ("stages", C.c_int32),
-                ("tile_w", C.c_int32), ("tile_h", C.c_int32), ("pool", C.c_int32), ("sm_budget", C.c_int32)]
+                ("tile_w", C.c_int32), ("tile_h", C.c_int32), ("pool", C.c_int32), ("sm_budget", C.c_int32),
+                ("weights2", C.c_void_p), ("cout2", C.c_int32), ("bias2", C.c_void_p), ("slope2", C.c_void_p),
+                ("out2_bf16", C.c_void_p), ("out2_cstride", C.c_int32), ("out2b_bf16", C.c_void_p), ("out2b_cstride", C.c_int32),
+                ("out2_f32", C.c_void_p), ("out2_f32_channels", C.c_int32)]
 
 
 class Scale(C.Structure):

@@ -164,6 +164,16 @@ int islpose_plan_add_conv(islpose_plan* plan, const islpose_conv_desc* d) {
   c.force_bh = d->tile_h;
   c.pool = d->pool;
   c.sm_budget = d->sm_budget;
+  c.w2 = static_cast<const __nv_bfloat16*>(d->weights2);
+  c.cout2 = d->cout2;
+  c.bias2 = d->bias2;
+  c.slope2 = d->slope2;
+  c.out2_bf16 = static_cast<__nv_bfloat16*>(d->out2_bf16);
+  c.out2_cstride = d->out2_cstride;
+  c.out2b_bf16 = static_cast<__nv_bfloat16*>(d->out2b_bf16);
+  c.out2b_cstride = d->out2b_cstride;
+  c.out2_f32 = d->out2_f32;
+  c.out2_f32_channels = d->out2_f32_channels;
   Op op;
   memset(&op, 0, sizeof(op));
   op.kind = kConv;

@@ -1208,6 +1208,266 @@ conv_umma_halo_swapped_kernel(const __grid_constant__ CUtensorMap tmX, const __g
   }
 }
 
+// ------------------------------------------------------------------------------------------------ v6: 1x1 -> 1x1 pair
+// Two chained 1x1 layers in one launch (Mconv6 -> Mconv7, conv5_4 -> conv5_5, conv6_1 -> conv6_2 of the reference's stages,
+// src/model.py:57-62): a 1x1 layer is bound by moving its operands, and the pair moved the 128..512-channel intermediate
+// out to L2 / HBM and back in again. Here a CTA owns one 128-pixel tile:
+//   1. first layer as in v1 (TMA ring, M = 128 pixels, N = all `mid` output channels: one or two N <= 256 MMAs per K step,
+//      accumulators in `mid` TMEM columns);
+//   2. its epilogue (bias, ReLU / PReLU, bf16) writes the tile into the now idle operand ring as mid/64 blocks of
+//      [128 pixels][64 channels] in the 128-byte-swizzled K-major layout - exactly the A operand of the second layer;
+//      meanwhile the second layer's weights (64 rows, zero-filled beyond cout2) arrive behind them by TMA;
+//   3. second layer: mid/64 x 4 MMAs of N = 64 into TMEM columns 0..63 (drained in step 2), then its own epilogue: bias,
+//      activation, bf16 slice(s) and / or float32 planar output.
+// The intermediate is rounded to bf16 exactly as the stored activation was, so results equal the two separate launches.
+constexpr uint32_t kPairW2Block = 64 * 128;   // 64 weight rows x 64 channels
+constexpr uint32_t kPairCtrlBytes = 256 + 2 * 512 * 4 + 2 * 64 * 4;  // barriers, bias / slope of layer 1 (<= 512), of layer 2
+
+__global__ void __launch_bounds__(kThreadsV1, 1)
+conv_umma_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ CUtensorMap tmB2, const ConvArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* const gbase = smem_raw + (base - raw);
+
+  const uint32_t sA0 = base;
+  const uint32_t sB0 = base + a.stages * kASlotBytes;
+  const uint32_t sI0 = base;                                   // intermediate blocks (over the idle ring)
+  const uint32_t sW2 = base + a.mid_blocks * kASlotBytes;      // second layer's weight blocks
+  const uint32_t ctrl = base + a.pair_ctrl_off;
+  uint8_t* const gctrl = gbase + a.pair_ctrl_off;
+  const uint32_t bar_full = ctrl;          // kMaxStages x 8 B
+  const uint32_t bar_empty = ctrl + 64;    // kMaxStages x 8 B
+  const uint32_t bar_accum = ctrl + 128;   // first layer's accumulators complete (and the ring idle)
+  const uint32_t tmem_slot = ctrl + 136;
+  const uint32_t bar_mid = ctrl + 144;     // intermediate written by the eight epilogue warps
+  const uint32_t bar_w2 = ctrl + 152;      // second layer's weights landed
+  const uint32_t bar_accum2 = ctrl + 160;  // second layer's accumulator complete
+  volatile uint32_t* const tmem_slot_g = reinterpret_cast<volatile uint32_t*>(gctrl + 136);
+  float* const s_bias = reinterpret_cast<float*>(gctrl + 256);
+  float* const s_slope = s_bias + 512;
+  float* const s_bias2 = s_slope + 512;
+  float* const s_slope2 = s_bias2 + 64;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int t = blockIdx.x;
+  const int tx = t % a.tiles_x;
+  const int ty = (t / a.tiles_x) % a.tiles_y;
+  const int img = t / (a.tiles_x * a.tiles_y);
+  const int x0 = tx * a.bw;
+  const int y0 = ty * a.bh;
+  const int cblocks = (a.cin_k16 + 3) >> 2;
+  const int mid = a.mid_blocks * 64;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < a.stages; ++s) {
+      ptx::mbar_init(bar_full + 8 * s, 1);
+      ptx::mbar_init(bar_empty + 8 * s, 1);
+    }
+    ptx::mbar_init(bar_accum, 1);
+    ptx::mbar_init(bar_mid, 8);  // one arrival per epilogue warp
+    ptx::mbar_init(bar_w2, 1);
+    ptx::mbar_init(bar_accum2, 1);
+    ptx::mbar_fence_init();
+    ptx::prefetch_tensormap(&tmA);
+    ptx::prefetch_tensormap(&tmB);
+    ptx::prefetch_tensormap(&tmB2);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, a.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  if (warp >= 2) {
+    for (int i = threadIdx.x - 64; i < mid; i += kThreadsV1 - 64) {
+      s_bias[i] = a.bias[i];
+      s_slope[i] = a.slope[i];
+    }
+    if (threadIdx.x - 64 < 64) {
+      s_bias2[threadIdx.x - 64] = a.bias2[threadIdx.x - 64];
+      s_slope2[threadIdx.x - 64] = a.slope2[threadIdx.x - 64];
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_g;
+  ptx::pdl_launch_dependents();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    ptx::pdl_wait();
+    const uint32_t tx_bytes = 128u * a.bw * a.bh + 128u * static_cast<uint32_t>(mid);
+    ptx::RingPos r(bar_full, bar_empty, a.stages);
+    uint32_t sa = sA0, sb = sB0;
+    for (int cb = 0; cb < cblocks; ++cb) {
+      ptx::mbar_wait(r.empty, r.ph ^ 1);
+      if (ptx::elect_one()) {
+        ptx::mbar_arrive_expect_tx(r.full, tx_bytes);
+        ptx::tma_load_4d(sa, &tmA, r.full, cb * 64, x0, y0, img);
+        for (int p = 0; p < a.n1_parts; ++p)
+          ptx::tma_load_3d(sb + static_cast<uint32_t>(p * a.n1_mma) * 128u, &tmB, r.full, cb * 64, p * a.n1_mma, 0);
+      }
+      __syncwarp();
+      sa += kASlotBytes;
+      sb += a.b_stage_bytes;
+      if (r.advance()) {
+        sa = sA0;
+        sb = sB0;
+      }
+    }
+    // the ring is idle once every MMA of the first layer has retired: the second layer's weights go behind the
+    // intermediate blocks (they may overlap ring slots)
+    ptx::mbar_wait(bar_accum, 0);
+    if (ptx::elect_one()) {
+      ptx::mbar_arrive_expect_tx(bar_w2, static_cast<uint32_t>(a.mid_blocks) * kPairW2Block);
+      for (int b = 0; b < a.mid_blocks; ++b) ptx::tma_load_3d(sW2 + b * kPairW2Block, &tmB2, bar_w2, b * 64, 0, 0);
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    {
+      const uint32_t idesc = ptx::umma_idesc_bf16(128, a.n1_mma);
+      const int tail_ksteps = a.cin_k16 - (cblocks - 1) * 4;
+      const uint64_t da0 = ptx::umma_desc_sw128(sA0), db0 = ptx::umma_desc_sw128(sB0);
+      const uint32_t a_step = kASlotBytes >> 4, b_step = a.b_stage_bytes >> 4;
+      const uint32_t part_step = (static_cast<uint32_t>(a.n1_mma) * 128u) >> 4;
+      uint64_t da = da0, db = db0;
+      ptx::RingPos r(bar_full, bar_empty, a.stages);
+      for (int cb = 0; cb < cblocks; ++cb) {
+        ptx::mbar_wait(r.full, r.ph);
+        ptx::tc_fence_after();
+        const int ksteps = cb == cblocks - 1 ? tail_ksteps : 4;
+        if (ptx::elect_one()) {
+          for (int p = 0; p < a.n1_parts; ++p)
+            issue_kblock(tmem_base + static_cast<uint32_t>(p * a.n1_mma), da, db + p * part_step, idesc, cb != 0, ksteps);
+          ptx::umma_commit(r.empty);
+        }
+        __syncwarp();
+        da += a_step;
+        db += b_step;
+        if (r.advance()) {
+          da = da0;
+          db = db0;
+        }
+      }
+      if (ptx::elect_one()) ptx::umma_commit(bar_accum);
+      __syncwarp();
+    }
+    // second layer: A = the intermediate blocks, B = its weight blocks, D = TMEM columns 0..63
+    ptx::mbar_wait(bar_mid, 0);
+    ptx::mbar_wait(bar_w2, 0);
+    ptx::tc_fence_after();
+    if (ptx::elect_one()) {
+      const uint32_t idesc2 = ptx::umma_idesc_bf16(128, 64);
+      uint64_t di = ptx::umma_desc_sw128(sI0), dw = ptx::umma_desc_sw128(sW2);
+      for (int b = 0; b < a.mid_blocks; ++b) {
+        issue_kblock4(tmem_base, di, dw, idesc2, b != 0);
+        di += kASlotBytes >> 4;
+        dw += kPairW2Block >> 4;
+      }
+      ptx::umma_commit(bar_accum2);
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------ epilogues
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const int py = row / a.bw;
+    const int px = row - py * a.bw;
+    const int x = x0 + px;
+    const int y = y0 + py;
+    const bool valid = (row < a.bw * a.bh) && (x < a.W) && (y < a.H);
+    const long long pix = (static_cast<long long>(img) * a.H + y) * a.W + x;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+
+    ptx::mbar_wait(bar_accum, 0);
+    ptx::tc_fence_after();
+    for (int c = half * 32; c < mid; c += 64) {
+      uint32_t r[32];
+      ptx::tmem_ld_32x32(lane_base + c, r);
+      ptx::tmem_ld_wait();
+      const uint32_t blk = sI0 + static_cast<uint32_t>(c >> 6) * kASlotBytes + static_cast<uint32_t>(row) * 128u;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i = 8 * j + 2 * e;
+          float v0 = __uint_as_float(r[i]) + s_bias[c + i];
+          float v1 = __uint_as_float(r[i + 1]) + s_bias[c + i + 1];
+          v0 = v0 > 0.f ? v0 : v0 * s_slope[c + i];
+          v1 = v1 > 0.f ? v1 : v1 * s_slope[c + i + 1];
+          const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+          pk[e] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        const uint32_t chunk = static_cast<uint32_t>(((c & 63) >> 3) + j);
+        const uint32_t addr = blk + ((chunk ^ (static_cast<uint32_t>(row) & 7u)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+      }
+    }
+    ptx::fence_proxy_async_smem();  // generic-proxy writes -> the tensor core's async proxy
+    ptx::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(bar_mid);
+
+    ptx::mbar_wait(bar_accum2, 0);
+    ptx::tc_fence_after();
+    {
+      const int c = half * 32;
+      uint32_t r[32];
+      ptx::tmem_ld_32x32(lane_base + c, r);
+      ptx::tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float acc = __uint_as_float(r[i]) + s_bias2[c + i];
+        v[i] = acc > 0.f ? acc : acc * s_slope2[c + i];
+      }
+      if (valid) {
+#pragma unroll
+        for (int dsti = 0; dsti < 2; ++dsti) {
+          __nv_bfloat16* const ob = dsti ? a.out2b_bf16 : a.out2_bf16;
+          if (ob == nullptr) continue;
+          __nv_bfloat16* dst = ob + pix * (dsti ? a.out2b_pix_stride : a.out2_pix_stride) + c;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (c + 8 * j < a.cout2_store) {
+              uint4 pk;
+              __nv_bfloat162 h;
+              h = __floats2bfloat162_rn(v[8 * j + 0], v[8 * j + 1]);
+              pk.x = *reinterpret_cast<uint32_t*>(&h);
+              h = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+              pk.y = *reinterpret_cast<uint32_t*>(&h);
+              h = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
+              pk.z = *reinterpret_cast<uint32_t*>(&h);
+              h = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+              pk.w = *reinterpret_cast<uint32_t*>(&h);
+              *reinterpret_cast<uint4*>(dst + 8 * j) = pk;
+            }
+          }
+        }
+        if (a.out2_f32 != nullptr) {
+          const long long plane = static_cast<long long>(a.H) * a.W;
+          float* dst = a.out2_f32 + (static_cast<long long>(img) * a.out2_f32_channels + c) * plane + static_cast<long long>(y) * a.W + x;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (c + i < a.cout2) dst[i * plane] = v[i];
+          }
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tmem_dealloc(tmem_base, a.tmem_cols);
+  }
+}
+
 // ------------------------------------------------------------------ host side
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -1267,7 +1527,7 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   if (d.out_bf16 != nullptr &&
       ((reinterpret_cast<uintptr_t>(d.out_bf16) & 15) != 0 || d.out_cstride % 8 != 0))
     return fail(err, errlen, "conv: bf16 output slice must be 16-byte aligned (stride %lld)", d.out_cstride);
-  if (d.out_bf16 == nullptr && d.out_f32 == nullptr) return fail(err, errlen, "conv: no output given");
+  if (d.out_bf16 == nullptr && d.out_f32 == nullptr && d.w2 == nullptr) return fail(err, errlen, "conv: no output given");
   if (d.N <= 0 || d.H <= 0 || d.W <= 0 || d.cout <= 0) return fail(err, errlen, "conv: empty problem");
   EncodeTiledFn encode = get_encode_tiled();
   if (encode == nullptr) return fail(err, errlen, "conv: cuTensorMapEncodeTiled entry point not found");
@@ -1431,6 +1691,101 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
   a.tiles_x = (d.W + bw - 1) / bw;
   a.tiles_y = (d.H + bh - 1) / bh;
   const long long m_tiles = static_cast<long long>(a.tiles_x) * a.tiles_y * d.N;
+
+  if (d.w2 != nullptr) {
+    // ---- variant 6: this 1x1 layer and the 1x1 layer behind it in one launch (see the kernel)
+    if (d.ksize != 1) return fail(err, errlen, "conv: a chained pair needs two 1x1 layers");
+    if (d.cout % 64 != 0 || d.cout < 64 || d.cout > 512) return fail(err, errlen, "conv: pair: first layer must have 64..512 output channels in 64s, got %lld", d.cout);
+    if (d.cout2 < 1 || d.cout2 > 64) return fail(err, errlen, "conv: pair: second layer must have 1..64 output channels, got %lld", d.cout2);
+    if (d.out_bf16 != nullptr || d.out_f32 != nullptr) return fail(err, errlen, "conv: pair: the intermediate is not stored");
+    if (d.out2_bf16 == nullptr && d.out2_f32 == nullptr) return fail(err, errlen, "conv: pair: no output given");
+    if (d.bias2 == nullptr || d.slope2 == nullptr) return fail(err, errlen, "conv: pair: null bias / slope");
+    if ((reinterpret_cast<uintptr_t>(d.w2) & 15) != 0) return fail(err, errlen, "conv: pair: weights must be 16-byte aligned");
+    if (d.out2_bf16 != nullptr && ((reinterpret_cast<uintptr_t>(d.out2_bf16) & 15) != 0 || d.out2_cstride % 8 != 0))
+      return fail(err, errlen, "conv: pair: bf16 output slice must be 16-byte aligned (stride %lld)", d.out2_cstride);
+    if (d.out2b_bf16 != nullptr && ((reinterpret_cast<uintptr_t>(d.out2b_bf16) & 15) != 0 || d.out2b_cstride % 8 != 0))
+      return fail(err, errlen, "conv: pair: second bf16 output slice must be 16-byte aligned (stride %lld)", d.out2b_cstride);
+    const int cblocks6 = (a.cin_k16 + 3) / 4;
+    a.n_tile = d.cout;
+    a.n_tiles = 1;
+    a.cout = d.cout;
+    a.cout_store = d.cout;
+    a.n1_mma = d.cout < 256 ? d.cout : 256;
+    a.n1_parts = d.cout / a.n1_mma;
+    a.mid_blocks = d.cout / 64;
+    a.b_stage_bytes = static_cast<uint32_t>(d.cout) * 128u;
+    int cols6 = 64;
+    while (cols6 < d.cout) cols6 <<= 1;
+    a.tmem_cols = cols6;
+    a.stages = d.force_stages > 0 ? d.force_stages : (cblocks6 < 2 ? 1 : 2);
+    if (a.stages > kMaxStages) a.stages = kMaxStages;
+    const uint32_t ring = static_cast<uint32_t>(a.stages) * (kASlotBytes + a.b_stage_bytes);
+    const uint32_t chain = static_cast<uint32_t>(a.mid_blocks) * (kASlotBytes + kPairW2Block);
+    a.pair_ctrl_off = ring > chain ? ring : chain;
+    out->smem_bytes = a.pair_ctrl_off + kPairCtrlBytes + 1024u;
+    if (out->smem_bytes > lim.smem_optin) return fail(err, errlen, "conv: pair: shared memory budget exceeded (%lld B)", out->smem_bytes);
+    a.m_tiles = static_cast<int>(m_tiles);
+    a.work_items = a.m_tiles;
+    a.bias = d.bias;
+    a.slope = d.slope;
+    a.cout2 = d.cout2;
+    a.cout2_store = (d.cout2 + 7) / 8 * 8;
+    a.bias2 = d.bias2;
+    a.slope2 = d.slope2;
+    a.out2_bf16 = d.out2_bf16;
+    a.out2_pix_stride = d.out2_cstride;
+    a.out2b_bf16 = d.out2b_bf16;
+    a.out2b_pix_stride = d.out2b_cstride;
+    a.out2_f32 = d.out2_f32;
+    a.out2_f32_channels = d.out2_f32_channels;
+    {
+      int c_dim = d.in_c;
+      const int c64 = (d.in_c + 63) / 64 * 64;
+      if (d.in_c_readable >= c64) c_dim = c64;
+      cuuint64_t gdim[4] = {static_cast<cuuint64_t>(c_dim), static_cast<cuuint64_t>(d.W), static_cast<cuuint64_t>(d.H),
+                            static_cast<cuuint64_t>(d.N)};
+      cuuint64_t gstr[3] = {static_cast<cuuint64_t>(d.in_cstride) * 2, static_cast<cuuint64_t>(d.in_cstride) * 2 * d.W,
+                            static_cast<cuuint64_t>(d.in_cstride) * 2 * d.W * d.H};
+      cuuint32_t box[4] = {64, static_cast<cuuint32_t>(bw), static_cast<cuuint32_t>(bh), 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      if (encode(&out->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(d.in), gdim, gstr, box, estr,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return fail(err, errlen, "conv: pair: activation tensor map rejected");
+    }
+    {
+      const int w_cin = d.w_cin > 0 ? d.w_cin : d.in_c;
+      if (w_cin < d.in_c || w_cin % 8 != 0) return fail(err, errlen, "conv: bad weight Cin stride %lld", w_cin);
+      cuuint64_t gdim[3] = {static_cast<cuuint64_t>(w_cin), static_cast<cuuint64_t>(d.cout), 1};
+      cuuint64_t gstr[2] = {static_cast<cuuint64_t>(w_cin) * 2, static_cast<cuuint64_t>(w_cin) * 2 * d.cout};
+      cuuint32_t box[3] = {64, static_cast<cuuint32_t>(a.n1_mma), 1};
+      cuuint32_t estr[3] = {1, 1, 1};
+      if (encode(&out->tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(d.w), gdim, gstr, box, estr,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return fail(err, errlen, "conv: pair: weight tensor map rejected");
+      cuuint64_t gdim2[3] = {static_cast<cuuint64_t>(d.cout), static_cast<cuuint64_t>(d.cout2), 1};
+      cuuint64_t gstr2[2] = {static_cast<cuuint64_t>(d.cout) * 2, static_cast<cuuint64_t>(d.cout) * 2 * d.cout2};
+      cuuint32_t box2[3] = {64, 64, 1};
+      if (encode(&out->tmB2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(d.w2), gdim2, gstr2, box2, estr,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return fail(err, errlen, "conv: pair: second weight tensor map rejected");
+    }
+    out->variant = 6;
+    out->grid = dim3(static_cast<unsigned>(m_tiles), 1, 1);
+    const double px = static_cast<double>(d.H) * d.W * d.N;
+    out->flops = 2.0 * d.in_c * d.cout * px + 2.0 * d.cout * d.cout2 * px;
+    static bool attr6_dev[64] = {};
+    int dev6 = 0;
+    cudaGetDevice(&dev6);
+    if (!attr6_dev[dev6 & 63]) {
+      if (cudaFuncSetAttribute(conv_umma_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(lim.smem_optin)) != cudaSuccess)
+        return fail(err, errlen, "conv: cannot raise dynamic shared memory limit");
+      attr6_dev[dev6 & 63] = true;
+    }
+    return 0;
+  }
 
   // Channel tile (UMMA N): multiple of 16, at most 256. 128 keeps a stage at 32 KB so that two CTAs fit on one SM
   // with a 3-deep ring each: the second CTA's main loop hides the first one's epilogue and pipeline fill.
@@ -1625,6 +1980,7 @@ static int launch_pdl(void (*kernel)(KArgs...), dim3 grid, int threads, uint32_t
 int conv_run(const ConvLaunch& l, cudaStream_t stream) {
   if (l.variant == 2) return launch_pdl(conv_umma_persistent_kernel, l.grid, kThreadsV1, l.smem_bytes, stream, l.tmA, l.tmB, l.args);
   if (l.variant == 5) return launch_pdl(conv_umma_halo_swapped_kernel, l.grid, kThreadsV1, l.smem_bytes, stream, l.tmA, l.tmB, l.args);
+  if (l.variant == 6) return launch_pdl(conv_umma_pair_kernel, l.grid, kThreadsV1, l.smem_bytes, stream, l.tmA, l.tmB, l.tmB2, l.args);
 #ifdef ISLPOSE_BRINGUP_VARIANTS
   if (l.variant == 3) {
     conv_umma_halo_kernel<<<l.grid, kThreads, l.smem_bytes, stream>>>(l.tmA, l.tmB, l.args);

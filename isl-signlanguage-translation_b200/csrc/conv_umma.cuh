@@ -58,6 +58,19 @@ struct ConvDesc {
   int acc_bufs; // v2: TMEM accumulator buffers (0 = automatic, 1 or 2)
   int pool;     // 1: nn.MaxPool2d(2,2) fused behind the activation (v5 only): out_bf16 is the [N,H/2,W/2] pooled buffer
   int sm_budget;  // SMs the persistent variants may occupy (0 = all): plans that run side by side each get a share
+  // A second 1x1 layer chained behind this 1x1 layer in the same launch (variant 6; w2 != nullptr): this layer's cout
+  // (64..512, multiple of 64) activations of a pixel tile stay in shared memory as the second layer's A operand and are
+  // never written (out_bf16 / out_f32 must be null); the outputs below are the second layer's.
+  const __nv_bfloat16* w2;  // [1][cout2][cout]
+  int cout2;                // 1..64
+  const float* bias2;
+  const float* slope2;
+  __nv_bfloat16* out2_bf16;   // may be null
+  int out2_cstride;
+  __nv_bfloat16* out2b_bf16;  // a second copy of the same slice in another buffer (may be null)
+  int out2b_cstride;
+  float* out2_f32;            // planar NCHW, may be null
+  int out2_f32_channels;
 };
 
 // A fully resolved launch (tensor maps built once, reusable for every replay).
@@ -93,12 +106,26 @@ struct ConvArgs {
   int out_f32_channels;
   const float* bias;
   const float* slope;
+  // 1x1 pair (variant 6)
+  int n1_mma, n1_parts;   // the first layer's N per MMA (<= 256) and MMAs per K step
+  int mid_blocks;         // 64-channel blocks of the intermediate
+  uint32_t pair_ctrl_off; // control block offset from the 1024-aligned base
+  int cout2, cout2_store;
+  const float* bias2;
+  const float* slope2;
+  __nv_bfloat16* out2_bf16;
+  long long out2_pix_stride;
+  __nv_bfloat16* out2b_bf16;
+  long long out2b_pix_stride;
+  float* out2_f32;
+  int out2_f32_channels;
 };
 
 struct ConvLaunch {
   alignas(64) CUtensorMap tmA;
   alignas(64) CUtensorMap tmB;
   alignas(64) CUtensorMap tmC;  // v4: bf16 output slice, written with TMA stores
+  alignas(64) CUtensorMap tmB2; // v6: the second layer's weights
   ConvArgs args;
   dim3 grid;
   uint32_t smem_bytes;

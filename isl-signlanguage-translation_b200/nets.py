@@ -223,6 +223,48 @@ class _Instance:
             return (nxt is not None and nxt[0] == "pool" and s["dst"] is not None and nxt[1] == s["dst"][0]
                     and s["k"] >= 3 and s["src"][2] >= 64 and s["cout"] >= 48 and s["f32"] is None and not s["first"])
 
+        def pair_followers(si):
+            """1x1 conv step si whose output only feeds the 1x1 layer right behind it (Mconv6 -> Mconv7, conv5_4 -> conv5_5,
+            conv6_1 -> conv6_2; body25 writes one Mconv7 into two buffers = two steps of the same layer): the step indices
+            of that layer, which then runs in the same launch (csrc/conv_umma.cu, variant 6), else []."""
+            s = steps[si][1]
+            if not net.tuning.get("pair", True) or steps[si][0] != "conv" or s["first"] or s["k"] != 1 or s["dst"] is None:
+                return []
+            if s["f32"] is not None or s["cout"] % 64 != 0 or not 64 <= s["cout"] <= 512 or s["dst"][1] != 0:
+                return []
+            want = (s["dst"][0], 0, s["cout"])
+            out = []
+            sj = si + 1
+            while sj < len(steps) and steps[sj][0] == "conv":
+                t = steps[sj][1]
+                if not (t["k"] == 1 and tuple(t["src"]) == want and t["cout"] <= 64 and (not out or t["layer"] == steps[out[0]][1]["layer"])):
+                    break
+                out.append(sj)
+                sj += 1
+            if not out or len(out) > 2 or sum(steps[j][1]["f32"] is not None for j in out) > 1:
+                return []
+            if sum(steps[j][1]["dst"] is not None for j in out) == 0 and all(steps[j][1]["f32"] is None for j in out):
+                return []
+            # nobody else may read the intermediate before it is written again
+            for sk in range(sj, len(steps)):
+                if steps[sk][0] != "conv":
+                    continue
+                u = steps[sk][1]
+                if not u["first"] and u["src"][0] == want[0]:
+                    return []
+                if u["dst"] is not None and u["dst"][0] == want[0]:
+                    break
+            return out
+
+        pairs = {si: pair_followers(si) for si in range(len(steps)) if steps[si][0] == "conv"}
+        pairs = {si: f for si, f in pairs.items() if f}
+        paired = {j for f in pairs.values() for j in f}
+        packed_index, ci_ = {}, 0
+        for si, step in enumerate(steps):
+            if step[0] == "conv":
+                packed_index[si] = ci_
+                ci_ += 1
+
         if share is not None:
             if share.h != h or share.w != w or share.n < n or share.net is not net:
                 raise ValueError("cannot share buffers of a %dx%dx%d instance for %dx%dx%d" % (share.n, share.h, share.w, n, h, w))
@@ -239,11 +281,11 @@ class _Instance:
             for si, step in enumerate(steps):
                 if step[0] == "conv":
                     s = step[1]
-                    if not s["first"]:
+                    if not s["first"] and si not in paired:
                         used.add(s["src"][0])
                     if pool_fusable(si):
                         used.add(steps[si + 1][2])
-                    elif s["dst"] is not None:
+                    elif s["dst"] is not None and si not in pairs:   # a pair's intermediate stays in shared memory
                         used.add(s["dst"][0])
             for name, (ch, level) in net.program.bufs.items():
                 if name not in used:
@@ -256,7 +298,6 @@ class _Instance:
         handle = C.c_void_p()
         _lib.check(L.islpose_plan_create(C.byref(handle)), "islpose_plan_create")
         self.handle = handle
-        ci = 0
         fused_pools = set()
         self.op_names = []   # one name per recorded launch (tools/layer_times.py)
         for si, step in enumerate(steps):
@@ -267,8 +308,9 @@ class _Instance:
                     raise _lib.IslposeError("max-pool after %r cannot be fused into its producer" % (steps[si - 1],))
                 continue   # done in the epilogue of the layer before it
             s = step[1]
-            wt, bias, slope = net.packed[ci]
-            ci += 1
+            if si in paired:
+                continue   # runs inside the launch of the 1x1 layer before it
+            wt, bias, slope = net.packed[packed_index[si]]
             if s["first"]:
                 # conv1_1 in one launch straight from the float32 network input (csrc/conv_first.cu)
                 db = self.bufs[s["dst"][0]]
@@ -298,6 +340,23 @@ class _Instance:
                 d.out_cstride = db.shape[3]
                 d.pool = 1
                 fused_pools.add(si + 1)
+            elif si in pairs:
+                # this 1x1 layer and the 1x1 layer behind it in one launch; the outputs are the second layer's
+                fol = [steps[j][1] for j in pairs[si]]
+                wt2, bias2, slope2 = net.packed[packed_index[pairs[si][0]]]
+                d.weights2, d.cout2 = wt2.data_ptr(), wt2.shape[1]
+                d.bias2, d.slope2 = bias2.data_ptr(), slope2.data_ptr()
+                dsts = [t["dst"] for t in fol if t["dst"] is not None]
+                if dsts:
+                    db = self.bufs[dsts[0][0]]
+                    d.out2_bf16, d.out2_cstride = db.data_ptr() + 2 * dsts[0][1], db.shape[3]
+                if len(dsts) > 1:
+                    db = self.bufs[dsts[1][0]]
+                    d.out2b_bf16, d.out2b_cstride = db.data_ptr() + 2 * dsts[1][1], db.shape[3]
+                for t in fol:
+                    if t["f32"] is not None:
+                        o = self.outputs[t["f32"]]
+                        d.out2_f32, d.out2_f32_channels = o.data_ptr(), o.shape[1]
             elif s["dst"] is not None:
                 db = self.bufs[s["dst"][0]]
                 d.out_bf16 = db.data_ptr() + 2 * s["dst"][1]
@@ -310,7 +369,7 @@ class _Instance:
             d.n_tile, d.stages = cfg.get("n_tile", 0), cfg.get("stages", 0)
             d.sm_budget = sm_budget
             _lib.check(L.islpose_plan_add_conv(handle, C.byref(d)), "islpose_plan_add_conv(%s)" % s["layer"])
-            self.op_names.append(s["layer"] + ("+pool" if d.pool else ""))
+            self.op_names.append(s["layer"] + ("+pool" if d.pool else "") + ("+" + steps[pairs[si][0]][1]["layer"] if si in pairs else ""))
         self.flops = L.islpose_plan_conv_flops(handle)
         self.launches = L.islpose_plan_num_launches(handle)
         if not net.tuning.get("graph", True):

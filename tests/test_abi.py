@@ -34,7 +34,7 @@ def test_header_symbols_are_exported_and_bound():
 def test_struct_sizes_match_the_header_layout():
     # LP64: pointers 8 bytes, int32 4 bytes, natural alignment - the same rules the C compiler applies
     assert ctypes.sizeof(_lib.Scale) == 24
-    assert ctypes.sizeof(_lib.ConvDesc) == 128
+    assert ctypes.sizeof(_lib.ConvDesc) == 208
     assert ctypes.sizeof(_lib.GroupBuffers) % 8 == 0
     assert ctypes.sizeof(_lib.HandCrop) == 8 + 4 * 24
 
