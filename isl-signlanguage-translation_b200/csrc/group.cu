@@ -156,7 +156,7 @@ paf_score_kernel(const ScaleSet ss, const LimbTable lt, int H, int W, int parts,
 // accepting it blocks exactly the pairs the sequential walk would skip.) The walk stops at min(nA, nB) connections,
 // which is also when no free row or no free column is left. Accepted connections are finally sorted into the
 // order the walk would have produced them in, because the person assembly consumes them in that order.
-// Dynamic shared memory, sized by the peak capacity (match_smem_bytes): 32.25 bytes per peak slot.
+// Dynamic shared memory, sized by the peak capacity (match_smem_bytes): 32.25 bytes per peak slot, plus the work area.
 // Array lengths are the capacity rounded up to a power of two (the final bitonic sort pads to one).
 __host__ __device__ inline int pow2_at_least(int v) {
   int p = 32;
@@ -168,10 +168,13 @@ __host__ __device__ inline size_t match_smem_bytes(int cap) {
   return c * 32 + (c / 32 + 1) * 8;
 }
 
-// mat_pairs: pair scores that fit behind those arrays; a limb's nA x nB matrix that fits is copied there once, so that the
-// rounds (two scans of the whole matrix each) read shared memory instead of L2.
+// Behind those arrays sits the work area (`work_bytes`): on noisy maps a limb has a few ten thousand candidate pairs of
+// which a few thousand carry a positive score, and only those can ever be accepted. They are compacted once into a list
+// (score, i, j) in shared memory and the rounds run over the list - three passes of a few entries per thread (row / column
+// maxima by 64-bit atomicMax on the score bits, ties to the smallest index by atomicMin, then the mutual-best test) instead
+// of two scans of the whole nA x nB matrix in L2 per round. When the list does not fit, the dense rounds below run.
 __global__ void __launch_bounds__(256)
-match_kernel(const LimbTable lt, const GroupBuffers gb, int mat_pairs) {
+match_kernel(const LimbTable lt, const GroupBuffers gb, int work_bytes) {
   extern __shared__ double s_match[];
   const int kcap = pow2_at_least(gb.cap);
   double* const s_rowv = s_match;                 // [cap] best free partner's score per row
@@ -182,7 +185,7 @@ match_kernel(const LimbTable lt, const GroupBuffers gb, int mat_pairs) {
   int* const s_cj = s_ci + kcap;
   uint32_t* const s_usedA = reinterpret_cast<uint32_t*>(s_cj + kcap);
   uint32_t* const s_usedB = s_usedA + (kcap / 32 + 1);
-  __shared__ int s_made, s_round;
+  __shared__ int s_made, s_round, s_nent;
   const int k = blockIdx.x, n = blockIdx.y;
   const int parts = lt.njoint - 1;
   const int slot = n * lt.nlimbs + k;
@@ -198,18 +201,98 @@ match_kernel(const LimbTable lt, const GroupBuffers gb, int mat_pairs) {
     return;
   }
   const double* sc = gb.pair_score + static_cast<long long>(slot) * gb.pair_cap;
-  if (nA * nB <= mat_pairs) {
-    double* s_mat = s_match + match_smem_bytes(gb.cap) / sizeof(double);
-    for (int i = threadIdx.x; i < nA * nB; i += blockDim.x) s_mat[i] = sc[i];
-    sc = s_mat;
-  }
   for (int i = threadIdx.x; i < kcap / 32 + 1; i += blockDim.x) {
     s_usedA[i] = 0;
     s_usedB[i] = 0;
   }
-  if (threadIdx.x == 0) s_made = 0;
+  if (threadIdx.x == 0) {
+    s_made = 0;
+    s_nent = 0;
+  }
   __syncthreads();
 
+  // ---- work area: column maxima [kcap] (64-bit), then the list: score bits [list_cap], (i << 16 | j) [list_cap]
+  unsigned long long* const s_colmax = reinterpret_cast<unsigned long long*>(s_match + match_smem_bytes(gb.cap) / sizeof(double));
+  unsigned long long* const s_rowmax = reinterpret_cast<unsigned long long*>(s_rowv);
+  const int list_cap = (work_bytes - kcap * 8) / 12;
+  unsigned long long* const s_ev = s_colmax + kcap;
+  uint32_t* const s_eij = reinterpret_cast<uint32_t*>(s_ev + (list_cap > 0 ? list_cap : 0));
+  bool listed = list_cap > 0 && nA <= 65535 && nB <= 65535;
+  if (listed) {
+    const int total = nA * nB;
+    for (int base = 0; base < total; base += blockDim.x) {
+      const int idx = base + threadIdx.x;
+      const double v = idx < total ? sc[idx] : -1.0;
+      const bool pos = v > 0.0;
+      const unsigned m = __ballot_sync(0xffffffffu, pos);
+      int wbase = 0;
+      if (lane == 0 && m != 0) wbase = atomicAdd(&s_nent, __popc(m));
+      wbase = __shfl_sync(0xffffffffu, wbase, 0);
+      if (pos) {
+        const int at = wbase + __popc(m & ((1u << lane) - 1u));
+        if (at < list_cap) {
+          const int i = idx / nB;
+          s_ev[at] = static_cast<unsigned long long>(__double_as_longlong(v));  // positive doubles order like their bits
+          s_eij[at] = (static_cast<uint32_t>(i) << 16) | static_cast<uint32_t>(idx - i * nB);
+        }
+      }
+    }
+    __syncthreads();
+    listed = s_nent <= list_cap;
+  }
+  if (listed) {
+    const int nent = s_nent;
+    while (true) {
+      for (int i = threadIdx.x; i < nA; i += blockDim.x) {
+        s_rowmax[i] = 0ull;
+        s_rowj[i] = 0x7fffffff;
+      }
+      for (int j = threadIdx.x; j < nB; j += blockDim.x) {
+        s_colmax[j] = 0ull;
+        s_coli[j] = 0x7fffffff;
+      }
+      if (threadIdx.x == 0) s_round = 0;
+      __syncthreads();
+      for (int e = threadIdx.x; e < nent; e += blockDim.x) {  // best free score of every row and column
+        const int i = s_eij[e] >> 16, j = s_eij[e] & 0xffffu;
+        if (((s_usedA[i >> 5] >> (i & 31)) | (s_usedB[j >> 5] >> (j & 31))) & 1u) continue;
+        atomicMax(&s_rowmax[i], s_ev[e]);
+        atomicMax(&s_colmax[j], s_ev[e]);
+      }
+      __syncthreads();
+      for (int e = threadIdx.x; e < nent; e += blockDim.x) {  // ties: the smallest j of a row, the smallest i of a column
+        const int i = s_eij[e] >> 16, j = s_eij[e] & 0xffffu;
+        if (((s_usedA[i >> 5] >> (i & 31)) | (s_usedB[j >> 5] >> (j & 31))) & 1u) continue;
+        if (s_ev[e] == s_rowmax[i]) atomicMin(&s_rowj[i], j);
+        if (s_ev[e] == s_colmax[j]) atomicMin(&s_coli[j], i);
+      }
+      __syncthreads();
+      for (int e = threadIdx.x; e < nent; e += blockDim.x) {  // a pair that is the best of its row and of its column
+        const int i = s_eij[e] >> 16, j = s_eij[e] & 0xffffu;
+        if (s_ev[e] == s_rowmax[i] && s_rowj[i] == j && s_ev[e] == s_colmax[j] && s_coli[j] == i &&
+            !(((s_usedA[i >> 5] >> (i & 31)) | (s_usedB[j >> 5] >> (j & 31))) & 1u)) {
+          const int pos = atomicAdd(&s_made, 1);
+          s_ci[pos] = i;
+          s_cj[pos] = j;
+          s_round = 1;
+        }
+      }
+      __syncthreads();
+      // the accepted pairs of this round: mark their ends used (after the pass, so that it saw one state of the flags)
+      const int made_now = s_made;
+      const bool any = s_round != 0;
+      __syncthreads();
+      if (!any) break;
+      for (int c = threadIdx.x; c < made_now; c += blockDim.x) {
+        atomicOr(&s_usedA[s_ci[c] >> 5], 1u << (s_ci[c] & 31));
+        atomicOr(&s_usedB[s_cj[c] >> 5], 1u << (s_cj[c] & 31));
+      }
+      __syncthreads();
+    }
+    // scores of the accepted pairs (the row maxima array doubles as s_rowv and is dead now)
+    for (int c = threadIdx.x; c < s_made; c += blockDim.x) s_cv[c] = sc[static_cast<long long>(s_ci[c]) * nB + s_cj[c]];
+    __syncthreads();
+  } else
   while (true) {
     // best free column of every free row (one warp per row, lanes across columns: coalesced)
     for (int i = warp; i < nA; i += 8) {
@@ -492,13 +575,14 @@ int launch_paf_score(const ScaleSet& paf, const LimbTable& lt, int N, int H, int
 int launch_group(const LimbTable& lt, int N, int W, const GroupBuffers& gb, cudaStream_t st) {
   if (gb.cap > kMaxPeakCap || lt.njoint + 1 > 32) return 1;
   const size_t smem = match_smem_bytes(gb.cap);
-  // behind the per-peak arrays: room for a limb's pair-score matrix, at most 96 KB and what the 227 KB of an SM leave
+  // behind the per-peak arrays: the work area of the list-based rounds (column maxima + up to 12288 listed pairs), as far
+  // as the 227 KB of an SM allow
   const size_t limit = 220 * 1024;
   if (smem > limit) return 1;
-  long long mat_ll = static_cast<long long>((limit - smem) / 8);
-  if (mat_ll > 12288) mat_ll = 12288;
-  if (mat_ll > gb.pair_cap) mat_ll = gb.pair_cap;
-  const int mat_pairs = static_cast<int>(mat_ll);
+  const size_t kcap = static_cast<size_t>(pow2_at_least(gb.cap));
+  size_t work = kcap * 8 + 12 * 12288;
+  if (work > limit - smem) work = limit - smem;
+  const int work_bytes = static_cast<int>(work / 8 * 8);
   {  // opt in to large dynamic shared memory once per device
     static bool done[64] = {};
     int dev = 0;
@@ -509,7 +593,7 @@ int launch_group(const LimbTable& lt, int N, int W, const GroupBuffers& gb, cuda
       done[dev & 63] = true;
     }
   }
-  match_kernel<<<dim3(lt.nlimbs, N), 256, smem + static_cast<size_t>(mat_pairs) * 8, st>>>(lt, gb, mat_pairs);
+  match_kernel<<<dim3(lt.nlimbs, N), 256, smem + static_cast<size_t>(work_bytes), st>>>(lt, gb, work_bytes);
   assemble_kernel<<<N, 256, 0, st>>>(lt, W, gb);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
