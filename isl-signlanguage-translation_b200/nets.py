@@ -202,6 +202,48 @@ def _up64(c):
     return (c + 63) // 64 * 64
 
 
+def pair_followers(steps, si):
+    """1x1 conv step si whose output only feeds the 1x1 layer right behind it (Mconv6 -> Mconv7, conv5_4 -> conv5_5,
+    conv6_1 -> conv6_2; body25 writes one Mconv7 into two buffers = two steps of the same layer): the step indices of that
+    layer, which then runs in the same launch (csrc/conv_umma.cu, variant 6), else []."""
+    s = steps[si][1]
+    if steps[si][0] != "conv" or s["first"] or s["k"] != 1 or s["dst"] is None:
+        return []
+    if s["f32"] is not None or s["cout"] % 64 != 0 or not 64 <= s["cout"] <= 512 or s["dst"][1] != 0:
+        return []
+    want = (s["dst"][0], 0, s["cout"])
+    out = []
+    sj = si + 1
+    while sj < len(steps) and steps[sj][0] == "conv":
+        t = steps[sj][1]
+        if not (t["k"] == 1 and tuple(t["src"]) == want and t["cout"] <= 64 and (not out or t["layer"] == steps[out[0]][1]["layer"])):
+            break
+        out.append(sj)
+        sj += 1
+    if not out or len(out) > 2 or sum(steps[j][1]["f32"] is not None for j in out) > 1:
+        return []
+    if sum(steps[j][1]["dst"] is not None for j in out) == 0 and all(steps[j][1]["f32"] is None for j in out):
+        return []
+    # nobody else may read the intermediate before it is written again
+    for sk in range(sj, len(steps)):
+        if steps[sk][0] != "conv":
+            continue
+        u = steps[sk][1]
+        if not u["first"] and u["src"][0] == want[0]:
+            return []
+        if u["dst"] is not None and u["dst"][0] == want[0]:
+            break
+    return out
+
+
+def find_pairs(steps, enabled=True):
+    """{index of the first layer of a chained 1x1 pair: [indices of the second layer's steps]}."""
+    if not enabled:
+        return {}
+    pairs = {si: pair_followers(steps, si) for si in range(len(steps)) if steps[si][0] == "conv"}
+    return {si: f for si, f in pairs.items() if f}
+
+
 class _Instance:
     """One (batch, h, w) instantiation: device buffers + the C launch plan.
 
@@ -223,41 +265,7 @@ class _Instance:
             return (nxt is not None and nxt[0] == "pool" and s["dst"] is not None and nxt[1] == s["dst"][0]
                     and s["k"] >= 3 and s["src"][2] >= 64 and s["cout"] >= 48 and s["f32"] is None and not s["first"])
 
-        def pair_followers(si):
-            """1x1 conv step si whose output only feeds the 1x1 layer right behind it (Mconv6 -> Mconv7, conv5_4 -> conv5_5,
-            conv6_1 -> conv6_2; body25 writes one Mconv7 into two buffers = two steps of the same layer): the step indices
-            of that layer, which then runs in the same launch (csrc/conv_umma.cu, variant 6), else []."""
-            s = steps[si][1]
-            if not net.tuning.get("pair", True) or steps[si][0] != "conv" or s["first"] or s["k"] != 1 or s["dst"] is None:
-                return []
-            if s["f32"] is not None or s["cout"] % 64 != 0 or not 64 <= s["cout"] <= 512 or s["dst"][1] != 0:
-                return []
-            want = (s["dst"][0], 0, s["cout"])
-            out = []
-            sj = si + 1
-            while sj < len(steps) and steps[sj][0] == "conv":
-                t = steps[sj][1]
-                if not (t["k"] == 1 and tuple(t["src"]) == want and t["cout"] <= 64 and (not out or t["layer"] == steps[out[0]][1]["layer"])):
-                    break
-                out.append(sj)
-                sj += 1
-            if not out or len(out) > 2 or sum(steps[j][1]["f32"] is not None for j in out) > 1:
-                return []
-            if sum(steps[j][1]["dst"] is not None for j in out) == 0 and all(steps[j][1]["f32"] is None for j in out):
-                return []
-            # nobody else may read the intermediate before it is written again
-            for sk in range(sj, len(steps)):
-                if steps[sk][0] != "conv":
-                    continue
-                u = steps[sk][1]
-                if not u["first"] and u["src"][0] == want[0]:
-                    return []
-                if u["dst"] is not None and u["dst"][0] == want[0]:
-                    break
-            return out
-
-        pairs = {si: pair_followers(si) for si in range(len(steps)) if steps[si][0] == "conv"}
-        pairs = {si: f for si, f in pairs.items() if f}
+        pairs = find_pairs(steps, net.tuning.get("pair", True))
         paired = {j for f in pairs.values() for j in f}
         packed_index, ci_ = {}, 0
         for si, step in enumerate(steps):

@@ -74,3 +74,32 @@ def test_package_weight_generator_matches_the_oracle_generator():
             b = O.make_flat_weights(kind, seed=3, init=init)
             assert list(a) == list(b)
             assert all(torch.equal(a[k], b[k]) for k in a)
+
+
+def test_chained_1x1_pairs_found_by_the_plan_builder():
+    """Every 1x1 layer whose only consumer is the 1x1 layer behind it runs in that layer's launch (csrc/conv_umma.cu variant
+    6): Mconv6 -> Mconv7 of every stage, conv5_4 -> conv5_5 (coco), conv6_1 -> conv6_2 (hand); body25's stage that writes its
+    Mconv7 into two buffers keeps both destinations; nothing else is paired."""
+    from isl_b200 import nets
+    want = {"coco": 12, "hand": 6, "body25": 6}
+    for kind, n_pairs in want.items():
+        steps = nets.build_program(kind).steps
+        pairs = nets.find_pairs(steps)
+        assert len(pairs) == n_pairs
+        assert nets.find_pairs(steps, enabled=False) == {}
+        for first, followers in pairs.items():
+            a = steps[first][1]
+            assert a["k"] == 1 and a["cout"] % 64 == 0 and a["f32"] is None
+            names = {steps[j][1]["layer"] for j in followers}
+            assert len(names) == 1 and 1 <= len(followers) <= 2
+            for j in followers:
+                b = steps[j][1]
+                assert b["k"] == 1 and tuple(b["src"]) == (a["dst"][0], 0, a["cout"]) and b["cout"] <= 64
+            assert a["layer"].replace("Mconv6", "Mconv7").replace("conv5_4", "conv5_5").replace("conv6_1", "conv6_2") in names
+        two = [f for f in pairs.values() if len(f) == 2]
+        assert len(two) == (1 if kind == "body25" else 0)
+        # every 1x1 layer that reads a whole temporary is inside a pair
+        paired = {j for f in pairs.values() for j in f}
+        for si, st in enumerate(steps):
+            if st[0] == "conv" and st[1]["k"] == 1 and not st[1]["first"] and st[1]["cout"] <= 64:
+                assert si in paired, st[1]["layer"]
