@@ -567,7 +567,8 @@ int launch_paf_score(const ScaleSet& paf, const LimbTable& lt, int N, int H, int
   if (mid_num != 10 || gb.cap > kMaxPeakCap) return 1;
   if (gb.end_paf == nullptr) return 1;
   paf_endpoints_kernel<<<dim3(8, lt.nlimbs * 2, N), 128, 0, st>>>(paf, lt, W, lt.njoint - 1, gb);
-  const dim3 grid(48, lt.nlimbs, N);
+  // CTAs per (limb, frame): on a single frame the pairs of a few limbs are all the work there is - spread them wider
+  const dim3 grid(N <= 2 ? 144 : (N <= 4 ? 96 : 48), lt.nlimbs, N);
   paf_score_kernel<<<grid, 256, 0, st>>>(paf, lt, H, W, lt.njoint - 1, thre2, gb);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
