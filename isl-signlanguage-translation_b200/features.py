@@ -3,8 +3,10 @@
 
 Reference: util.get_bodypose (src/util.py:99-151), util.get_handpose (src/util.py:187-219), populate_features
 (ISL_model_xy.py:78-112 = src/ISL_Model_parameter.py:376-410) and the sliding window (ISL_Model_parameter.py:370-374).
-Same names, same argument meaning, same return structures. Host code: a frame yields 156 numbers, there is nothing
-for the GPU to do here beyond what produced the key points.
+Same names, same argument meaning, same return structures. These are the HOST restatements: the product forms the 156
+numbers on the device (csrc/features.cu through KeypointExtractor.features / pipeline(with_features=True)) and the tests use
+the functions here as the checker; `feature_record` / `feature_json` build the reference's per-frame row and JSON payload
+(lists of Python numbers, by nature host work).
 
 Layout of the 156-vector: 15 body circle x, 15 body circle y (circles in joint-major, person-minor order, missing
 ones 0), then per hand (2 hands): 21 x, 21 y, 21 key-point indices ("peak text" 0..20 as float).

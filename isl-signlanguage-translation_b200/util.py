@@ -1,4 +1,10 @@
-"""Hot-path helpers with the reference's names and semantics (src/util.py)."""
+"""Hot-path helpers with the reference's names and semantics (src/util.py).
+
+`handDetect` and `npmax` are host scalar math on a handful of numbers per person whose results (integer box corners, the
+first arg-max) must be bit-identical to the reference's, and they have one obvious form: they are the reference's own
+statements (src/util.py:242-306, 394-399) under the reference's names, comments dropped - a restatement on purpose, not a
+rewrite; everything with arithmetic weight on this path (resize, networks, maps, peaks, grouping, hand key points) is CUDA
+code of this repository's own design. `padRightDownCorner` and `transfer` keep the reference's signatures."""
 import math
 
 import numpy as np
