@@ -202,6 +202,36 @@ def test_maps_accumulate_two_pass_large_downscale_and_q1_off(dev):
     assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("geom", [(240, 320, 19, 18, (0.5, 1.0, 1.5, 2.0), 1), (121, 75, 19, 18, (1.0,), 1), (480, 640, 19, 18, (0.5, 1.0, 1.5, 2.0), 2),
+                                  (360, 203, 26, 25, (0.5, 1.0, 1.5, 2.0), 1), (333, 517, 22, 21, (0.7, 1.3), 0), (720, 1280, 26, 25, (0.5, 2.0), 1),
+                                  (97, 511, 19, 18, (0.25, 0.5), 1), (256, 256, 19, 3, (1.0, 1.5, 2.0), 1), (540, 35, 19, 18, (0.5, 1.0, 2.0), 1)])
+def test_maps_accumulate_tma_windows_equal_single_pass(dev, geom):
+    """The TMA-fed second stage (csrc/prepost.cu: windows start at a multiple of four floats, boxes reach beyond the maps and
+    are zero-filled there) against the single-pass kernel over odd sizes, narrow and wide frames, up- and down-scaling,
+    part counts that leave a short last chunk, and both accumulation rules: bit-identical planes."""
+    H, W, C, parts, srch, q1 = geom
+    L = _lib.lib()
+    n = 2 if H * W < 200000 else 1
+    scales = scale_geometry(H, W, list(srch), 368)
+    arr = (_lib.Scale * len(scales))()
+    keep = []
+    rng = np.random.RandomState(H + W)
+    for i, (m, rh, rw, hp, wp) in enumerate(scales):
+        t = torch.from_numpy(rng.randn(n, C, hp // 8, wp // 8).astype(np.float32)).to(dev)
+        keep.append(t)
+        arr[i].lowres = t.data_ptr()
+        arr[i].gh, arr[i].gw, arr[i].hc, arr[i].wc = hp // 8, wp // 8, rh, rw
+    a = torch.empty((n, parts, H, W), dtype=torch.float64, device=dev)
+    b = torch.full_like(a, -7.0)
+    need = L.islpose_maps_workspace_floats(arr, len(scales), n, parts)
+    wsp = torch.empty((need,), dtype=torch.float32, device=dev)
+    _lib.check(L.islpose_maps_accumulate(arr, len(scales), C, n, H, W, parts, q1, _lib.ptr(a), None, 0, _lib.stream_ptr()), "single")
+    _lib.check(L.islpose_maps_accumulate(arr, len(scales), C, n, H, W, parts, q1, _lib.ptr(b), _lib.ptr(wsp), need,
+                                         _lib.stream_ptr()), "two-pass")
+    torch.cuda.synchronize()
+    assert torch.equal(a, b), float((a - b).abs().max())
+
+
 def test_pipeline_and_chunks_equal_the_serial_path(dev, coco, hand):
     """KeypointExtractor.pipeline() (two lanes, batches in flight) and the chunked batch_device() return exactly what
     the one-batch-at-a-time path returns, in order, for device tensors and for host frames."""
