@@ -27,6 +27,9 @@ const char* islpose_last_error(void);
 /* Number of kernels this library has launched since it was loaded (all threads); bench.py reports the difference
  * over its timed region as gpu_launches. */
 int64_t islpose_launch_count(void);
+/* sizeof of the four structs below as this library was compiled: islpose_scale, islpose_conv_desc, islpose_group_buffers,
+ * islpose_hand_crop. A binding compares them with its own layout before passing any struct. */
+int islpose_struct_sizes(int32_t out[4]);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Network plans: a recorded list of kernel launches (one per layer) over caller-owned device buffers,

@@ -72,6 +72,7 @@ SYMBOLS = {
     "islpose_abi_version": (C.c_int, []),
     "islpose_last_error": (C.c_char_p, []),
     "islpose_launch_count": (C.c_int64, []),
+    "islpose_struct_sizes": (C.c_int, [C.POINTER(C.c_int32)]),
     "islpose_pack_conv_weights": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                             C.c_void_p, C.c_void_p]),
     "islpose_plan_create": (C.c_int, [C.POINTER(C.c_void_p)]),
@@ -130,6 +131,11 @@ def lib():
         if handle.islpose_abi_version() != ABI_VERSION:
             raise IslposeError("libislpose.so has ABI version %d, expected %d (rebuild it)" % (handle.islpose_abi_version(),
                                                                                             ABI_VERSION))
+        sizes = (C.c_int32 * 4)()
+        handle.islpose_struct_sizes(sizes)
+        mine = [C.sizeof(Scale), C.sizeof(ConvDesc), C.sizeof(GroupBuffers), C.sizeof(HandCrop)]
+        if list(sizes) != mine:
+            raise IslposeError("struct layouts of libislpose.so %s and of this binding %s differ (rebuild the library)" % (list(sizes), mine))
         _lib = handle
     return _lib
 

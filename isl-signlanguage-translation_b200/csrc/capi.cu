@@ -124,6 +124,14 @@ extern "C" {
 
 int islpose_abi_version(void) { return ISLPOSE_ABI_VERSION; }
 int64_t islpose_launch_count(void) { return g_launches.load(); }
+int islpose_struct_sizes(int32_t out[4]) {
+  if (out == nullptr) return set_err("struct_sizes: null pointer");
+  out[0] = static_cast<int32_t>(sizeof(islpose_scale));
+  out[1] = static_cast<int32_t>(sizeof(islpose_conv_desc));
+  out[2] = static_cast<int32_t>(sizeof(islpose_group_buffers));
+  out[3] = static_cast<int32_t>(sizeof(islpose_hand_crop));
+  return 0;
+}
 const char* islpose_last_error(void) { return g_err; }
 
 int islpose_plan_create(islpose_plan** out) {

@@ -37,6 +37,10 @@ def test_struct_sizes_match_the_header_layout():
     assert ctypes.sizeof(_lib.ConvDesc) == 208
     assert ctypes.sizeof(_lib.GroupBuffers) % 8 == 0
     assert ctypes.sizeof(_lib.HandCrop) == 8 + 4 * 24
+    # and what the compiler made of include/islpose.h
+    sizes = (ctypes.c_int32 * 4)()
+    assert _lib.lib().islpose_struct_sizes(sizes) == 0
+    assert list(sizes) == [ctypes.sizeof(_lib.Scale), ctypes.sizeof(_lib.ConvDesc), ctypes.sizeof(_lib.GroupBuffers), ctypes.sizeof(_lib.HandCrop)]
 
 
 def test_no_cpu_fallback():
