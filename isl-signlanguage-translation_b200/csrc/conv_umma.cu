@@ -1211,7 +1211,7 @@ conv_umma_halo_swapped_kernel(const __grid_constant__ CUtensorMap tmX, const __g
 // ------------------------------------------------------------------------------------------------ v6: 1x1 -> 1x1 pair
 // Two chained 1x1 layers in one launch (Mconv6 -> Mconv7, conv5_4 -> conv5_5, conv6_1 -> conv6_2 of the reference's stages,
 // src/model.py:57-62): a 1x1 layer is bound by moving its operands, and the pair moved the 128..512-channel intermediate
-// out to L2 / HBM and back in again. Here a CTA owns one 128-pixel tile:
+// out to L2 / HBM and back in again. Here a CTA (persistent, up to three per SM) walks 128-pixel tiles; per tile:
 //   1. first layer as in v1 (TMA ring, M = 128 pixels, N = all `mid` output channels: one or two N <= 256 MMAs per K step,
 //      accumulators in `mid` TMEM columns);
 //   2. its epilogue (bias, ReLU / PReLU, bf16) writes the tile into the now idle operand ring as mid/64 blocks of
@@ -1219,11 +1219,14 @@ conv_umma_halo_swapped_kernel(const __grid_constant__ CUtensorMap tmX, const __g
 //      meanwhile the second layer's weights (64 rows, zero-filled beyond cout2) arrive behind them by TMA;
 //   3. second layer: mid/64 x 4 MMAs of N = 64 into TMEM columns 0..63 (drained in step 2), then its own epilogue: bias,
 //      activation, bf16 slice(s) and / or float32 planar output.
+// Between tiles: the next tile's operands may enter the ring only after the second layer's MMAs have read the intermediate
+// and the weights that overlay it (the producer waits for their commit), and the next first-layer MMAs overwrite TMEM
+// columns 0..63 only after the eight epilogue warps have the second accumulator in registers (bar_done).
 // The intermediate is rounded to bf16 exactly as the stored activation was, so results equal the two separate launches.
 constexpr uint32_t kPairW2Block = 64 * 128;   // 64 weight rows x 64 channels
 constexpr uint32_t kPairCtrlBytes = 256 + 2 * 512 * 4 + 2 * 64 * 4;  // barriers, bias / slope of layer 1 (<= 512), of layer 2
 
-__global__ void __launch_bounds__(kThreadsV1, 1)
+__global__ void __launch_bounds__(kThreadsV1, 3)
 conv_umma_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmB2, const ConvArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -1244,6 +1247,7 @@ conv_umma_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   const uint32_t bar_mid = ctrl + 144;     // intermediate written by the eight epilogue warps
   const uint32_t bar_w2 = ctrl + 152;      // second layer's weights landed
   const uint32_t bar_accum2 = ctrl + 160;  // second layer's accumulator complete
+  const uint32_t bar_done = ctrl + 168;    // the eight epilogue warps have drained the second accumulator
   volatile uint32_t* const tmem_slot_g = reinterpret_cast<volatile uint32_t*>(gctrl + 136);
   float* const s_bias = reinterpret_cast<float*>(gctrl + 256);
   float* const s_slope = s_bias + 512;
@@ -1252,12 +1256,7 @@ conv_umma_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int t = blockIdx.x;
-  const int tx = t % a.tiles_x;
-  const int ty = (t / a.tiles_x) % a.tiles_y;
-  const int img = t / (a.tiles_x * a.tiles_y);
-  const int x0 = tx * a.bw;
-  const int y0 = ty * a.bh;
+  const int tiles_per_img = a.tiles_x * a.tiles_y;
   const int cblocks = (a.cin_k16 + 3) >> 2;
   const int mid = a.mid_blocks * 64;
 
@@ -1270,6 +1269,7 @@ conv_umma_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     ptx::mbar_init(bar_mid, 8);  // one arrival per epilogue warp
     ptx::mbar_init(bar_w2, 1);
     ptx::mbar_init(bar_accum2, 1);
+    ptx::mbar_init(bar_done, 8);
     ptx::mbar_fence_init();
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
@@ -1301,6 +1301,12 @@ conv_umma_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const uint32_t tx_bytes = 128u * a.bw * a.bh + 128u * static_cast<uint32_t>(mid);
     ptx::RingPos r(bar_full, bar_empty, a.stages);
     uint32_t sa = sA0, sb = sB0;
+    uint32_t ph = 0;
+    for (int t = blockIdx.x; t < a.m_tiles; t += gridDim.x, ph ^= 1) {
+    const int img = t / tiles_per_img;
+    const int rr = t - img * tiles_per_img;
+    const int ty = rr / a.tiles_x;
+    const int x0 = (rr - ty * a.tiles_x) * a.bw, y0 = ty * a.bh;
     for (int cb = 0; cb < cblocks; ++cb) {
       ptx::mbar_wait(r.empty, r.ph ^ 1);
       if (ptx::elect_one()) {
@@ -1319,12 +1325,16 @@ conv_umma_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
     // the ring is idle once every MMA of the first layer has retired: the second layer's weights go behind the
     // intermediate blocks (they may overlap ring slots)
-    ptx::mbar_wait(bar_accum, 0);
+    ptx::mbar_wait(bar_accum, ph);
     if (ptx::elect_one()) {
       ptx::mbar_arrive_expect_tx(bar_w2, static_cast<uint32_t>(a.mid_blocks) * kPairW2Block);
       for (int b = 0; b < a.mid_blocks; ++b) ptx::tma_load_3d(sW2 + b * kPairW2Block, &tmB2, bar_w2, b * 64, 0, 0);
     }
     __syncwarp();
+    // the next tile's operands go into ring slots the intermediate and these weights occupy: not before the second
+    // layer's MMAs have read them
+    ptx::mbar_wait(bar_accum2, ph);
+    }  // tile loop
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     {
@@ -1335,6 +1345,13 @@ conv_umma_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const uint32_t part_step = (static_cast<uint32_t>(a.n1_mma) * 128u) >> 4;
       uint64_t da = da0, db = db0;
       ptx::RingPos r(bar_full, bar_empty, a.stages);
+      const uint32_t idesc2 = ptx::umma_idesc_bf16(128, 64);
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < a.m_tiles; t += gridDim.x, ph ^= 1) {
+      if (t != static_cast<int>(blockIdx.x)) {  // the previous tile's second accumulator (columns 0..63) has been read
+        ptx::mbar_wait(bar_done, ph ^ 1);
+        ptx::tc_fence_after();
+      }
       for (int cb = 0; cb < cblocks; ++cb) {
         ptx::mbar_wait(r.full, r.ph);
         ptx::tc_fence_after();
@@ -1354,13 +1371,11 @@ conv_umma_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       }
       if (ptx::elect_one()) ptx::umma_commit(bar_accum);
       __syncwarp();
-    }
     // second layer: A = the intermediate blocks, B = its weight blocks, D = TMEM columns 0..63
-    ptx::mbar_wait(bar_mid, 0);
-    ptx::mbar_wait(bar_w2, 0);
+    ptx::mbar_wait(bar_mid, ph);
+    ptx::mbar_wait(bar_w2, ph);
     ptx::tc_fence_after();
     if (ptx::elect_one()) {
-      const uint32_t idesc2 = ptx::umma_idesc_bf16(128, 64);
       uint64_t di = ptx::umma_desc_sw128(sI0), dw = ptx::umma_desc_sw128(sW2);
       for (int b = 0; b < a.mid_blocks; ++b) {
         issue_kblock4(tmem_base, di, dw, idesc2, b != 0);
@@ -1370,6 +1385,8 @@ conv_umma_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       ptx::umma_commit(bar_accum2);
     }
     __syncwarp();
+      }  // tile loop
+    }
   } else {
     // ------------------------------------------------------------ epilogues
     const int q = warp & 3;
@@ -1377,13 +1394,18 @@ conv_umma_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int row = q * 32 + lane;
     const int py = row / a.bw;
     const int px = row - py * a.bw;
-    const int x = x0 + px;
-    const int y = y0 + py;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    uint32_t ph = 0;
+    for (int t = blockIdx.x; t < a.m_tiles; t += gridDim.x, ph ^= 1) {
+    const int img = t / tiles_per_img;
+    const int rr = t - img * tiles_per_img;
+    const int ty = rr / a.tiles_x;
+    const int x = (rr - ty * a.tiles_x) * a.bw + px;
+    const int y = ty * a.bh + py;
     const bool valid = (row < a.bw * a.bh) && (x < a.W) && (y < a.H);
     const long long pix = (static_cast<long long>(img) * a.H + y) * a.W + x;
-    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
 
-    ptx::mbar_wait(bar_accum, 0);
+    ptx::mbar_wait(bar_accum, ph);
     ptx::tc_fence_after();
     for (int c = half * 32; c < mid; c += 64) {
       uint32_t r[32];
@@ -1413,13 +1435,16 @@ conv_umma_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     __syncwarp();
     if (lane == 0) ptx::mbar_arrive(bar_mid);
 
-    ptx::mbar_wait(bar_accum2, 0);
+    ptx::mbar_wait(bar_accum2, ph);
     ptx::tc_fence_after();
     {
       const int c = half * 32;
       uint32_t r[32];
       ptx::tmem_ld_32x32(lane_base + c, r);
       ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar_done);  // the accumulator is in registers: the next tile may overwrite it
       float v[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
@@ -1459,6 +1484,7 @@ conv_umma_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         }
       }
     }
+    }  // tile loop
   }
 
   ptx::tc_fence_before();
@@ -1773,7 +1799,18 @@ int conv_prepare(const ConvDesc& d, ConvLaunch* out, char* err, int errlen) {
         return fail(err, errlen, "conv: pair: second weight tensor map rejected");
     }
     out->variant = 6;
-    out->grid = dim3(static_cast<unsigned>(m_tiles), 1, 1);
+    {
+      // persistent: as many CTAs as fit side by side (shared memory, TMEM columns, 320 threads x 63 registers: at most 3),
+      // each walking its share of the tiles - barriers, TMEM and biases are set up once per CTA instead of once per 128
+      // pixels. Measured against one tile per CTA (launch by launch, tools/gpu_call24.sh): coco Mconv6+7 291 -> 254 us per
+      // 10, conv5_4+5 229 -> 179 us per 2, body25 Mconv6+7 1065 -> 889 us per 6, hand Mconv6+7 206 -> 177 us per 5.
+      int per_sm = static_cast<int>(lim.smem_optin / (out->smem_bytes + 1024u));
+      if (per_sm * a.tmem_cols > 512) per_sm = 512 / a.tmem_cols;
+      if (per_sm > 3) per_sm = 3;
+      if (per_sm < 1) per_sm = 1;
+      const long long slots = static_cast<long long>(nsm) * per_sm;
+      out->grid = dim3(static_cast<unsigned>(m_tiles < slots ? m_tiles : slots), 1, 1);
+    }
     const double px = static_cast<double>(d.H) * d.W * d.N;
     out->flops = 2.0 * d.in_c * d.cout * px + 2.0 * d.cout * d.cout2 * px;
     static bool attr6_dev[64] = {};
