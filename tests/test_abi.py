@@ -51,6 +51,9 @@ def test_no_cpu_fallback():
         isl_b200.Body({}, "coco")
     with pytest.raises(_lib.IslposeError):
         isl_b200.Hand({})
+    from isl_b200 import translate as TR
+    with pytest.raises(_lib.IslposeError):
+        TR.Translator(TR.random_weights(7))
 
 
 def test_argument_validation_without_gpu():
@@ -58,6 +61,11 @@ def test_argument_validation_without_gpu():
     assert L.islpose_resize_pad_normalize(None, 1, 8, 8, 1.0, 8, 8, 8, 8, None, None, None) != 0
     assert b"null" in L.islpose_last_error()
     assert L.islpose_plan_add_conv(None, None) != 0
+    # the classifier's entry point validates before it launches anything
+    assert L.islpose_translate(None, 1, 20, 156, None, 0, 167, None, None) != 0 and b"bad argument" in L.islpose_last_error()
+    assert L.islpose_translate(None, 0, 20, 156, None, 0, 167, None, None) == 0          # nothing to do
+    assert L.islpose_translate_weight_floats(167) == 4 * 156 + 2 * (156 * 128 + 32 * 128 + 128) + 2 * (64 * 128 + 32 * 128 + 128) \
+        + 64 * 32 + 4 * 32 + 32 * 32 + 4 * 32 + 32 * 167 + 167
 
 
 def test_host_helpers_match_oracle():
